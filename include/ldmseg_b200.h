@@ -1,0 +1,213 @@
+/*
+ * ldmseg_b200.h -- C ABI of the B200-native LDMSeg sampler hot path (libldmseg_b200.so).
+ *
+ * The reference (weentiaan/Video-latent-diffusion-panoptic-segmentation) is pure Python and has no FFI; its
+ * seam for this path is four Python call signatures.  The Python mirror classes under
+ * video_latent_diffusion_panoptic_segmentation_b200/ldmseg/ keep those signatures and bind the entry points
+ * below through ctypes.  Each entry point cites the reference code whose arithmetic it replaces.
+ *
+ * Conventions (all entry points):
+ *   - raw device pointers + explicit shapes in POD structs; the CALLER owns all memory (no allocation inside);
+ *   - asynchronous on the given CUDA stream, no device synchronisation, no global mutable state;
+ *   - return 0 on success, negative ldm_status on error; ldm_last_error() returns a thread-local message;
+ *   - activations are NHWC ("channels last"): [B, H, W, C]; bf16 = __nv_bfloat16 bit pattern; f32 = IEEE float;
+ *   - built only for sm_100a: ldm_check_device() refuses any other device.
+ */
+#ifndef LDMSEG_B200_H_
+#define LDMSEG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* ldm_stream_t; /* cudaStream_t */
+
+enum ldm_status {
+  LDM_OK = 0,
+  LDM_ERR_BAD_ARG = -1,
+  LDM_ERR_BAD_SHAPE = -2,
+  LDM_ERR_ALIGNMENT = -3,
+  LDM_ERR_ARCH = -4,
+  LDM_ERR_CUDA = -5,
+  LDM_ERR_DRIVER = -6
+};
+
+int ldm_abi_version(void);
+const char* ldm_last_error(void);
+/* 0 when the current device is compute capability 10.0 (B200); LDM_ERR_ARCH otherwise. */
+int ldm_check_device(void);
+/* number of kernels this library has launched in the calling process (bench.py "gpu_launches"). */
+long long ldm_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Tensor-core contraction: plain GEMM (Linear / conv1x1) and implicit-GEMM conv3x3 (stride 1, pad 1).
+ * Replaces: diffusers Conv2d/Linear inside ResnetBlock2D / Transformer2DModel / BasicTransformerBlock
+ * (call sites ldmseg/models/unet.py:357-431) and the seg-AE decoder convs
+ * (ldmseg/models/vae.py:134-173).
+ *   out[b,y,x,n] = epilogue( sum_{tap,c} A[b, y+dy(tap), x+dx(tap), c] * W[n, tap*(c1+c2) + c] )
+ * A is the channel concatenation of source a1 (c1 channels) and optional a2 (c2 channels); c1, c2 % 64 == 0
+ * for taps == 9 (any multiple of 8 for taps == 1 with a2 == NULL).
+ * ---------------------------------------------------------------------------------------------------------- */
+enum ldm_gemm_flags {
+  LDM_GEMM_OUT_F32 = 1 << 0,   /* out is f32 [rows, N] (default bf16)                                         */
+  LDM_GEMM_GEGLU = 1 << 1,     /* weights/bias pre-interleaved in blocks of 16 (value | gate);                 */
+                               /* out[rows, N/2] = value * gelu_erf(gate)   (diffusers GEGLU)                  */
+  LDM_GEMM_QKV_SPLIT = 1 << 2, /* N = 3*heads*head_dim; scatter to q/k [B*heads, seq, dpad], vt [B*heads, d, seq_pad] */
+  LDM_GEMM_SILU = 1 << 3,      /* out = silu(acc + bias ...)                                                   */
+  LDM_GEMM_CONVT_LN_SILU = 1 << 4 /* N = 4*Cout: ConvTranspose2d(k2,s2) pixel-shuffle + LayerNorm2d + SiLU
+                                     (vae.py:156-158,310-323); block_n must equal Cout (<= 256)               */
+};
+
+typedef struct ldm_gemm_desc {
+  const void* a1;       /* bf16 NHWC [B,H,W,c1]                                                  */
+  const void* a2;       /* bf16 NHWC [B,H,W,c2] or NULL                                          */
+  const void* w;        /* bf16 [N, taps*(c1+c2)] (tap-major, channel-minor)                     */
+  const float* bias;    /* f32 [N] or NULL                                                       */
+  const float* rowbias; /* f32 [B, N] or NULL: per-image bias (time-embedding projection)         */
+  const void* residual; /* bf16 [B*H*W, N] or NULL, added after bias                             */
+  void* out;            /* bf16/f32 [B*H*W, N] (GEGLU: N/2 columns; CONVT: bf16 [B,2H,2W,N/4])   */
+  void* q;              /* QKV_SPLIT outputs                                                     */
+  void* k;
+  void* vt;
+  const float* ln_gamma; /* CONVT_LN_SILU: LayerNorm2d weight/bias f32 [Cout], eps                */
+  const float* ln_beta;
+  float ln_eps;
+  int32_t B, H, W;      /* output (= input) spatial extents; a plain GEMM uses B=1,H=1,W=rows    */
+  int32_t c1, c2;
+  int32_t N;
+  int32_t taps;         /* 1 or 9                                                                */
+  int32_t block_n;      /* 0 = choose; else multiple of 32 in [32,256]                           */
+  int32_t flags;
+  int32_t heads, head_dim, dpad, seq, seq_pad; /* QKV_SPLIT geometry (seq = tokens per image)    */
+} ldm_gemm_desc;
+
+int ldm_gemm_bf16(const ldm_gemm_desc* d, ldm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Fused flash-style self-attention, softmax(Q K^T * scale) V, per (image, head).
+ * Replaces: diffusers Attention / AttnProcessor2_0 (F.scaled_dot_product_attention) in BasicTransformerBlock.attn1
+ * (cross-attention removed by ldmseg/models/unet.py:83-105).
+ *   q, k : bf16 [B*heads, seq, dpad]   (dpad = 64*ceil(d/64), columns >= d are zero)
+ *   vt   : bf16 [B*heads, d, seq_pad]  (V transposed; seq_pad % 8 == 0)
+ *   out  : bf16 [B*seq, heads*d]
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct ldm_attn_desc {
+  const void* q;
+  const void* k;
+  const void* vt;
+  void* out;
+  int32_t B, heads, seq, head_dim, dpad, seq_pad;
+  float scale; /* head_dim^-0.5 */
+} ldm_attn_desc;
+
+int ldm_flash_attn_fwd(const ldm_attn_desc* d, ldm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * GroupNorm (+ optional SiLU) over the channel concatenation of x1 (c1) and x2 (c2), NHWC bf16.
+ * Replaces: torch.nn.GroupNorm + SiLU in ResnetBlock2D.norm1/norm2, Transformer2DModel.norm,
+ * UNet.conv_norm_out (unet.py:428-430), seg-AE decoder GroupNorm (vae.py:163-164).
+ * stats: caller-provided scratch, f64 [B, groups, 2], zeroed by the call.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct ldm_groupnorm_desc {
+  const void* x1;
+  const void* x2; /* or NULL */
+  const float* gamma;
+  const float* beta;
+  void* out;     /* bf16 [B, HW, c1+c2] */
+  double* stats; /* [B, groups, 2] */
+  int32_t B, HW, c1, c2, groups;
+  float eps;
+  int32_t silu;
+} ldm_groupnorm_desc;
+
+int ldm_groupnorm_silu(const ldm_groupnorm_desc* d, ldm_stream_t stream);
+
+/* LayerNorm over the last dim of bf16 [rows, C] (BasicTransformerBlock.norm1 / norm3). */
+int ldm_layernorm(const void* x, const float* gamma, const float* beta, void* out, int32_t rows, int32_t C,
+                  float eps, ldm_stream_t stream);
+
+/* Timestep embedding pieces (unet.py:301-307 + diffusers Timesteps / TimestepEmbedding; the timestep is one
+ * 0-dim tensor expanded over the batch, unet.py:302-303, so the embedding is a single vector).
+ *   ldm_timestep_sinusoid: out[0:half] = cos(t*freqs), out[half:2*half] = sin(t*freqs)  (flip_sin_to_cos, shift 0),
+ *   t = timesteps[*t_index] (int64 device array; t_index on device so a captured CUDA graph replays every step).
+ *   ldm_gemv_bf16: out[n] = act(bias[n] + bias2[n] + sum_k w[n,k]*x[k]); w bf16 [N,K]; x,out f32; act = SiLU if
+ *   silu_out. Used for linear_1 (+SiLU), linear_2 (+SiLU, the resnets' nonlinearity(temb)) and for ALL
+ *   time_emb_proj layers in one launch (bias2 = the conv1 biases, so the result is conv1's epilogue bias). */
+int ldm_timestep_sinusoid(const int64_t* timesteps, const int32_t* t_index, const float* freqs, float* out,
+                          int32_t half, ldm_stream_t stream);
+int ldm_gemv_bf16(const void* w, const float* bias, const float* bias2, const float* x, float* out, int32_t N,
+                  int32_t K, int32_t silu_out, ldm_stream_t stream);
+
+/* 3x3 conv (pad 1) with few input channels, fused with the latent concat + cast + scale:
+ *   conv_in of the UNet: cat([x_t, rgb_latents(, condition)], 1) (trainers_ldm_cond.py:1131-1141) -> unet.py:357
+ *   seg-AE decoder[0]  : z * (1/scaling_factor) (trainers_ldm_cond.py:423) -> vae.py:134
+ * s0..s2: f32 NCHW [B,cps,h,w] sources (nsrc of them), scaled by `scale`; w f32 [cout, nsrc*cps, 3, 3]
+ * (reference layout); out bf16 NHWC [B,h,w,cout]. */
+int ldm_conv3x3_small_cin(const float* s0, const float* s1, const float* s2, int32_t nsrc, int32_t cps, float scale,
+                          const float* w, const float* bias, void* out, int32_t B, int32_t h, int32_t wd,
+                          int32_t cout, ldm_stream_t stream);
+
+/* conv_out: bf16 NHWC [B,h,w,Cin] (already GroupNorm+SiLU'ed) -> conv3x3 -> f32 NCHW [B,Cout,h,w] (Cout <= 8).
+ * w f32 [Cout,Cin,3,3] (unet.py:431). */
+int ldm_conv_out(const void* x, const float* w, const float* bias, float* out, int32_t B, int32_t h, int32_t wd,
+                 int32_t cin, int32_t cout, ldm_stream_t stream);
+
+/* DDIM update (ddim_scheduler.py:218-269, epsilon prediction, no clipping), fp32, bit-exact with the reference's
+ * op order:  x0 = (x - sqrt(1-a_t)*eps) / sqrt(a_t);  prev = sqrt(a_prev)*x0 + sqrt(1-a_prev)*eps.
+ * coef: device f32 [T,4] = {sqrt(1-a_t), sqrt(a_t), sqrt(a_prev), sqrt(1-a_prev)} rows selected by *t_index.
+ * prev_sample / pred_x0 may be NULL.  */
+int ldm_ddim_step(const float* eps, const float* sample, const float* coef, const int32_t* t_index,
+                  float* prev_sample, float* pred_x0, int64_t n, ldm_stream_t stream);
+
+/* Layout helpers (NHWC bf16). */
+int ldm_upsample_nearest(const void* x, void* out, int32_t B, int32_t h, int32_t w, int32_t C, int32_t oh,
+                         int32_t ow, ldm_stream_t stream); /* F.interpolate(mode="nearest") */
+int ldm_im2col3x3_s2(const void* x, void* out, int32_t B, int32_t h, int32_t w, int32_t C, int32_t oh, int32_t ow,
+                     ldm_stream_t stream); /* Downsample2D conv (stride 2, pad 1) -> [B*oh*ow, 9*C] */
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Integer tail.
+ * ---------------------------------------------------------------------------------------------------------- */
+/* argmax + softmax-max threshold (trainers_ldm_cond.py:1287-1295) on NHWC f32 logits [B,h,w,C] upsampled
+ * bilinearly (align_corners=False) by `up` (1 or 2) on the fly (vae.py:271 / trainers_ldm_cond.py:1264-1269).
+ * ids: int32 [B, up*h, up*w] (argmax, or ignore_label where max softmax prob < mask_th)
+ * Also accumulates, per image, count[c] = #pixels with id == c and over[c] = #pixels with sigmoid(logit_c) >= mask_th
+ * (the two sums of the merge, :1307-1315).  counts: int32 [B, 2, C], zeroed by the call. */
+int ldm_logits_to_ids(const float* logits, int32_t* ids, int32_t* counts, int32_t B, int32_t h, int32_t w,
+                      int32_t C, int32_t up, float mask_th, int32_t ignore_label, ldm_stream_t stream);
+/* Materialising variant of the bilinear x`up` resize: NHWC f32 [B,h,w,C] -> NCHW f32 [B,C,up*h,up*w]. */
+int ldm_bilinear_up_nchw(const float* logits, float* out, int32_t B, int32_t h, int32_t w, int32_t C, int32_t up,
+                         ldm_stream_t stream);
+/* Panoptic merge (trainers_ldm_cond.py:1303-1325): for every class c, keep[c] = count[c] >= count_th and
+ * c != ignore_label and not (count[c] / over[c] < overlap_th) (float64 ratio as numpy computes it); then
+ * cleaned[i] = keep[ids[i]] ? ids[i] : -1.  counts is the [B,2,C] array written by ldm_logits_to_ids. */
+int ldm_segment_filter(const int32_t* ids, const int32_t* counts, int32_t* cleaned, int32_t B, int64_t hw,
+                       int32_t C, int32_t count_th, double overlap_th, int32_t ignore_label, ldm_stream_t stream);
+/* decode_bitmap (ldmseg/data/cityscapes.py:263-270, kitti.py:299-306; coco.py:385-391 has no ==31 line):
+ * x f32 [B,n,H,W] -> int32 [B,H,W], id = sum_i (x_i > 0) << i; id == 31 -> 0 when quirk31. n <= 24. */
+int ldm_decode_bitmap(const float* x, int32_t* ids, int32_t B, int32_t nbits, int64_t hw, int32_t quirk31,
+                      ldm_stream_t stream);
+/* encode_bitmap (cityscapes.py:256-261): ids int32 [B,H,W] -> f32 [B,n,H,W]; pixels == ignore_label -> fill. */
+int ldm_encode_bitmap(const int32_t* ids, float* x, int32_t B, int32_t nbits, int64_t hw, int32_t ignore_label,
+                      float fill, ldm_stream_t stream);
+/* 4-connected component labelling with scipy.ndimage.label numbering (components numbered in raster order of
+ * their first pixel) of the binary mask (sem == target), per image: labels int32 [B,H,W] (0 = background),
+ * ncomp int32 [B]. scratch: ldm_ccl_scratch_bytes(B,H,W) bytes. (cityscapes_pap_eval.py:76-84,96-101) */
+size_t ldm_ccl_scratch_bytes(int32_t B, int32_t H, int32_t W);
+int ldm_ccl_label4(const int32_t* sem, int32_t target, int32_t* labels, int32_t* ncomp, int32_t* scratch, int32_t B,
+                   int32_t H, int32_t W, ldm_stream_t stream);
+/* Joint histogram of id pairs (a[i], b[i]) -- the np.unique(gt*offset + pred, return_counts=True) of vpq_eval
+ * (eval/eval_dvpq.py:39-49) and the mask intersections of CityscapesPanopticEvaluator.add_image
+ * (cityscapes_pap_eval.py:113-146) -- as an open-addressing hash table in caller memory:
+ * keys[slot] = ((uint64)(uint32)a << 32) | (uint32)b, or 0x8000000000000000 when empty; counts[slot] = pixels.
+ * capacity: power of two >= 64; *overflow is set to 1 if the table filled up. The call clears the table first. */
+int ldm_joint_hist(const int32_t* a, const int32_t* b, int64_t n, unsigned long long* keys, int32_t* counts,
+                   int32_t capacity, int32_t* overflow, ldm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LDMSEG_B200_H_ */

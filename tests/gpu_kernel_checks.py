@@ -1,0 +1,461 @@
+"""Per-kernel parity checks (GPU). Each ``check_*`` returns a dict with error statistics and raises AssertionError
+on failure. The checker is plain PyTorch fp32 math (or numpy/scipy for the integer tail) on the same seeded inputs;
+the thing under test always goes through the C ABI (ops.py -> libldmseg_b200.so).
+
+Used by tests/test_kernels_gpu.py (pytest -m gpu) and by tools/gpu_diag.py (one subprocess per check, so a trapped
+kernel cannot take the other checks down with it).
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from video_latent_diffusion_panoptic_segmentation_b200 import _lib as L
+from video_latent_diffusion_panoptic_segmentation_b200 import ops
+
+DEV = "cuda"
+bf16 = torch.bfloat16
+
+
+def _gen(seed):
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    return g
+
+
+def _randn(shape, seed, scale=1.0, dtype=torch.float32):
+    return (torch.randn(shape, generator=_gen(seed)) * scale).to(dtype).to(DEV)
+
+
+def _stats(got, ref, name, atol, rtol):
+    got = got.float()
+    ref = ref.float()
+    err = (got - ref).abs()
+    denom = ref.abs().max().item() + 1e-12
+    res = {
+        "name": name,
+        "max_abs": err.max().item(),
+        "ref_max": denom,
+        "rel_l2": (err.pow(2).sum().sqrt() / (ref.pow(2).sum().sqrt() + 1e-12)).item(),
+        "nan": bool(torch.isnan(got).any().item()),
+    }
+    bad = err > (atol + rtol * ref.abs())
+    res["n_bad"] = int(bad.sum().item())
+    res["n"] = got.numel()
+    if res["n_bad"] or res["nan"]:
+        idx = bad.nonzero()[:8].tolist()
+        res["first_bad"] = idx
+        raise AssertionError(f"{name}: {res}")
+    return res
+
+
+# ----------------------------------------------------------------------------------------------------------- DDIM
+def check_ddim():
+    n = 8 * 4 * 48 * 156
+    eps, x = _randn((n,), 1), _randn((n,), 2)
+    a_t, a_p = torch.tensor(0.0047), torch.tensor(0.0060)
+    coef = torch.stack([(1 - a_t) ** 0.5, a_t ** 0.5, a_p ** 0.5, (1 - a_p) ** 0.5]).float().view(1, 4).to(DEV)
+    ti = torch.zeros(1, dtype=torch.int32, device=DEV)
+    prev, x0 = torch.empty_like(x), torch.empty_like(x)
+    ops.ddim_step(eps, x, coef, ti, prev, x0)
+    c = coef[0].cpu()
+    xc, ec = x.cpu(), eps.cpu()
+    x0_ref = (xc - c[0] * ec) / c[1]
+    prev_ref = c[2] * x0_ref + c[3] * ec
+    assert torch.equal(x0.cpu(), x0_ref), "ddim pred_x0 not bit-exact"
+    assert torch.equal(prev.cpu(), prev_ref), "ddim prev_sample not bit-exact"
+    return {"name": "ddim", "bit_exact": True}
+
+
+# ----------------------------------------------------------------------------------------------------------- norms
+def check_layernorm(C=640, rows=1000):
+    x = _randn((rows, C), 3, dtype=bf16)
+    g, b = _randn((C,), 4) * 0.2 + 1, _randn((C,), 5) * 0.1
+    out = torch.empty_like(x)
+    ops.layernorm(x, g, b, out, 1e-5)
+    ref = F.layer_norm(x.float(), (C,), g, b, 1e-5)
+    return _stats(out, ref, f"layernorm C={C}", 2e-2, 1e-2)
+
+
+def check_groupnorm(c1=320, c2=0, HW=468, B=2, silu=True, eps=1e-5):
+    x1 = _randn((B, HW, c1), 6, dtype=bf16) * 1.5 + 0.3
+    x2 = (_randn((B, HW, c2), 7, dtype=bf16) * 0.7 - 0.2) if c2 else None
+    C = c1 + c2
+    g, b = _randn((C,), 8) * 0.2 + 1, _randn((C,), 9) * 0.1
+    out = torch.empty((B, HW, C), dtype=bf16, device=DEV)
+    stats = torch.empty(B * 32 * 2, dtype=torch.float64, device=DEV)
+    ops.groupnorm(x1, g, b, out, stats, x2=x2, groups=32, eps=eps, silu=silu)
+    xin = x1 if x2 is None else torch.cat([x1, x2], dim=-1)
+    ref = F.group_norm(xin.float().permute(0, 2, 1), 32, g, b, eps)
+    if silu:
+        ref = F.silu(ref)
+    ref = ref.permute(0, 2, 1)
+    return _stats(out, ref, f"groupnorm c1={c1} c2={c2} HW={HW}", 3e-2, 2e-2)
+
+
+# ----------------------------------------------------------------------------------------------------------- small ops
+def check_gemv():
+    N, K = 1000, 1280
+    w = _randn((N, K), 10, 0.05, bf16)
+    x = _randn((K,), 11)
+    b1, b2 = _randn((N,), 12), _randn((N,), 13)
+    out = torch.empty(N, device=DEV)
+    ops.gemv(w, x, out, b1, b2, silu=True)
+    ref = F.silu(w.float() @ x + b1 + b2)
+    return _stats(out, ref, "gemv", 1e-3, 1e-3)
+
+
+def check_timestep_sinusoid():
+    half = 160
+    exponent = -math.log(10000) * torch.arange(0, half, dtype=torch.float32) / half
+    freqs = torch.exp(exponent)
+    ts = torch.tensor([999, 979, 19], dtype=torch.int64, device=DEV)
+    res = None
+    for i in range(3):
+        ti = torch.tensor([i], dtype=torch.int32, device=DEV)
+        out = torch.empty(2 * half, device=DEV)
+        ops.timestep_sinusoid(ts, ti, freqs.to(DEV), out)
+        emb = ts[i].float().cpu() * freqs
+        ref = torch.cat([torch.cos(emb), torch.sin(emb)])
+        res = _stats(out, ref.to(DEV), f"timestep_sinusoid t={int(ts[i])}", 2e-5, 0)
+    return res
+
+
+def check_conv_small_cin():
+    B, h, w, cout = 2, 12, 39, 320
+    xt, rgb = _randn((B, 4, h, w), 14), _randn((B, 4, h, w), 15)
+    wt, bias = _randn((cout, 8, 3, 3), 16, 0.1), _randn((cout,), 17)
+    out = torch.empty((B, h, w, cout), dtype=bf16, device=DEV)
+    ops.conv3x3_small_cin([xt, rgb], wt, bias, out, scale=1.0)
+    ref = F.conv2d(torch.cat([xt, rgb], 1), wt, bias, padding=1).permute(0, 2, 3, 1)
+    r = _stats(out, ref, "conv3x3_small_cin(8->320)", 2e-2, 1e-2)
+    z = _randn((B, 4, h, w), 18)
+    w2, b2 = _randn((256, 4, 3, 3), 19, 0.1), _randn((256,), 20)
+    out2 = torch.empty((B, h, w, 256), dtype=bf16, device=DEV)
+    ops.conv3x3_small_cin([z], w2, b2, out2, scale=5.0)
+    ref2 = F.conv2d(z * 5.0, w2, b2, padding=1).permute(0, 2, 3, 1)
+    _stats(out2, ref2, "conv3x3_small_cin(4->256, scale)", 4e-2, 1e-2)
+    return r
+
+
+def check_conv_out():
+    B, h, w, cin = 2, 12, 39, 320
+    x = _randn((B, h, w, cin), 21, dtype=bf16)
+    wt, bias = _randn((4, cin, 3, 3), 22, 0.05), _randn((4,), 23)
+    out = torch.empty((B, 4, h, w), device=DEV)
+    ops.conv_out(x, wt, bias, out)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt, bias, padding=1)
+    return _stats(out, ref, "conv_out", 2e-3, 1e-3)
+
+
+def check_upsample_im2col():
+    B, h, w, C = 2, 6, 20, 64
+    x = _randn((B, h, w, C), 24, dtype=bf16)
+    out = torch.empty((B, 12, 39, C), dtype=bf16, device=DEV)
+    ops.upsample_nearest(x, out)
+    ref = F.interpolate(x.float().permute(0, 3, 1, 2), size=(12, 39), mode="nearest").permute(0, 2, 3, 1)
+    assert torch.equal(out.float(), ref), "upsample_nearest (size) mismatch"
+    out2 = torch.empty((B, 12, 40, C), dtype=bf16, device=DEV)
+    ops.upsample_nearest(x, out2)
+    ref2 = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1)
+    assert torch.equal(out2.float(), ref2), "upsample_nearest (x2) mismatch"
+    x3 = _randn((B, 12, 39, C), 25, dtype=bf16)
+    oh, ow = 6, 20
+    col = torch.empty((B * oh * ow, 9 * C), dtype=bf16, device=DEV)
+    ops.im2col3x3_s2(x3, col)
+    unf = F.unfold(x3.float().permute(0, 3, 1, 2), 3, padding=1, stride=2)  # [B, C*9, L] (c-major, tap-minor)
+    unf = unf.view(B, C, 9, oh * ow).permute(0, 3, 2, 1).reshape(B * oh * ow, 9 * C)
+    assert torch.equal(col.float(), unf), "im2col3x3_s2 mismatch"
+    return {"name": "upsample/im2col", "bit_exact": True}
+
+
+# ----------------------------------------------------------------------------------------------------------- GEMM
+def _gemm_ref(a, w, bias=None, residual=None):
+    ref = a.float() @ w.float().t()
+    if bias is not None:
+        ref = ref + bias
+    if residual is not None:
+        ref = ref + residual.float()
+    return ref
+
+
+def check_gemm_tiny():
+    """Smallest possible tcgen05 tile: one k-block, one tile. Prints structure of the error if any."""
+    M, N, K = 128, 32, 64
+    a = _randn((M, K), 30, 1.0, bf16)
+    w = _randn((N, K), 31, 1.0, bf16)
+    out = torch.empty((M, N), dtype=torch.float32, device=DEV)
+    ops.gemm(a, w, out, flags=L.LDM_GEMM_OUT_F32, block_n=32)
+    torch.cuda.synchronize()
+    ref = _gemm_ref(a, w)
+    err = (out - ref).abs()
+    info = {"name": "gemm_tiny", "max_abs": err.max().item(),
+            "rows_bad": int((err.max(dim=1).values > 1e-2).sum()), "cols_bad": int((err.max(dim=0).values > 1e-2).sum())}
+    if info["max_abs"] > 1e-2:
+        # structural hints for descriptor bugs
+        info["out[0,:4]"] = out[0, :4].tolist()
+        info["ref[0,:4]"] = ref[0, :4].tolist()
+        info["out[1,:4]"] = out[1, :4].tolist()
+        info["ref[1,:4]"] = ref[1, :4].tolist()
+        # is it the k=0..15 partial product only?
+        for kk in (16, 32, 48):
+            part = a[:, :kk].float() @ w[:, :kk].float().t()
+            info[f"matches_first_{kk}_k"] = bool((out - part).abs().max().item() < 1e-2)
+        raise AssertionError(str(info))
+    return info
+
+
+def check_gemm_plain(M=1000, N=320, K=320, block_n=0, bias=True, residual=True, f32out=False):
+    a = _randn((M, K), 32, 1.0, bf16)
+    w = _randn((N, K), 33, 0.05, bf16)
+    b = _randn((N,), 34) if bias else None
+    r = _randn((M, N), 35, 1.0, bf16) if residual else None
+    out = torch.empty((M, N), dtype=torch.float32 if f32out else bf16, device=DEV)
+    ops.gemm(a, w, out, bias=b, residual=r, flags=L.LDM_GEMM_OUT_F32 if f32out else 0, block_n=block_n)
+    ref = _gemm_ref(a, w, b, r)
+    return _stats(out, ref, f"gemm M={M} N={N} K={K} bn={block_n}", 3e-2 if not f32out else 2e-3, 1e-2)
+
+
+def check_gemm_conv3x3(B=2, H=12, W=39, c1=128, c2=0, N=192, block_n=0):
+    x1 = _randn((B, H, W, c1), 36, 1.0, bf16)
+    x2 = _randn((B, H, W, c2), 37, 1.0, bf16) if c2 else None
+    C = c1 + c2
+    wt = _randn((N, C, 3, 3), 38, 0.03)
+    wp = wt.permute(0, 2, 3, 1).reshape(N, 9 * C).contiguous().to(bf16)
+    bias = _randn((N,), 39)
+    res = _randn((B * H * W, N), 40, 1.0, bf16)
+    out = torch.empty((B, H, W, N), dtype=bf16, device=DEV)
+    ops.gemm(x1, wp, out, a2=x2, taps=9, bias=bias, residual=res, block_n=block_n)
+    xin = x1 if x2 is None else torch.cat([x1, x2], -1)
+    ref = F.conv2d(xin.float().permute(0, 3, 1, 2), wp.float().view(N, 3, 3, C).permute(0, 3, 1, 2), bias, padding=1)
+    ref = ref.permute(0, 2, 3, 1) + res.float().view(B, H, W, N)
+    return _stats(out, ref, f"conv3x3 B={B} {H}x{W} c1={c1} c2={c2} N={N}", 5e-2, 2e-2)
+
+
+def check_gemm_concat_1x1():
+    B, H, W, c1, c2, N = 2, 6, 20, 128, 64, 128
+    x1, x2 = _randn((B, H, W, c1), 41, 1.0, bf16), _randn((B, H, W, c2), 42, 1.0, bf16)
+    w = _randn((N, c1 + c2), 43, 0.05, bf16)
+    bias = _randn((N,), 44)
+    out = torch.empty((B, H, W, N), dtype=bf16, device=DEV)
+    ops.gemm(x1, w, out, a2=x2, taps=1, bias=bias)
+    ref = torch.cat([x1, x2], -1).float() @ w.float().t() + bias
+    return _stats(out, ref, "conv1x1 concat", 3e-2, 1e-2)
+
+
+def check_gemm_geglu():
+    M, C = 500, 320
+    a = _randn((M, C), 45, 1.0, bf16)
+    w = _randn((8 * C, C), 46, 0.05)
+    b = _randn((8 * C,), 47)
+    inner = 4 * C
+    # interleave value/gate rows in blocks of 16 (what the host packer does)
+    idx = torch.arange(inner).view(-1, 16)
+    perm = torch.cat([idx, idx + inner], dim=1).reshape(-1).to(DEV)
+    wp, bp = w[perm].contiguous().to(bf16), b[perm].contiguous()
+    out = torch.empty((M, inner), dtype=bf16, device=DEV)
+    ops.gemm(a, wp, out, bias=bp, flags=L.LDM_GEMM_GEGLU)
+    h = a.float() @ w.to(bf16).float().t() + b
+    val, gate = h.chunk(2, dim=-1)
+    ref = val * F.gelu(gate)
+    return _stats(out, ref, "gemm GEGLU", 3e-2, 2e-2)
+
+
+def _alloc_qkv(B, heads, seq, d):
+    dpad = ((d + 63) // 64) * 64
+    seq_pad = ((seq + 7) // 8) * 8
+    q = torch.zeros((B * heads, seq, dpad), dtype=bf16, device=DEV)
+    k = torch.zeros_like(q)
+    vt = torch.zeros((B * heads, d, seq_pad), dtype=bf16, device=DEV)
+    return q, k, vt, dpad, seq_pad
+
+
+def check_gemm_qkv(B=2, heads=8, d=40, seq=300):
+    C = heads * d
+    a = _randn((B * seq, C), 48, 1.0, bf16)
+    w = _randn((3 * C, C), 49, 0.05, bf16)
+    q, k, vt, dpad, seq_pad = _alloc_qkv(B, heads, seq, d)
+    ops.gemm(a, w, None, flags=L.LDM_GEMM_QKV_SPLIT,
+             qkv=dict(q=q, k=k, vt=vt, heads=heads, head_dim=d, dpad=dpad, seq=seq, seq_pad=seq_pad))
+    ref = (a.float() @ w.float().t()).view(B, seq, 3, heads, d)
+    qr = ref[:, :, 0].permute(0, 2, 1, 3).reshape(B * heads, seq, d)
+    kr = ref[:, :, 1].permute(0, 2, 1, 3).reshape(B * heads, seq, d)
+    vr = ref[:, :, 2].permute(0, 2, 3, 1).reshape(B * heads, d, seq)
+    _stats(q[:, :, :d], qr, "qkv q", 3e-2, 1e-2)
+    _stats(k[:, :, :d], kr, "qkv k", 3e-2, 1e-2)
+    assert float(q[:, :, d:].abs().max()) == 0.0, "q padding overwritten"
+    return _stats(vt[:, :, :seq], vr, f"qkv vt d={d}", 3e-2, 1e-2)
+
+
+def check_gemm_convt():
+    B, H, W, cin, cout = 2, 6, 20, 256, 256
+    x = _randn((B, H, W, cin), 50, 1.0, bf16)
+    wt = _randn((cin, cout, 2, 2), 51, 0.05)
+    bias = _randn((cout,), 52)
+    g, be = _randn((cout,), 53) * 0.2 + 1, _randn((cout,), 54) * 0.1
+    wp = wt.permute(2, 3, 1, 0).reshape(4 * cout, cin).contiguous().to(bf16)  # [(dy,dx,co), ci]
+    bp = bias.repeat(4).contiguous()
+    out = torch.empty((B, 2 * H, 2 * W, cout), dtype=bf16, device=DEV)
+    ops.gemm(x, wp, out, bias=bp, flags=L.LDM_GEMM_CONVT_LN_SILU, block_n=cout, ln=(g, be, 1e-6))
+    wq = wp.float().view(2, 2, cout, cin).permute(3, 2, 0, 1)
+    y = F.conv_transpose2d(x.float().permute(0, 3, 1, 2), wq, bias, stride=2)
+    u = y.mean(1, keepdim=True)
+    s = (y - u).pow(2).mean(1, keepdim=True)
+    y = (y - u) / torch.sqrt(s + 1e-6)
+    y = F.silu(g[:, None, None] * y + be[:, None, None]).permute(0, 2, 3, 1)
+    return _stats(out, y, "convT+LN2d+SiLU", 4e-2, 2e-2)
+
+
+# ----------------------------------------------------------------------------------------------------------- attention
+def check_attention(B=1, heads=2, d=40, seq=300):
+    q, k, vt, dpad, seq_pad = _alloc_qkv(B, heads, seq, d)
+    qf = _randn((B * heads, seq, d), 55, 1.0, bf16)
+    kf = _randn((B * heads, seq, d), 56, 1.0, bf16)
+    vf = _randn((B * heads, seq, d), 57, 1.0, bf16)
+    q[:, :, :d] = qf
+    k[:, :, :d] = kf
+    vt[:, :, :seq] = vf.transpose(1, 2)
+    out = torch.empty((B * seq, heads * d), dtype=bf16, device=DEV)
+    ops.flash_attn(q, k, vt, out, B=B, heads=heads, seq=seq, head_dim=d, dpad=dpad, seq_pad=seq_pad, scale=d ** -0.5)
+    ref = F.scaled_dot_product_attention(qf.float(), kf.float(), vf.float())  # [BH, seq, d]
+    ref = ref.view(B, heads, seq, d).permute(0, 2, 1, 3).reshape(B * seq, heads * d)
+    return _stats(out, ref, f"flash_attn d={d} seq={seq}", 2e-2, 2e-2)
+
+
+# ----------------------------------------------------------------------------------------------------------- integer tail
+def check_logits_to_ids(up=2):
+    B, h, w, C = 2, 24, 78, 128
+    lg = _randn((B, h, w, C), 58, 2.0)
+    lg[:, :, :, 5] += 3.0  # a dominant class so that the threshold keeps some pixels
+    lg[0, 3, 4, 7] = lg[0, 3, 4, 9] = 50.0  # exact tie -> first index
+    H, W = h * up, w * up
+    ids = torch.empty((B, H, W), dtype=torch.int32, device=DEV)
+    counts = torch.empty((B, 2, C), dtype=torch.int32, device=DEV)
+    ops.logits_to_ids(lg, ids, counts, up=up, mask_th=0.5, ignore_label=127)
+    x = lg.permute(0, 3, 1, 2).cpu()
+    if up != 1:
+        x = F.interpolate(x, scale_factor=up, mode="bilinear", align_corners=False)
+    full = torch.empty((B, C, H, W), device=DEV)
+    ops.bilinear_up_nchw(lg, full, up)
+    interp_exact = bool(torch.equal(full.cpu(), x))
+    pred = torch.argmax(x, dim=1)
+    probs = F.softmax(x, dim=1).max(dim=1)[0]
+    pred[probs < 0.5] = 127
+    sig = torch.sigmoid(x)
+    mism = int((pred != ids.cpu().long()).sum())
+    cnt_ref = torch.stack([torch.bincount(pred[b].flatten(), minlength=C) for b in range(B)])
+    over_ref = (sig >= 0.5).flatten(2).sum(-1)
+    c = counts.cpu().long()
+    info = {"name": f"logits_to_ids up={up}", "interp_bit_exact": interp_exact, "id_mismatch": mism,
+            "count_mismatch": int((c[:, 0] != cnt_ref).sum()), "over_mismatch": int((c[:, 1] != over_ref).sum())}
+    assert mism == 0 and info["count_mismatch"] == 0 and info["over_mismatch"] == 0, str(info)
+    # merge filter
+    cleaned = torch.empty_like(ids)
+    ops.segment_filter(ids, counts, cleaned, count_th=512, overlap_th=0.5, ignore_label=127)
+    cl_ref = pred.clone().numpy()
+    pn, sg = pred.numpy(), sig.numpy()
+    for b in range(B):
+        cb = cl_ref[b]
+        for lab, cnt in zip(*np.unique(pn[b], return_counts=True)):
+            if cnt < 512 or lab in {-1, 127}:
+                cb[cb == lab] = -1
+                continue
+            om = sg[b, lab] >= 0.5
+            if (pn[b] == lab).sum() / om.sum() < 0.5:
+                cb[cb == lab] = -1
+    assert np.array_equal(cl_ref, cleaned.cpu().numpy()), "segment_filter mismatch"
+    info["kept_labels"] = int(len(np.unique(cl_ref)) - 1)
+    return info
+
+
+def check_bitmap():
+    B, n, H, W = 2, 16, 24, 78
+    rng = np.random.default_rng(0)
+    ids_np = rng.integers(0, 60, size=(B, H, W)).astype(np.int32)
+    ids_np[0, :2] = 31
+    ids_np[1, 5:7] = 255
+    ids = torch.from_numpy(ids_np).to(DEV)
+    x = torch.empty((B, n, H, W), device=DEV)
+    ops.encode_bitmap(ids, x, ignore_label=255, fill=0.5)
+    t = torch.from_numpy(ids_np[0]).long()
+    ign = t == 255
+    ref = torch.remainder(torch.bitwise_right_shift(t, torch.arange(n)[:, None, None]), 2).float()
+    ref[:, ign] = 0.5
+    assert torch.equal(x[0].cpu(), ref), "encode_bitmap mismatch"
+    dec = torch.empty((B, H, W), dtype=torch.int32, device=DEV)
+    ops.decode_bitmap(x, dec, quirk31=True)
+    exp = ids_np.copy()
+    exp[exp == 31] = 0
+    exp[ids_np == 255] = 65535
+    assert np.array_equal(dec.cpu().numpy(), exp), "decode_bitmap mismatch"
+    return {"name": "bitmap", "bit_exact": True}
+
+
+def check_ccl():
+    from scipy import ndimage
+    B, H, W = 2, 96, 312
+    rng = np.random.default_rng(1)
+    sem = (rng.random((B, H, W)) < 0.55).astype(np.int32) * 13
+    sem[1, 10:40, 20:200] = 13
+    sem[1, 20:30, 50:150] = 2
+    lab, nc = ops.ccl_label4(torch.from_numpy(sem).to(DEV), 13)
+    lab, nc = lab.cpu().numpy(), nc.cpu().numpy()
+    for b in range(B):
+        ref, n = ndimage.label(sem[b] == 13)
+        assert n == nc[b], f"ccl count {nc[b]} != {n}"
+        assert np.array_equal(ref, lab[b]), "ccl labels differ from scipy.ndimage.label"
+    return {"name": "ccl", "components": nc.tolist()}
+
+
+def check_joint_hist():
+    rng = np.random.default_rng(2)
+    n = 384 * 1248
+    a = (rng.integers(0, 19, n) * (1 << 20) + rng.integers(0, 30, n)).astype(np.int32)
+    b = (rng.integers(0, 19, n) * (1 << 20) + rng.integers(0, 5, n)).astype(np.int32)
+    a[:1000] = -1
+    av, bv, c = ops.joint_hist(torch.from_numpy(a).to(DEV), torch.from_numpy(b).to(DEV), capacity=1 << 12)
+    key = a.astype(np.int64) * (1 << 31) + b.astype(np.int64)
+    uk, uc = np.unique(key, return_counts=True)
+    got = av * (1 << 31) + bv
+    assert np.array_equal(got, uk) and np.array_equal(c, uc), "joint_hist mismatch"
+    return {"name": "joint_hist", "pairs": int(len(uk))}
+
+
+CHECKS = {
+    "ddim": check_ddim,
+    "layernorm_320": lambda: check_layernorm(320),
+    "layernorm_1280": lambda: check_layernorm(1280, 468),
+    "groupnorm_320": lambda: check_groupnorm(320),
+    "groupnorm_960cat": lambda: check_groupnorm(640, 320, 1872),
+    "groupnorm_1920cat_nosilu": lambda: check_groupnorm(1280, 640, 468, silu=False, eps=1e-6),
+    "gemv": check_gemv,
+    "timestep_sinusoid": check_timestep_sinusoid,
+    "conv_small_cin": check_conv_small_cin,
+    "conv_out": check_conv_out,
+    "upsample_im2col": check_upsample_im2col,
+    "gemm_tiny": check_gemm_tiny,
+    "gemm_plain_320": check_gemm_plain,
+    "gemm_plain_f32_k1280": lambda: check_gemm_plain(777, 1280, 1280, f32out=True),
+    "gemm_plain_bn256_multi_tile": lambda: check_gemm_plain(20000, 1280, 640, block_n=256),
+    "gemm_plain_ktail": lambda: check_gemm_plain(300, 64, 72, residual=False),
+    "gemm_conv3x3": check_gemm_conv3x3,
+    "gemm_conv3x3_cat": lambda: check_gemm_conv3x3(2, 24, 78, 128, 64, 320),
+    "gemm_conv3x3_L0": lambda: check_gemm_conv3x3(1, 48, 156, 320, 0, 320),
+    "gemm_conv3x3_L3": lambda: check_gemm_conv3x3(3, 6, 20, 256, 0, 256),
+    "gemm_concat_1x1": check_gemm_concat_1x1,
+    "gemm_geglu": check_gemm_geglu,
+    "gemm_qkv_40": check_gemm_qkv,
+    "gemm_qkv_160": lambda: check_gemm_qkv(1, 8, 160, 468),
+    "gemm_convt": check_gemm_convt,
+    "attn_40_tail": check_attention,
+    "attn_40_long": lambda: check_attention(1, 2, 40, 1872),
+    "attn_80": lambda: check_attention(1, 2, 80, 468),
+    "attn_160": lambda: check_attention(2, 2, 160, 120),
+    "attn_160_b": lambda: check_attention(1, 2, 160, 468),
+    "logits_to_ids_up2": check_logits_to_ids,
+    "logits_to_ids_up1": lambda: check_logits_to_ids(1),
+    "bitmap": check_bitmap,
+    "ccl": check_ccl,
+    "joint_hist": check_joint_hist,
+}

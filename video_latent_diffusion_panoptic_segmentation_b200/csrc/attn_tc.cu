@@ -1,0 +1,355 @@
+// Fused flash-style self-attention for the UNet's BasicTransformerBlock.attn1 (softmax(QK^T * d^-0.5) V).
+//
+//   grid = (ceil(seq / (128*NQ)), B*heads); one CTA owns NQ tiles of 128 queries of one (image, head).
+//     warp 0              TMA producer : Q tiles once, then a ring of (K block | V^T block) stages
+//     warp 1              MMA issuer   : S = Q K^T and O_part = P V with tcgen05.mma (fp32 in TMEM)
+//     warps 2..2+4*NQ-1   softmax      : one query row per thread. Two passes over S in TMEM (row max, then
+//                                        exp2 / row sum / bf16 P written to swizzled smem as the A operand of the
+//                                        PV MMA); O is accumulated in registers from the per-block O_part so no
+//                                        TMEM read-modify-write rescale is needed.
+//   With NQ = 2 the tensor core computes group B's S / PV while group A is in its softmax.
+//   Layouts: q,k [B*heads, seq, dpad] (dpad = 64*ceil(d/64), zero padded), vt [B*heads, d, seq_pad] (V transposed so
+//   that both MMAs see K-major operands), out [B*seq, heads*d]; all bf16.
+#include "common.cuh"
+#include "host_util.h"
+
+namespace {
+using namespace ldm;
+
+struct AttnParams {
+  int seq, heads, head_dim;
+  float scale_log2;  // scale * log2(e)
+  __nv_bfloat16* out;
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int D, int NQ, int BKV, int STAGES>
+struct AttnCfg {
+  static constexpr int kAtoms = (D + 63) / 64;         // 64-wide K atoms of Q / K tiles
+  static constexpr int kSteps = (D + 15) / 16;         // UMMA k-steps for S = Q K^T
+  static constexpr int kDN = ((D + 15) / 16) * 16;     // UMMA N for O = P V
+  static constexpr int kQBytes = kAtoms * 128 * 128;   // per group
+  static constexpr int kKBytes = kAtoms * BKV * 128;
+  static constexpr int kVAtoms = BKV / 64;
+  static constexpr int kVBytes = kVAtoms * kDN * 128;
+  static constexpr int kVBytesPad = ((kVBytes + 1023) / 1024) * 1024;
+  static constexpr int kStageBytes = kKBytes + kVBytesPad;
+  static constexpr int kPBytes = kVAtoms * 128 * 128;  // per group
+  static constexpr int kSmem = NQ * (kQBytes + kPBytes) + STAGES * kStageBytes + 1024 + 256;
+  static constexpr int kThreads = 64 + 128 * NQ;
+  static constexpr int kTmemGroupStride = 256;
+  static constexpr int kTmemCols = (NQ == 2) ? 512 : ((BKV + kDN <= 256) ? 256 : 512);
+  static_assert(NQ == 1 || BKV + kDN <= 256, "TMEM budget");
+  static_assert(kSmem <= 227 * 1024, "smem budget");
+};
+
+template <int D, int NQ, int BKV, int STAGES>
+__global__ void __launch_bounds__(AttnCfg<D, NQ, BKV, STAGES>::kThreads, 1)
+flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                  const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  using Cfg = AttnCfg<D, NQ, BKV, STAGES>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                  // NQ * kQBytes
+  uint8_t* sP = sQ + NQ * Cfg::kQBytes;                // NQ * kPBytes
+  uint8_t* sKV = sP + NQ * Cfg::kPBytes;               // STAGES * kStageBytes
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + STAGES * Cfg::kStageBytes);
+  uint64_t* q_full = bars;               // [NQ]
+  uint64_t* kv_full = q_full + 2;        // [STAGES]
+  uint64_t* kv_empty = kv_full + 8;      // [STAGES]
+  uint64_t* s_full = kv_empty + 8;       // [NQ]
+  uint64_t* p_full = s_full + 2;         // [NQ]
+  uint64_t* o_full = p_full + 2;         // [NQ]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int bh = blockIdx.y;
+  const int q_base = blockIdx.x * 128 * NQ;
+  const int nblk = (p.seq + BKV - 1) / BKV;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    for (int g = 0; g < NQ; ++g) {
+      mbar_init(&q_full[g], 1);
+      mbar_init(&s_full[g], 1);
+      mbar_init(&p_full[g], 128);
+      mbar_init(&o_full[g], 1);
+    }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      for (int g = 0; g < NQ; ++g) {
+        mbar_arrive_expect_tx(&q_full[g], Cfg::kQBytes);
+        for (int a = 0; a < Cfg::kAtoms; ++a)
+          tma_load_3d(sQ + g * Cfg::kQBytes + a * 128 * 128, &tmQ, &q_full[g], a * 64, q_base + g * 128, bh);
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < nblk; ++j) {
+        mbar_wait(&kv_empty[stage], phase ^ 1);
+        uint8_t* sk = sKV + stage * Cfg::kStageBytes;
+        uint8_t* sv = sk + Cfg::kKBytes;
+        mbar_arrive_expect_tx(&kv_full[stage], Cfg::kKBytes + Cfg::kVBytes);
+        for (int a = 0; a < Cfg::kAtoms; ++a)
+          tma_load_3d(sk + a * BKV * 128, &tmK, &kv_full[stage], a * 64, j * BKV, bh);
+        for (int a = 0; a < Cfg::kVAtoms; ++a)
+          tma_load_3d(sv + a * Cfg::kDN * 128, &tmV, &kv_full[stage], j * BKV + a * 64, 0, bh);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16(128, BKV);
+      const uint32_t idesc_o = umma_idesc_bf16(128, Cfg::kDN);
+      auto issue_s = [&](int g, int stage) {
+        const uint32_t qa = smem_u32(sQ + g * Cfg::kQBytes);
+        const uint32_t ka = smem_u32(sKV + stage * Cfg::kStageBytes);
+        const uint32_t d_tmem = tmem_base + g * Cfg::kTmemGroupStride;
+#pragma unroll
+        for (int kk = 0; kk < Cfg::kSteps; ++kk) {
+          const uint64_t da = umma_desc_k_sw128(qa + (kk >> 2) * (128 * 128) + (kk & 3) * 32);
+          const uint64_t db = umma_desc_k_sw128(ka + (kk >> 2) * (BKV * 128) + (kk & 3) * 32);
+          umma_bf16(d_tmem, da, db, idesc_s, kk != 0);
+        }
+        umma_commit(&s_full[g]);
+      };
+      auto issue_o = [&](int g, int stage) {
+        const uint32_t pa = smem_u32(sP + g * Cfg::kPBytes);
+        const uint32_t va = smem_u32(sKV + stage * Cfg::kStageBytes + Cfg::kKBytes);
+        const uint32_t d_tmem = tmem_base + g * Cfg::kTmemGroupStride + BKV;
+#pragma unroll
+        for (int kk = 0; kk < BKV / 16; ++kk) {
+          const uint64_t da = umma_desc_k_sw128(pa + (kk >> 2) * (128 * 128) + (kk & 3) * 32);
+          const uint64_t db = umma_desc_k_sw128(va + (kk >> 2) * (Cfg::kDN * 128) + (kk & 3) * 32);
+          umma_bf16(d_tmem, da, db, idesc_o, kk != 0);
+        }
+        umma_commit(&o_full[g]);
+      };
+      for (int g = 0; g < NQ; ++g) mbar_wait(&q_full[g], 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      for (int g = 0; g < NQ; ++g) issue_s(g, 0);
+      for (int j = 0; j < nblk; ++j) {
+        int nstage = stage + 1;
+        uint32_t nphase = phase;
+        if (nstage == STAGES) {
+          nstage = 0;
+          nphase ^= 1;
+        }
+        const bool has_next = (j + 1 < nblk);
+        if (has_next) {
+          mbar_wait(&kv_full[nstage], nphase);
+          tc_fence_after();
+        }
+        for (int g = 0; g < NQ; ++g) {
+          mbar_wait(&p_full[g], j & 1);
+          tc_fence_after();
+          issue_o(g, stage);
+          if (has_next) issue_s(g, nstage);
+        }
+        umma_commit(&kv_empty[stage]);
+        stage = nstage;
+        phase = nphase;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ softmax / output (one row per thread)
+    const int g = (warp - 2) >> 2;
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    const int qrow = q_base + g * 128 + r;
+    const uint32_t t_s = tmem_base + ((uint32_t)(quad * 32) << 16) + g * Cfg::kTmemGroupStride;
+    const uint32_t t_o = t_s + BKV;
+    uint8_t* myP = sP + g * Cfg::kPBytes;
+    float o_acc[Cfg::kDN];
+#pragma unroll
+    for (int i = 0; i < Cfg::kDN; ++i) o_acc[i] = 0.f;
+    float m = -INFINITY, l = 0.f;
+
+    auto add_o_part = [&](float alpha) {
+#pragma unroll
+      for (int c = 0; c < Cfg::kDN; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(t_o + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o_acc[c + i] = (o_acc[c + i] + __uint_as_float(v[i])) * alpha;
+      }
+    };
+
+    for (int j = 0; j < nblk; ++j) {
+      const int kv0 = j * BKV;
+      const int nvalid = p.seq - kv0;  // keys of this block inside the sequence (>= 1)
+      mbar_wait(&s_full[g], j & 1);
+      tc_fence_after();
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < BKV; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(t_s + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float s = (c + i < nvalid) ? __uint_as_float(v[i]) : -INFINITY;
+          mx = fmaxf(mx, s);
+        }
+      }
+      const float m_new = fmaxf(m, mx * p.scale_log2);
+      const float alpha = ex2(m - m_new);
+      if (j > 0) {
+        mbar_wait(&o_full[g], (j - 1) & 1);
+        tc_fence_after();
+        add_o_part(alpha);
+      }
+      l *= alpha;
+      m = m_new;
+#pragma unroll
+      for (int c = 0; c < BKV; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(t_s + c, v);
+        tmem_ld_wait();
+        float pv[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float e = ex2(fmaf(__uint_as_float(v[i]), p.scale_log2, -m));
+          pv[i] = (c + i < nvalid) ? e : 0.f;
+          l += pv[i];
+        }
+        // row r of the K-major SWIZZLE_128B tile: 16-byte chunk index XOR (r & 7)
+        uint8_t* rowp = myP + (c >> 6) * (128 * 128) + r * 128;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const int chunk = ((c & 63) >> 3) + q4;
+          uint4 u;
+          u.x = pack_bf16(pv[q4 * 8 + 0], pv[q4 * 8 + 1]);
+          u.y = pack_bf16(pv[q4 * 8 + 2], pv[q4 * 8 + 3]);
+          u.z = pack_bf16(pv[q4 * 8 + 4], pv[q4 * 8 + 5]);
+          u.w = pack_bf16(pv[q4 * 8 + 6], pv[q4 * 8 + 7]);
+          *reinterpret_cast<uint4*>(rowp + ((chunk ^ (r & 7)) << 4)) = u;
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(&p_full[g]);
+    }
+    mbar_wait(&o_full[g], (nblk - 1) & 1);
+    tc_fence_after();
+    add_o_part(1.0f);
+    if (qrow < p.seq) {
+      const float inv = 1.0f / l;
+      const int b = bh / p.heads, head = bh - b * p.heads;
+      __nv_bfloat16* dst = p.out + ((long long)b * p.seq + qrow) * (p.heads * p.head_dim) + head * p.head_dim;
+#pragma unroll
+      for (int c = 0; c < D; c += 8) {
+        uint4 u;
+        u.x = pack_bf16(o_acc[c + 0] * inv, o_acc[c + 1] * inv);
+        u.y = pack_bf16(o_acc[c + 2] * inv, o_acc[c + 3] * inv);
+        u.z = pack_bf16(o_acc[c + 4] * inv, o_acc[c + 5] * inv);
+        u.w = pack_bf16(o_acc[c + 6] * inv, o_acc[c + 7] * inv);
+        *reinterpret_cast<uint4*>(dst + c) = u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int D, int NQ, int BKV, int STAGES>
+int launch_attn(const ldm_attn_desc* d, cudaStream_t s) {
+  using namespace ldm_host;
+  using Cfg = AttnCfg<D, NQ, BKV, STAGES>;
+  const int BH = d->B * d->heads;
+  CUtensorMap tmQ, tmK, tmV;
+  {
+    const uint64_t dims[3] = {(uint64_t)d->dpad, (uint64_t)d->seq, (uint64_t)BH};
+    const uint64_t str[2] = {(uint64_t)d->dpad * 2, (uint64_t)d->dpad * 2 * d->seq};
+    const uint32_t boxq[3] = {64, 128, 1};
+    const uint32_t boxk[3] = {64, (uint32_t)BKV, 1};
+    int rc = make_tmap(&tmQ, d->q, 3, dims, str, boxq, 2, true);
+    if (rc) return rc;
+    rc = make_tmap(&tmK, d->k, 3, dims, str, boxk, 2, true);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)d->seq, (uint64_t)d->head_dim, (uint64_t)BH};
+    const uint64_t str[2] = {(uint64_t)d->seq_pad * 2, (uint64_t)d->seq_pad * 2 * d->head_dim};
+    const uint32_t box[3] = {64, (uint32_t)Cfg::kDN, 1};
+    int rc = make_tmap(&tmV, d->vt, 3, dims, str, box, 2, true);
+    if (rc) return rc;
+  }
+  AttnParams p;
+  p.seq = d->seq;
+  p.heads = d->heads;
+  p.head_dim = d->head_dim;
+  p.scale_log2 = d->scale * 1.4426950408889634f;
+  p.out = reinterpret_cast<__nv_bfloat16*>(d->out);
+  auto kern = flash_attn_kernel<D, NQ, BKV, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+    if (e != cudaSuccess) return set_error(LDM_ERR_CUDA, "cudaFuncSetAttribute(attn): %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  dim3 grid((d->seq + 128 * NQ - 1) / (128 * NQ), BH);
+  kern<<<grid, Cfg::kThreads, Cfg::kSmem, s>>>(tmQ, tmK, tmV, p);
+  count_launch();
+  return check_launch("flash_attn_kernel");
+}
+
+}  // namespace
+
+extern "C" int ldm_flash_attn_fwd(const ldm_attn_desc* d, ldm_stream_t stream) {
+  using namespace ldm_host;
+  LDM_REQUIRE(d && d->q && d->k && d->vt && d->out, LDM_ERR_BAD_ARG, "ldm_flash_attn_fwd: null arg");
+  LDM_REQUIRE(d->B > 0 && d->heads > 0 && d->seq > 0, LDM_ERR_BAD_SHAPE, "ldm_flash_attn_fwd: bad B/heads/seq");
+  LDM_REQUIRE(d->dpad == ((d->head_dim + 63) / 64) * 64 && d->seq_pad % 8 == 0 && d->seq_pad >= d->seq,
+              LDM_ERR_BAD_SHAPE, "ldm_flash_attn_fwd: dpad=%d seq_pad=%d inconsistent with head_dim=%d seq=%d", d->dpad,
+              d->seq_pad, d->head_dim, d->seq);
+  cudaStream_t s = as_stream(stream);
+  switch (d->head_dim) {
+    case 40:
+      return launch_attn<40, 2, 128, 4>(d, s);
+    case 80:
+      return launch_attn<80, 1, 128, 3>(d, s);
+    case 160:
+      return launch_attn<160, 1, 64, 3>(d, s);
+    default:
+      return set_error(LDM_ERR_BAD_SHAPE, "ldm_flash_attn_fwd: head_dim %d not built (40, 80, 160)", d->head_dim);
+  }
+}

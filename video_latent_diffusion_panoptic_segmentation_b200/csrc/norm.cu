@@ -1,0 +1,236 @@
+// HBM-bound normalisation kernels on NHWC bf16 activations: GroupNorm(+SiLU) over a (virtual) channel concat and
+// LayerNorm over the channel dim. 16-byte vector loads/stores, warp-shuffle + shared-memory reductions, fp32 math,
+// fp64 cross-CTA accumulation of the GroupNorm moments.
+#include "common.cuh"
+#include "host_util.h"
+
+namespace {
+using namespace ldm;
+
+// ---------------------------------------------------------------------------------------------------------
+// GroupNorm pass 1: per-(image, group) sum and sum of squares.
+// grid = (chunks, B); block = (C/8 vectors, ppb pixels). Each thread owns one 8-channel vector position and walks
+// pixels with stride ppb*chunks, so every warp reads contiguous 16-byte vectors of one pixel row.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, const __nv_bfloat16* __restrict__ x2, int c1,
+                                int c2, int HW, int groups, double* __restrict__ stats) {
+  extern __shared__ float sh[];  // [groups*2]
+  const int C = c1 + c2;
+  const int cpg = C / groups;
+  const int b = blockIdx.y;
+  const int v = threadIdx.x;  // vector index within the pixel
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  for (int i = tid; i < groups * 2; i += blockDim.x * blockDim.y) sh[i] = 0.f;
+  __syncthreads();
+
+  const int c0 = v * 8;
+  const __nv_bfloat16* src;
+  int cs, coff;
+  if (c0 < c1) {
+    src = x1; cs = c1; coff = c0;
+  } else {
+    src = x2; cs = c2; coff = c0 - c1;
+  }
+  float s[8], ss[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
+  for (int pix = blockIdx.x * blockDim.y + threadIdx.y; pix < HW; pix += gridDim.x * blockDim.y) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + ((long long)b * HW + pix) * cs + coff));
+    const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
+    const float f[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j] += f[j];
+      ss[j] += f[j] * f[j];
+    }
+  }
+  // fold the 8 channels into their groups (a vector may straddle two groups when cpg % 8 != 0)
+  int g_prev = c0 / cpg;
+  float acc_s = 0.f, acc_ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int g = (c0 + j) / cpg;
+    if (g != g_prev) {
+      atomicAdd(&sh[g_prev * 2], acc_s);
+      atomicAdd(&sh[g_prev * 2 + 1], acc_ss);
+      acc_s = acc_ss = 0.f;
+      g_prev = g;
+    }
+    acc_s += s[j];
+    acc_ss += ss[j];
+  }
+  atomicAdd(&sh[g_prev * 2], acc_s);
+  atomicAdd(&sh[g_prev * 2 + 1], acc_ss);
+  __syncthreads();
+  for (int i = tid; i < groups * 2; i += blockDim.x * blockDim.y)
+    atomicAdd(&stats[(long long)b * groups * 2 + i], (double)sh[i]);
+}
+
+// GroupNorm pass 2: normalise + affine (+ SiLU), one 16-byte vector per thread-iteration.
+__global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, const __nv_bfloat16* __restrict__ x2, int c1,
+                                int c2, int HW, int groups, const double* __restrict__ stats,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
+                                __nv_bfloat16* __restrict__ out) {
+  extern __shared__ float sh[];  // mean[groups], rstd[groups]
+  const int C = c1 + c2;
+  const int cpg = C / groups;
+  const int b = blockIdx.y;
+  const double n = (double)cpg * (double)HW;
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    const double m = stats[((long long)b * groups + g) * 2] / n;
+    double var = stats[((long long)b * groups + g) * 2 + 1] / n - m * m;
+    if (var < 0.0) var = 0.0;
+    sh[g] = (float)m;
+    sh[groups + g] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  const int vpp = C / 8;
+  const long long total = (long long)HW * vpp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int pix = (int)(i / vpp);
+    const int c0 = (int)(i - (long long)pix * vpp) * 8;
+    const __nv_bfloat16* src = (c0 < c1) ? x1 + ((long long)b * HW + pix) * c1 + c0
+                                         : x2 + ((long long)b * HW + pix) * c2 + (c0 - c1);
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(src));
+    const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
+    float f[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c0));
+    const float4 gb = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
+    const float4 ba = __ldg(reinterpret_cast<const float4*>(beta + c0));
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
+    const float gm[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+    const float bt[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = (c0 + j) / cpg;
+      float y = (f[j] - sh[g]) * sh[groups + g] * gm[j] + bt[j];
+      f[j] = silu ? silu_f(y) : y;
+    }
+    uint4 o;
+    o.x = pack_bf16(f[0], f[1]);
+    o.y = pack_bf16(f[2], f[3]);
+    o.z = pack_bf16(f[4], f[5]);
+    o.w = pack_bf16(f[6], f[7]);
+    *reinterpret_cast<uint4*>(out + ((long long)b * HW + pix) * C + c0) = o;
+  }
+}
+
+// LayerNorm: one warp per row, row cached in registers (C <= 32*8*kMaxVec).
+constexpr int kMaxVec = 6;  // up to C = 1536
+__global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, __nv_bfloat16* __restrict__ out, int rows, int C,
+                                 float eps) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nvec = C / 8;
+  for (long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < rows;
+       row += (long long)gridDim.x * warps_per_block) {
+    const __nv_bfloat16* src = x + row * C;
+    float f[kMaxVec][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxVec; ++k) {
+      const int v = lane + k * 32;
+      if (v < nvec) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + v * 8));
+        const float2 a = unpack_bf16(u.x), b2 = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+        f[k][0] = a.x; f[k][1] = a.y; f[k][2] = b2.x; f[k][3] = b2.y;
+        f[k][4] = c.x; f[k][5] = c.y; f[k][6] = d.x; f[k][7] = d.y;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sum += f[k][j];
+      }
+    }
+    const float mean = warp_sum(sum) / (float)C;
+    float sq = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxVec; ++k) {
+      const int v = lane + k * 32;
+      if (v < nvec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = f[k][j] - mean;
+          sq += d * d;
+        }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
+#pragma unroll
+    for (int k = 0; k < kMaxVec; ++k) {
+      const int v = lane + k * 32;
+      if (v < nvec) {
+        const int c0 = v * 8;
+        const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c0));
+        const float4 gb = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
+        const float4 ba = __ldg(reinterpret_cast<const float4*>(beta + c0));
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
+        const float gm[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+        const float bt[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (f[k][j] - mean) * rstd * gm[j] + bt[j];
+        uint4 u;
+        u.x = pack_bf16(o[0], o[1]);
+        u.y = pack_bf16(o[2], o[3]);
+        u.z = pack_bf16(o[4], o[5]);
+        u.w = pack_bf16(o[6], o[7]);
+        *reinterpret_cast<uint4*>(out + row * C + c0) = u;
+      }
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int ldm_groupnorm_silu(const ldm_groupnorm_desc* d, ldm_stream_t stream) {
+  using namespace ldm_host;
+  LDM_REQUIRE(d && d->x1 && d->gamma && d->beta && d->out && d->stats, LDM_ERR_BAD_ARG, "ldm_groupnorm_silu: null arg");
+  const int c2 = d->x2 ? d->c2 : 0;
+  const int C = d->c1 + c2;
+  LDM_REQUIRE(d->B > 0 && d->HW > 0 && d->groups > 0 && C % d->groups == 0, LDM_ERR_BAD_SHAPE,
+              "ldm_groupnorm_silu: bad shape B=%d HW=%d C=%d groups=%d", d->B, d->HW, C, d->groups);
+  LDM_REQUIRE(d->c1 % 8 == 0 && c2 % 8 == 0 && C / 8 <= 1024, LDM_ERR_ALIGNMENT,
+              "ldm_groupnorm_silu: channels must be multiples of 8 and <= 8192");
+  cudaStream_t s = as_stream(stream);
+  cudaError_t e = cudaMemsetAsync(d->stats, 0, sizeof(double) * 2 * d->groups * d->B, s);
+  if (e != cudaSuccess) return set_error(LDM_ERR_CUDA, "memset stats: %s", cudaGetErrorString(e));
+  const int vpp = C / 8;
+  int ppb = 512 / vpp;
+  if (ppb < 1) ppb = 1;
+  if (ppb > d->HW) ppb = d->HW;
+  int chunks = (2 * num_sms() + d->B - 1) / d->B;
+  const int max_chunks = (d->HW + ppb - 1) / ppb;
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  const size_t shb = sizeof(float) * 2 * d->groups;
+  gn_stats_kernel<<<dim3(chunks, d->B), dim3(vpp, ppb), shb, s>>>(
+      reinterpret_cast<const __nv_bfloat16*>(d->x1), reinterpret_cast<const __nv_bfloat16*>(d->x2), d->c1, c2, d->HW,
+      d->groups, d->stats);
+  count_launch();
+  int rc = check_launch("gn_stats_kernel");
+  if (rc) return rc;
+  const long long total = (long long)d->HW * vpp;
+  int gx = (int)((total + 256 * 4 - 1) / (256 * 4));
+  if (gx < 1) gx = 1;
+  gn_apply_kernel<<<dim3(gx, d->B), 256, shb, s>>>(
+      reinterpret_cast<const __nv_bfloat16*>(d->x1), reinterpret_cast<const __nv_bfloat16*>(d->x2), d->c1, c2, d->HW,
+      d->groups, d->stats, d->gamma, d->beta, d->eps, d->silu, reinterpret_cast<__nv_bfloat16*>(d->out));
+  count_launch();
+  return check_launch("gn_apply_kernel");
+}
+
+extern "C" int ldm_layernorm(const void* x, const float* gamma, const float* beta, void* out, int32_t rows, int32_t C,
+                             float eps, ldm_stream_t stream) {
+  using namespace ldm_host;
+  LDM_REQUIRE(x && gamma && beta && out, LDM_ERR_BAD_ARG, "ldm_layernorm: null arg");
+  LDM_REQUIRE(rows > 0 && C > 0 && C % 8 == 0 && C <= 32 * 8 * kMaxVec, LDM_ERR_BAD_SHAPE,
+              "ldm_layernorm: rows=%d C=%d unsupported (C %% 8 == 0, C <= %d)", rows, C, 32 * 8 * kMaxVec);
+  const int wpb = 8;
+  int grid = (rows + wpb - 1) / wpb;
+  const int cap = num_sms() * 16;
+  if (grid > cap) grid = cap;
+  layernorm_kernel<<<grid, wpb * 32, 0, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta,
+                                                             reinterpret_cast<__nv_bfloat16*>(out), rows, C, eps);
+  count_launch();
+  return check_launch("layernorm_kernel");
+}

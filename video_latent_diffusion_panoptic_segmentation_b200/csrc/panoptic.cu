@@ -1,0 +1,470 @@
+// Integer tail of the sampler path: logits -> panoptic ids (fused bilinear up-sampling, argmax, softmax-max
+// threshold, per-class pixel counts), the count/overlap merge filter, the bit codec, 4-connected component
+// labelling with scipy numbering, and the joint (gt, pred) id histogram that vpq_eval / the Cityscapes PQ
+// evaluator reduce to. All HBM-bound byte/integer work: coalesced 16-byte loads, warp-aggregated atomics.
+#include "common.cuh"
+#include "host_util.h"
+
+namespace {
+using namespace ldm;
+
+// torch's CPU bilinear kernel (UpSampleKernel.cpp, Interpolate<2,...>::eval) evaluates
+//   out = (x00*wx0 + x01*wx1) * wy0 + (x10*wx0 + x11*wx1) * wy1
+// with "output = t*w0; output += t1*w1" which the vectorised build contracts to one multiply + one FMA.
+__device__ __forceinline__ float lerp2(float a, float wa, float b, float wb) { return fmaf(b, wb, __fmul_rn(a, wa)); }
+
+struct Axis {
+  int i0, i1;
+  float w0, w1;
+};
+// align_corners=False source index with an explicit scale_factor `up` (scale = 1/up), torch area_pixel_compute_source_index
+__device__ __forceinline__ Axis axis_for(int dst, int in_size, int up) {
+  Axis a;
+  if (up == 1) {
+    a.i0 = dst; a.i1 = dst < in_size - 1 ? dst + 1 : dst; a.w0 = 1.f; a.w1 = 0.f;
+    return a;
+  }
+  const float scale = 1.0f / (float)up;
+  float src = __fsub_rn(__fmul_rn(scale, __fadd_rn((float)dst, 0.5f)), 0.5f);
+  if (src < 0.f) src = 0.f;
+  a.i0 = (int)src;
+  if (a.i0 > in_size - 1) a.i0 = in_size - 1;
+  a.i1 = a.i0 < in_size - 1 ? a.i0 + 1 : a.i0;
+  a.w1 = __fsub_rn(src, (float)a.i0);
+  a.w0 = __fsub_rn(1.f, a.w1);
+  return a;
+}
+
+constexpr int kMaxVecPerLane = 4;  // C <= 512
+
+// grid = (chunks, B); one warp per output pixel (looping); lane owns channels {4*(lane+32k) .. +3}.
+__global__ void logits_to_ids_kernel(const float* __restrict__ logits, int32_t* __restrict__ ids,
+                                     int32_t* __restrict__ counts, int h, int w, int C, int up, float mask_th,
+                                     int ignore_label) {
+  extern __shared__ int hist[];  // [C] argmax-label histogram of this CTA
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int H = h * up, W = w * up;
+  const int nvec = C / 4;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  int over[kMaxVecPerLane * 4];
+#pragma unroll
+  for (int i = 0; i < kMaxVecPerLane * 4; ++i) over[i] = 0;
+  const float* img = logits + (long long)b * h * w * C;
+  const long long npix = (long long)H * W;
+  for (long long pix = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); pix < npix;
+       pix += (long long)gridDim.x * wpb) {
+    const int oy = (int)(pix / W), ox = (int)(pix - (long long)oy * W);
+    const Axis ay = axis_for(oy, h, up), ax = axis_for(ox, w, up);
+    const float* p00 = img + ((long long)ay.i0 * w + ax.i0) * C;
+    const float* p01 = img + ((long long)ay.i0 * w + ax.i1) * C;
+    const float* p10 = img + ((long long)ay.i1 * w + ax.i0) * C;
+    const float* p11 = img + ((long long)ay.i1 * w + ax.i1) * C;
+    float val[kMaxVecPerLane * 4];
+    float best = -INFINITY;
+    int besti = 0x7fffffff;
+#pragma unroll
+    for (int k = 0; k < kMaxVecPerLane; ++k) {
+      const int v = lane + 32 * k;
+      if (v < nvec) {
+        float4 a = __ldg(reinterpret_cast<const float4*>(p00) + v);
+        if (up != 1) {
+          const float4 bq = __ldg(reinterpret_cast<const float4*>(p01) + v);
+          const float4 c = __ldg(reinterpret_cast<const float4*>(p10) + v);
+          const float4 d = __ldg(reinterpret_cast<const float4*>(p11) + v);
+          a.x = lerp2(lerp2(a.x, ax.w0, bq.x, ax.w1), ay.w0, lerp2(c.x, ax.w0, d.x, ax.w1), ay.w1);
+          a.y = lerp2(lerp2(a.y, ax.w0, bq.y, ax.w1), ay.w0, lerp2(c.y, ax.w0, d.y, ax.w1), ay.w1);
+          a.z = lerp2(lerp2(a.z, ax.w0, bq.z, ax.w1), ay.w0, lerp2(c.z, ax.w0, d.z, ax.w1), ay.w1);
+          a.w = lerp2(lerp2(a.w, ax.w0, bq.w, ax.w1), ay.w0, lerp2(c.w, ax.w0, d.w, ax.w1), ay.w1);
+        }
+        val[k * 4 + 0] = a.x; val[k * 4 + 1] = a.y; val[k * 4 + 2] = a.z; val[k * 4 + 3] = a.w;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (val[k * 4 + j] > best) {  // strict: first index wins (torch.argmax)
+            best = val[k * 4 + j];
+            besti = v * 4 + j;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) val[k * 4 + j] = -INFINITY;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+      if (ov > best || (ov == best && oi < besti)) {
+        best = ov;
+        besti = oi;
+      }
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxVecPerLane; ++k) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float x = val[k * 4 + j];
+        if (lane + 32 * k < nvec) {
+          sum += expf(x - best);
+          // sigmoid(x) >= mask_th, evaluated like torch: 1 / (1 + exp(-x))
+          const float sg = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-x)));
+          over[k * 4 + j] += (sg >= mask_th) ? 1 : 0;
+        }
+      }
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) {
+      const float pmax = __fdiv_rn(1.f, sum);
+      int id = besti;
+      if (pmax < mask_th) id = ignore_label;
+      ids[(long long)b * npix + pix] = id;
+      if (id >= 0 && id < C) atomicAdd(&hist[id], 1);
+    }
+  }
+  __syncthreads();
+  int32_t* cb = counts + (long long)b * 2 * C;
+  for (int i = threadIdx.x; i < C; i += blockDim.x)
+    if (hist[i]) atomicAdd(&cb[i], hist[i]);
+  // per-class sigmoid-threshold areas: reduce the per-lane counters across the CTA's warps through smem
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kMaxVecPerLane; ++k) {
+    const int v = lane + 32 * k;
+    if (v < nvec) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (over[k * 4 + j]) atomicAdd(&hist[v * 4 + j], over[k * 4 + j]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x)
+    if (hist[i]) atomicAdd(&cb[C + i], hist[i]);
+}
+
+// Materialising bilinear x`up`: NHWC f32 [B,h,w,C] -> NCHW f32 [B,C,H,W] (parity checks of the interpolation).
+__global__ void bilinear_up_nchw_kernel(const float* __restrict__ logits, float* __restrict__ out, int B, int h, int w,
+                                        int C, int up) {
+  const int H = h * up, W = w * up;
+  const long long total = (long long)B * C * H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % W);
+    long long t = i / W;
+    const int oy = (int)(t % H);
+    t /= H;
+    const int c = (int)(t % C);
+    const int b = (int)(t / C);
+    const Axis ay = axis_for(oy, h, up), ax = axis_for(ox, w, up);
+    const float* img = logits + (long long)b * h * w * C + c;
+    const float x00 = img[((long long)ay.i0 * w + ax.i0) * C], x01 = img[((long long)ay.i0 * w + ax.i1) * C];
+    const float x10 = img[((long long)ay.i1 * w + ax.i0) * C], x11 = img[((long long)ay.i1 * w + ax.i1) * C];
+    out[i] = (up == 1) ? x00
+                       : lerp2(lerp2(x00, ax.w0, x01, ax.w1), ay.w0, lerp2(x10, ax.w0, x11, ax.w1), ay.w1);
+  }
+}
+
+// Merge filter (trainers_ldm_cond.py:1307-1325). counts = [B][2][C] (argmax area, sigmoid>=th area).
+__global__ void segment_filter_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ counts,
+                                      int32_t* __restrict__ cleaned, long long hw, int C, int count_th,
+                                      double overlap_th, int ignore_label) {
+  extern __shared__ int keep[];
+  const int b = blockIdx.y;
+  const int32_t* cb = counts + (long long)b * 2 * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int cnt = cb[c], ov = cb[C + c];
+    bool k = cnt >= count_th && c != ignore_label && cnt > 0;
+    // numpy: int / int -> float64 (x/0 -> inf, which is not < overlap_th)
+    if (k && ov > 0 && ((double)cnt / (double)ov) < overlap_th) k = false;
+    keep[c] = k ? 1 : 0;
+  }
+  __syncthreads();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += (long long)gridDim.x * blockDim.x) {
+    const int id = ids[(long long)b * hw + i];
+    cleaned[(long long)b * hw + i] = (id >= 0 && id < C && keep[id]) ? id : -1;
+  }
+}
+
+__global__ void decode_bitmap_kernel(const float* __restrict__ x, int32_t* __restrict__ ids, int nbits, long long hw,
+                                     int quirk31) {
+  const int b = blockIdx.y;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += (long long)gridDim.x * blockDim.x) {
+    int id = 0;
+    for (int k = 0; k < nbits; ++k) id |= (x[((long long)b * nbits + k) * hw + i] > 0.f) ? (1 << k) : 0;
+    if (quirk31 && id == 31) id = 0;
+    ids[(long long)b * hw + i] = id;
+  }
+}
+
+__global__ void encode_bitmap_kernel(const int32_t* __restrict__ ids, float* __restrict__ x, int nbits, long long hw,
+                                     int ignore_label, float fill) {
+  const int b = blockIdx.y;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += (long long)gridDim.x * blockDim.x) {
+    const int id = ids[(long long)b * hw + i];
+    for (int k = 0; k < nbits; ++k)
+      x[((long long)b * nbits + k) * hw + i] = (id == ignore_label) ? fill : (float)((id >> k) & 1);
+  }
+}
+
+// ---------------------------------------------------------------- connected components (4-connectivity)
+__device__ __forceinline__ int cc_find(const int32_t* L, int i) {
+  int p = L[i];
+  while (p != i) {
+    i = p;
+    p = L[i];
+  }
+  return i;
+}
+__device__ __forceinline__ void cc_union(int32_t* L, int a, int b) {
+  while (true) {
+    a = cc_find(L, a);
+    b = cc_find(L, b);
+    if (a == b) return;
+    if (a < b) {
+      const int t = a; a = b; b = t;
+    }
+    // a > b: hook the larger root under the smaller so the root is the first pixel in raster order
+    const int old = atomicMin(&L[a], b);
+    if (old == a) return;
+    a = old;
+  }
+}
+__global__ void ccl_init_kernel(const int32_t* __restrict__ sem, int target, int32_t* __restrict__ L, long long n,
+                                long long hw) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    L[i] = (sem[i] == target) ? (int)(i % hw) : -1;
+}
+__global__ void ccl_merge_kernel(int32_t* __restrict__ Lall, int H, int W) {
+  const long long hw = (long long)H * W;
+  int32_t* L = Lall + (long long)blockIdx.y * hw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += (long long)gridDim.x * blockDim.x) {
+    if (L[i] < 0) continue;
+    const int x = (int)(i % W);
+    if (x > 0 && L[i - 1] >= 0) cc_union(L, (int)i, (int)i - 1);
+    if (i >= W && L[i - W] >= 0) cc_union(L, (int)i, (int)(i - W));
+  }
+}
+__global__ void ccl_compress_count_kernel(int32_t* __restrict__ Lall, int32_t* __restrict__ block_counts, long long hw) {
+  // blockDim = 1024 pixels per block; counts roots per block
+  __shared__ int cnt;
+  if (threadIdx.x == 0) cnt = 0;
+  __syncthreads();
+  int32_t* L = Lall + (long long)blockIdx.y * hw;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  bool root = false;
+  if (i < hw && L[i] >= 0) {
+    const int r = cc_find(L, (int)i);
+    L[i] = r;
+    root = (r == (int)i);
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, root);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(&cnt, __popc(m));
+  __syncthreads();
+  if (threadIdx.x == 0) block_counts[(long long)blockIdx.y * gridDim.x + blockIdx.x] = cnt;
+}
+__global__ void ccl_scan_blocks_kernel(int32_t* __restrict__ block_counts, int32_t* __restrict__ ncomp, int nblocks) {
+  // one CTA per image: exclusive scan of block_counts in place (sequential over chunks of blockDim)
+  __shared__ int sh[1024];
+  __shared__ int carry;
+  int32_t* bc = block_counts + (long long)blockIdx.x * nblocks;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nblocks; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const int v = i < nblocks ? bc[i] : 0;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < blockDim.x; o <<= 1) {
+      const int t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += t;
+      __syncthreads();
+    }
+    const int incl = sh[threadIdx.x];
+    const int c = carry;
+    __syncthreads();
+    if (i < nblocks) bc[i] = c + incl - v;
+    if (threadIdx.x == blockDim.x - 1) carry = c + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) ncomp[blockIdx.x] = carry;
+}
+__global__ void ccl_rank_kernel(const int32_t* __restrict__ Lall, const int32_t* __restrict__ block_offsets,
+                                int32_t* __restrict__ rank_all, long long hw) {
+  // rank[root pixel] = 1-based component number in raster order of the root
+  __shared__ int warp_tot[32];
+  const int32_t* L = Lall + (long long)blockIdx.y * hw;
+  int32_t* rank = rank_all + (long long)blockIdx.y * hw;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool root = (i < hw) && (L[i] == (int)i);
+  const unsigned m = __ballot_sync(0xffffffffu, root);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) warp_tot[wid] = __popc(m);
+  __syncthreads();
+  int prefix = block_offsets[(long long)blockIdx.y * gridDim.x + blockIdx.x];
+  for (int k = 0; k < wid; ++k) prefix += warp_tot[k];
+  prefix += __popc(m & ((1u << lane) - 1));
+  if (root) rank[i] = prefix + 1;
+}
+__global__ void ccl_final_kernel(const int32_t* __restrict__ L, const int32_t* __restrict__ rank,
+                                 int32_t* __restrict__ labels, long long n, long long hw) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int r = L[i];
+    labels[i] = r < 0 ? 0 : rank[(i / hw) * hw + r];
+  }
+}
+
+// ---------------------------------------------------------------- joint id histogram (open-addressing hash)
+constexpr unsigned long long kEmptyKey = 0x8000000000000000ull;
+__global__ void hash_clear_kernel(unsigned long long* keys, int32_t* counts, int cap, int32_t* overflow) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
+    keys[i] = kEmptyKey;
+    counts[i] = 0;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *overflow = 0;
+}
+__global__ void joint_hist_kernel(const int32_t* __restrict__ a, const int32_t* __restrict__ b, long long n,
+                                  unsigned long long* __restrict__ keys, int32_t* __restrict__ counts, int cap,
+                                  int32_t* __restrict__ overflow) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long nround = ((n + stride - 1) / stride) * stride;  // keep warps converged for match_any
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
+    const bool valid = i < n;
+    const unsigned long long key =
+        valid ? (((unsigned long long)(uint32_t)a[i] << 32) | (unsigned long long)(uint32_t)b[i]) : kEmptyKey;
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    const int leader = __ffs(peers) - 1;
+    if (valid && (int)(threadIdx.x & 31) == leader) {
+      const int add = __popc(peers);
+      unsigned long long hsh = key * 0x9E3779B97F4A7C15ull;
+      int slot = (int)((hsh >> 32) & (unsigned)(cap - 1));
+      int probes = 0;
+      while (true) {
+        const unsigned long long prev = atomicCAS(&keys[slot], kEmptyKey, key);
+        if (prev == kEmptyKey || prev == key) {
+          atomicAdd(&counts[slot], add);
+          break;
+        }
+        slot = (slot + 1) & (cap - 1);
+        if (++probes >= cap) {
+          *overflow = 1;
+          break;
+        }
+      }
+    }
+  }
+}
+
+int grid1d(long long work, int threads, int mult = 16) {
+  long long g = (work + threads - 1) / threads;
+  const long long cap = (long long)ldm_host::num_sms() * mult;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace
+
+extern "C" int ldm_logits_to_ids(const float* logits, int32_t* ids, int32_t* counts, int32_t B, int32_t h, int32_t w,
+                                 int32_t C, int32_t up, float mask_th, int32_t ignore_label, ldm_stream_t stream) {
+  using namespace ldm_host;
+  LDM_REQUIRE(logits && ids && counts, LDM_ERR_BAD_ARG, "ldm_logits_to_ids: null arg");
+  LDM_REQUIRE(B > 0 && h > 0 && w > 0 && C > 0 && C % 4 == 0 && C <= 128 * kMaxVecPerLane && (up == 1 || up == 2),
+              LDM_ERR_BAD_SHAPE, "ldm_logits_to_ids: B=%d h=%d w=%d C=%d up=%d", B, h, w, C, up);
+  cudaStream_t s = as_stream(stream);
+  cudaError_t e = cudaMemsetAsync(counts, 0, sizeof(int32_t) * 2 * C * B, s);
+  if (e != cudaSuccess) return set_error(LDM_ERR_CUDA, "memset counts: %s", cudaGetErrorString(e));
+  int chunks = (num_sms() * 4 + B - 1) / B;
+  logits_to_ids_kernel<<<dim3(chunks, B), 256, sizeof(int) * C, s>>>(logits, ids, counts, h, w, C, up, mask_th,
+                                                                     ignore_label);
+  count_launch();
+  return check_launch("logits_to_ids_kernel");
+}
+
+extern "C" int ldm_bilinear_up_nchw(const float* logits, float* out, int32_t B, int32_t h, int32_t w, int32_t C,
+                                    int32_t up, ldm_stream_t stream) {
+  using namespace ldm_host;
+  LDM_REQUIRE(logits && out && B > 0 && h > 0 && w > 0 && C > 0 && (up == 1 || up == 2), LDM_ERR_BAD_ARG,
+              "ldm_bilinear_up_nchw: bad arg");
+  const long long total = (long long)B * C * h * up * w * up;
+  bilinear_up_nchw_kernel<<<grid1d(total, 256), 256, 0, as_stream(stream)>>>(logits, out, B, h, w, C, up);
+  count_launch();
+  return check_launch("bilinear_up_nchw_kernel");
+}
+
+extern "C" int ldm_segment_filter(const int32_t* ids, const int32_t* counts, int32_t* cleaned, int32_t B, int64_t hw,
+                                  int32_t C, int32_t count_th, double overlap_th, int32_t ignore_label,
+                                  ldm_stream_t stream) {
+  using namespace ldm_host;
+  LDM_REQUIRE(ids && counts && cleaned && B > 0 && hw > 0 && C > 0 && C <= 8192, LDM_ERR_BAD_ARG,
+              "ldm_segment_filter: bad arg");
+  int chunks = grid1d(hw, 256, 4);
+  segment_filter_kernel<<<dim3(chunks, B), 256, sizeof(int) * C, as_stream(stream)>>>(ids, counts, cleaned, hw, C,
+                                                                                      count_th, overlap_th, ignore_label);
+  count_launch();
+  return check_launch("segment_filter_kernel");
+}
+
+extern "C" int ldm_decode_bitmap(const float* x, int32_t* ids, int32_t B, int32_t nbits, int64_t hw, int32_t quirk31,
+                                 ldm_stream_t stream) {
+  using namespace ldm_host;
+  LDM_REQUIRE(x && ids && B > 0 && hw > 0 && nbits > 0 && nbits <= 24, LDM_ERR_BAD_ARG,
+              "ldm_decode_bitmap: bad arg (nbits must be in [1,24])");
+  decode_bitmap_kernel<<<dim3(grid1d(hw, 256, 4), B), 256, 0, as_stream(stream)>>>(x, ids, nbits, hw, quirk31);
+  count_launch();
+  return check_launch("decode_bitmap_kernel");
+}
+
+extern "C" int ldm_encode_bitmap(const int32_t* ids, float* x, int32_t B, int32_t nbits, int64_t hw,
+                                 int32_t ignore_label, float fill, ldm_stream_t stream) {
+  using namespace ldm_host;
+  LDM_REQUIRE(x && ids && B > 0 && hw > 0 && nbits > 0 && nbits <= 31, LDM_ERR_BAD_ARG, "ldm_encode_bitmap: bad arg");
+  encode_bitmap_kernel<<<dim3(grid1d(hw, 256, 4), B), 256, 0, as_stream(stream)>>>(ids, x, nbits, hw, ignore_label, fill);
+  count_launch();
+  return check_launch("encode_bitmap_kernel");
+}
+
+extern "C" size_t ldm_ccl_scratch_bytes(int32_t B, int32_t H, int32_t W) {
+  const long long hw = (long long)H * W;
+  const long long nblocks = (hw + 1023) / 1024;
+  return (size_t)(sizeof(int32_t) * (2 * (long long)B * hw + (long long)B * nblocks));
+}
+
+extern "C" int ldm_ccl_label4(const int32_t* sem, int32_t target, int32_t* labels, int32_t* ncomp, int32_t* scratch,
+                              int32_t B, int32_t H, int32_t W, ldm_stream_t stream) {
+  using namespace ldm_host;
+  LDM_REQUIRE(sem && labels && ncomp && scratch && B > 0 && H > 0 && W > 0, LDM_ERR_BAD_ARG, "ldm_ccl_label4: bad arg");
+  const long long hw = (long long)H * W;
+  LDM_REQUIRE(hw < (1ll << 31), LDM_ERR_BAD_SHAPE, "ldm_ccl_label4: image too large");
+  const long long n = hw * B;
+  const int nblocks = (int)((hw + 1023) / 1024);
+  int32_t* L = scratch;
+  int32_t* rank = scratch + n;
+  int32_t* bcnt = scratch + 2 * n;
+  cudaStream_t s = as_stream(stream);
+  ccl_init_kernel<<<grid1d(n, 256), 256, 0, s>>>(sem, target, L, n, hw);
+  ccl_merge_kernel<<<dim3(grid1d(hw, 256, 8), B), 256, 0, s>>>(L, H, W);
+  ccl_compress_count_kernel<<<dim3(nblocks, B), 1024, 0, s>>>(L, bcnt, hw);
+  ccl_scan_blocks_kernel<<<B, 1024, 0, s>>>(bcnt, ncomp, nblocks);
+  ccl_rank_kernel<<<dim3(nblocks, B), 1024, 0, s>>>(L, bcnt, rank, hw);
+  ccl_final_kernel<<<grid1d(n, 256), 256, 0, s>>>(L, rank, labels, n, hw);
+  count_launch(6);
+  return check_launch("ccl kernels");
+}
+
+extern "C" int ldm_joint_hist(const int32_t* a, const int32_t* b, int64_t n, unsigned long long* keys, int32_t* counts,
+                              int32_t capacity, int32_t* overflow, ldm_stream_t stream) {
+  using namespace ldm_host;
+  LDM_REQUIRE(a && b && keys && counts && overflow && n > 0, LDM_ERR_BAD_ARG, "ldm_joint_hist: bad arg");
+  LDM_REQUIRE(capacity >= 64 && (capacity & (capacity - 1)) == 0, LDM_ERR_BAD_SHAPE,
+              "ldm_joint_hist: capacity must be a power of two >= 64");
+  cudaStream_t s = as_stream(stream);
+  hash_clear_kernel<<<grid1d(capacity, 256, 2), 256, 0, s>>>(keys, counts, capacity, overflow);
+  joint_hist_kernel<<<grid1d(n, 256, 8), 256, 0, s>>>(a, b, n, keys, counts, capacity, overflow);
+  count_launch(2);
+  return check_launch("joint_hist_kernel");
+}

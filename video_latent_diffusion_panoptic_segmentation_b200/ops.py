@@ -1,0 +1,239 @@
+"""Torch-tensor front-ends of the C-ABI kernels. PyTorch here is plumbing only: device memory, streams.
+
+Every function takes CUDA tensors, validates dtype/contiguity, and enqueues the kernel on the current stream.
+Activations are NHWC bf16 (``[B, H, W, C]``); see include/ldmseg_b200.h for the per-op contracts.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+bf16, f32, i32, i64 = torch.bfloat16, torch.float32, torch.int32, torch.int64
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk(t, dtype, name):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise L.LdmError(f"{name}: expected a CUDA tensor (no CPU fallback)")
+    if t.dtype != dtype:
+        raise L.LdmError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise L.LdmError(f"{name}: expected a contiguous tensor")
+
+
+def gemm(a1, w, out=None, *, a2=None, taps=1, bias=None, rowbias=None, residual=None, flags=0, block_n=0,
+         qkv=None, ln=None):
+    """out = epilogue(conv/gemm(a1 ++ a2, w)). a1/a2: [B,H,W,C] or [rows,C] bf16; w: [N, taps*(c1+c2)] bf16.
+
+    qkv = dict(q=, k=, vt=, heads=, head_dim=, dpad=, seq=, seq_pad=) for LDM_GEMM_QKV_SPLIT;
+    ln = (gamma, beta, eps) for LDM_GEMM_CONVT_LN_SILU.
+    """
+    _chk(a1, bf16, "a1"); _chk(a2, bf16, "a2"); _chk(w, bf16, "w"); _chk(bias, f32, "bias")
+    _chk(rowbias, f32, "rowbias"); _chk(residual, bf16, "residual")
+    if a1.dim() == 2:
+        B, H, W, c1 = 1, 1, a1.shape[0], a1.shape[1]
+    else:
+        B, H, W, c1 = a1.shape
+    d = L.GemmDesc()
+    d.a1, d.a2, d.w = _p(a1), _p(a2), _p(w)
+    d.bias, d.rowbias, d.residual = _p(bias), _p(rowbias), _p(residual)
+    d.B, d.H, d.W, d.c1 = B, H, W, c1
+    d.c2 = 0 if a2 is None else a2.shape[-1]
+    d.N = w.shape[0]
+    d.taps, d.block_n, d.flags = taps, block_n, flags
+    if w.shape[1] != taps * (d.c1 + d.c2):
+        raise L.LdmError(f"gemm: weight K={w.shape[1]} != taps*(c1+c2)={taps * (d.c1 + d.c2)}")
+    if flags & L.LDM_GEMM_QKV_SPLIT:
+        for k_ in ("q", "k", "vt"):
+            _chk(qkv[k_], bf16, k_)
+        d.q, d.k, d.vt = _p(qkv["q"]), _p(qkv["k"]), _p(qkv["vt"])
+        d.heads, d.head_dim, d.dpad = qkv["heads"], qkv["head_dim"], qkv["dpad"]
+        d.seq, d.seq_pad = qkv["seq"], qkv["seq_pad"]
+    else:
+        _chk(out, f32 if flags & L.LDM_GEMM_OUT_F32 else bf16, "out")
+        d.out = _p(out)
+    if flags & L.LDM_GEMM_CONVT_LN_SILU:
+        g, b_, eps = ln
+        _chk(g, f32, "ln_gamma"); _chk(b_, f32, "ln_beta")
+        d.ln_gamma, d.ln_beta, d.ln_eps = _p(g), _p(b_), eps
+    L.check(L.lib().ldm_gemm_bf16(C.byref(d), _stream()), "ldm_gemm_bf16")
+    return out
+
+
+def flash_attn(q, k, vt, out, *, B, heads, seq, head_dim, dpad, seq_pad, scale):
+    for t, n in ((q, "q"), (k, "k"), (vt, "vt"), (out, "out")):
+        _chk(t, bf16, n)
+    d = L.AttnDesc()
+    d.q, d.k, d.vt, d.out = _p(q), _p(k), _p(vt), _p(out)
+    d.B, d.heads, d.seq, d.head_dim, d.dpad, d.seq_pad, d.scale = B, heads, seq, head_dim, dpad, seq_pad, scale
+    L.check(L.lib().ldm_flash_attn_fwd(C.byref(d), _stream()), "ldm_flash_attn_fwd")
+    return out
+
+
+def groupnorm(x1, gamma, beta, out, stats, *, x2=None, groups=32, eps=1e-5, silu=True):
+    _chk(x1, bf16, "x1"); _chk(x2, bf16, "x2"); _chk(gamma, f32, "gamma"); _chk(beta, f32, "beta")
+    _chk(out, bf16, "out"); _chk(stats, torch.float64, "stats")
+    B = x1.shape[0]
+    c1 = x1.shape[-1]
+    HW = x1.numel() // (B * c1)
+    d = L.GroupNormDesc()
+    d.x1, d.x2, d.gamma, d.beta, d.out, d.stats = _p(x1), _p(x2), _p(gamma), _p(beta), _p(out), _p(stats)
+    d.B, d.HW, d.c1, d.c2 = B, HW, c1, (0 if x2 is None else x2.shape[-1])
+    d.groups, d.eps, d.silu = groups, eps, int(silu)
+    if stats.numel() < B * groups * 2:
+        raise L.LdmError("groupnorm: stats scratch too small")
+    L.check(L.lib().ldm_groupnorm_silu(C.byref(d), _stream()), "ldm_groupnorm_silu")
+    return out
+
+
+def layernorm(x, gamma, beta, out, eps=1e-5):
+    _chk(x, bf16, "x"); _chk(gamma, f32, "gamma"); _chk(beta, f32, "beta"); _chk(out, bf16, "out")
+    Cc = x.shape[-1]
+    L.check(L.lib().ldm_layernorm(_p(x), _p(gamma), _p(beta), _p(out), x.numel() // Cc, Cc, eps, _stream()),
+            "ldm_layernorm")
+    return out
+
+
+def timestep_sinusoid(timesteps, t_index, freqs, out):
+    _chk(timesteps, i64, "timesteps"); _chk(t_index, i32, "t_index"); _chk(freqs, f32, "freqs"); _chk(out, f32, "out")
+    L.check(L.lib().ldm_timestep_sinusoid(_p(timesteps), _p(t_index), _p(freqs), _p(out), freqs.numel(), _stream()),
+            "ldm_timestep_sinusoid")
+    return out
+
+
+def gemv(w, x, out, bias=None, bias2=None, silu=False):
+    _chk(w, bf16, "w"); _chk(x, f32, "x"); _chk(out, f32, "out"); _chk(bias, f32, "bias"); _chk(bias2, f32, "bias2")
+    L.check(L.lib().ldm_gemv_bf16(_p(w), _p(bias), _p(bias2), _p(x), _p(out), w.shape[0], w.shape[1], int(silu),
+                                  _stream()), "ldm_gemv_bf16")
+    return out
+
+
+def conv3x3_small_cin(srcs, w, bias, out, scale=1.0):
+    """srcs: list of 1..3 f32 NCHW [B,cps,h,w]; w f32 [cout, len(srcs)*cps, 3, 3]; out bf16 NHWC [B,h,w,cout]."""
+    for s in srcs:
+        _chk(s, f32, "src")
+    _chk(w, f32, "w"); _chk(bias, f32, "bias"); _chk(out, bf16, "out")
+    B, cps, h, wd = srcs[0].shape
+    s = list(srcs) + [None] * (3 - len(srcs))
+    L.check(L.lib().ldm_conv3x3_small_cin(_p(s[0]), _p(s[1]), _p(s[2]), len(srcs), cps, scale, _p(w), _p(bias), _p(out),
+                                          B, h, wd, w.shape[0], _stream()), "ldm_conv3x3_small_cin")
+    return out
+
+
+def conv_out(x, w, bias, out):
+    """x bf16 NHWC [B,h,w,cin]; w f32 [cout,cin,3,3]; out f32 NCHW [B,cout,h,w]."""
+    _chk(x, bf16, "x"); _chk(w, f32, "w"); _chk(bias, f32, "bias"); _chk(out, f32, "out")
+    B, h, wd, cin = x.shape
+    L.check(L.lib().ldm_conv_out(_p(x), _p(w), _p(bias), _p(out), B, h, wd, cin, w.shape[0], _stream()), "ldm_conv_out")
+    return out
+
+
+def ddim_step(eps, sample, coef, t_index, prev_sample=None, pred_x0=None):
+    for t, n in ((eps, "eps"), (sample, "sample"), (coef, "coef"), (prev_sample, "prev"), (pred_x0, "x0")):
+        _chk(t, f32, n)
+    _chk(t_index, i32, "t_index")
+    L.check(L.lib().ldm_ddim_step(_p(eps), _p(sample), _p(coef), _p(t_index), _p(prev_sample), _p(pred_x0),
+                                  eps.numel(), _stream()), "ldm_ddim_step")
+
+
+def upsample_nearest(x, out):
+    _chk(x, bf16, "x"); _chk(out, bf16, "out")
+    B, h, w, Cc = x.shape
+    L.check(L.lib().ldm_upsample_nearest(_p(x), _p(out), B, h, w, Cc, out.shape[1], out.shape[2], _stream()),
+            "ldm_upsample_nearest")
+    return out
+
+
+def im2col3x3_s2(x, out):
+    _chk(x, bf16, "x"); _chk(out, bf16, "out")
+    B, h, w, Cc = x.shape
+    oh, ow = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    L.check(L.lib().ldm_im2col3x3_s2(_p(x), _p(out), B, h, w, Cc, oh, ow, _stream()), "ldm_im2col3x3_s2")
+    return out
+
+
+def logits_to_ids(logits, ids, counts, *, up, mask_th, ignore_label):
+    """logits f32 NHWC [B,h,w,C]; ids i32 [B,up*h,up*w]; counts i32 [B,2,C]."""
+    _chk(logits, f32, "logits"); _chk(ids, i32, "ids"); _chk(counts, i32, "counts")
+    B, h, w, Cc = logits.shape
+    L.check(L.lib().ldm_logits_to_ids(_p(logits), _p(ids), _p(counts), B, h, w, Cc, up, mask_th, ignore_label,
+                                      _stream()), "ldm_logits_to_ids")
+    return ids, counts
+
+
+def bilinear_up_nchw(logits, out, up):
+    _chk(logits, f32, "logits"); _chk(out, f32, "out")
+    B, h, w, Cc = logits.shape
+    L.check(L.lib().ldm_bilinear_up_nchw(_p(logits), _p(out), B, h, w, Cc, up, _stream()), "ldm_bilinear_up_nchw")
+    return out
+
+
+def segment_filter(ids, counts, cleaned, *, count_th, overlap_th, ignore_label):
+    _chk(ids, i32, "ids"); _chk(counts, i32, "counts"); _chk(cleaned, i32, "cleaned")
+    B = ids.shape[0]
+    L.check(L.lib().ldm_segment_filter(_p(ids), _p(counts), _p(cleaned), B, ids.numel() // B, counts.shape[-1],
+                                       count_th, float(overlap_th), ignore_label, _stream()), "ldm_segment_filter")
+    return cleaned
+
+
+def decode_bitmap(x, ids, quirk31=True):
+    _chk(x, f32, "x"); _chk(ids, i32, "ids")
+    B, n = x.shape[0], x.shape[1]
+    L.check(L.lib().ldm_decode_bitmap(_p(x), _p(ids), B, n, x.numel() // (B * n), int(quirk31), _stream()),
+            "ldm_decode_bitmap")
+    return ids
+
+
+def encode_bitmap(ids, x, ignore_label, fill):
+    _chk(x, f32, "x"); _chk(ids, i32, "ids")
+    B, n = x.shape[0], x.shape[1]
+    L.check(L.lib().ldm_encode_bitmap(_p(ids), _p(x), B, n, x.numel() // (B * n), ignore_label, fill, _stream()),
+            "ldm_encode_bitmap")
+    return x
+
+
+def ccl_label4(sem, target):
+    """sem i32 [B,H,W] -> (labels i32 [B,H,W], ncomp i32 [B]) numbered like scipy.ndimage.label (4-connectivity)."""
+    _chk(sem, i32, "sem")
+    B, H, W = sem.shape
+    labels = torch.empty_like(sem)
+    ncomp = torch.empty(B, dtype=i32, device=sem.device)
+    nbytes = L.lib().ldm_ccl_scratch_bytes(B, H, W)
+    scratch = torch.empty(nbytes // 4, dtype=i32, device=sem.device)
+    L.check(L.lib().ldm_ccl_label4(_p(sem), target, _p(labels), _p(ncomp), _p(scratch), B, H, W, _stream()),
+            "ldm_ccl_label4")
+    return labels, ncomp
+
+
+def joint_hist(a, b, capacity=1 << 14):
+    """Counts of distinct (a[i], b[i]) pairs. Returns (a_ids, b_ids, counts) as int64 numpy arrays sorted by
+    (a, b) -- i.e. the np.unique(a*offset+b, return_counts=True) of the reference in ascending key order."""
+    import numpy as np
+    _chk(a, i32, "a"); _chk(b, i32, "b")
+    keys = torch.empty(capacity, dtype=torch.int64, device=a.device)
+    counts = torch.empty(capacity, dtype=i32, device=a.device)
+    ovf = torch.empty(1, dtype=i32, device=a.device)
+    L.check(L.lib().ldm_joint_hist(_p(a), _p(b), a.numel(), _p(keys), _p(counts), capacity, _p(ovf), _stream()),
+            "ldm_joint_hist")
+    if int(ovf.item()) != 0:
+        if capacity >= 1 << 24:
+            raise L.LdmError("joint_hist: more than 2^24 distinct id pairs")
+        return joint_hist(a, b, capacity * 16)
+    k = keys.cpu().numpy().view(np.uint64)
+    c = counts.cpu().numpy()
+    used = k != np.uint64(L.HASH_EMPTY)
+    k, c = k[used], c[used].astype(np.int64)
+    av = (k >> np.uint64(32)).astype(np.uint32).view(np.int32).astype(np.int64)
+    bv = (k & np.uint64(0xFFFFFFFF)).astype(np.uint32).view(np.int32).astype(np.int64)
+    order = np.lexsort((bv, av))
+    return av[order], bv[order], c[order]
