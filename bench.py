@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""Benchmark of the LDMSeg sampler hot path (BASELINE.json metric: panoptic frames/sec, DDIM-50, 384x1248 KITTI).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = one pass of the hot path over one batch of 8 synthetic 384x1248 frames per GPU (configs[1]):
+noise -> 50 x (UNet, DDIM update) -> seg-AE decode -> fused argmax/threshold ids -> merge -> PQ statistics.
+Rank 0 prints ONE JSON line (see DESIGN.md "Measurement" for every field).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FRAME = (384, 1248)
+FLOP_PER_FRAME_STEP = 1597.2e9   # UNet, one DDIM step, one 384x1248 frame
+FLOP_AE_PER_FRAME = 90.4e9
+METRIC = "panoptic frames/sec (DDIM-50, 384x1248 KITTI)"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return d["hbm_gbs"], d["bf16_tflops"], d.get("bf16_tflops_sustained", d["bf16_tflops"]), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"  # B200_PROFILING.md fallback
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.lines, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------- reference arm
+class CpuReference:
+    """The reference's CPU path for this metric, bounded: the oracle (reference scheduler / seg-AE decoder / merge /
+    evaluator restated and pinned by tests/golden; UNet = restated diffusers, which is not installable here) on ONE
+    384x1248 frame. One `unet_step()` = one DDIM iteration (UNet fp32 + scheduler step); `tail()` = seg-AE decode +
+    ids/merge + PQ. frames/s is extrapolated to `ddim_steps` iterations."""
+
+    def __init__(self, ddim_steps, threads=None):
+        from oracle import ldmseg_oracle as LO
+        from oracle import unet_oracle as UO
+        self.LO = LO
+        self.threads = threads or os.cpu_count()
+        torch.set_num_threads(self.threads)
+        self.T = ddim_steps
+        h, w = FRAME[0] // 8, FRAME[1] // 8
+        self.unet = UO.build_unet(seed=0)
+        self.vae = LO.build_seg_decoder(seed=1)
+        self.sched = LO.DDIMOracle()
+        self.sched.set_timesteps_inference(ddim_steps)
+        self.rgb = 0.18215 * torch.randn((1, 4, h, w), generator=torch.Generator().manual_seed(1234))
+        self.lat = torch.randn((1, 4, h, w), generator=torch.Generator().manual_seed(42))
+        self.gt = np.random.default_rng(7).integers(0, 19, size=FRAME).astype(np.int64)
+        self.i = 0
+
+    def unet_step(self):
+        t = self.sched.timesteps[self.i % len(self.sched.timesteps)]
+        self.i += 1
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            eps = self.unet(torch.cat([self.lat, self.rgb], 1), t, encoder_hidden_states=None)
+            self.lat, _ = self.sched.step(eps, t, self.lat)
+        return time.perf_counter() - t0
+
+    def tail(self):
+        from oracle import eval_oracle as EO
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            logits = self.LO.decode_latents(self.vae, self.lat)
+            _, cleaned, _ = self.LO.logits_to_panoptic(logits[0], 0.5, 512, 0.5, 127)
+        ev = EO.CityscapesPQOracle()
+        ev.add_image(cleaned, self.gt)
+        return time.perf_counter() - t0
+
+    def describe(self, t_unet, t_tail, n):
+        return (f"1 frame 384x1248 on {self.threads} host threads: {n} of {self.T} DDIM iterations timed (UNet fp32 + "
+                f"scheduler, {t_unet:.2f} s each) + seg-AE decode + ids/merge + PQ ({t_tail:.2f} s), "
+                f"extrapolated to {self.T} iterations per frame")
+
+
+def cpu_reference_sample(ddim_steps, unet_iters=1):
+    ref = CpuReference(ddim_steps)
+    t_unet = float(np.mean([ref.unet_step() for _ in range(unet_iters)]))
+    t_tail = ref.tail()
+    return {"fps": 1.0 / (ddim_steps * t_unet + t_tail), "cores": ref.threads,
+            "sample": ref.describe(t_unet, t_tail, unet_iters)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    ref = CpuReference(args.ddim_steps)
+    t_tail = ref.tail()
+    budget_s, t_start, times = 240.0, time.perf_counter(), []
+    for i in range(args.warmup + args.steps):
+        dt = ref.unet_step()
+        if i >= args.warmup or time.perf_counter() - t_start > budget_s:
+            times.append(dt)
+        if time.perf_counter() - t_start > budget_s:  # keep the whole arm within a few minutes
+            break
+    t_unet = float(np.mean(times))
+    fps = 1.0 / (args.ddim_steps * t_unet + t_tail)
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": len(times), "warmup": args.warmup, "ms_per_step": 1e3 * t_unet, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"LDMSeg sampler, 384x1248 frames, DDIM {args.ddim_steps}, random-init UNet + seg-AE, "
+                                   "CPU reference path (oracle port: diffusers is not installable here); one step = "
+                                   "one DDIM iteration of one frame"},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": ref.threads, "kind": "port",
+                             "sample": ref.describe(t_unet, t_tail, len(times))},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch.distributed as dist
+    from video_latent_diffusion_panoptic_segmentation_b200 import _lib as L
+    from video_latent_diffusion_panoptic_segmentation_b200 import ops
+    from video_latent_diffusion_panoptic_segmentation_b200.ldmseg.evaluations import CityscapesPanopticEvaluator
+    from video_latent_diffusion_panoptic_segmentation_b200.ldmseg.trainers import TrainerDiffusion
+    from video_latent_diffusion_panoptic_segmentation_b200.ldmseg.trainers.trainers_ldm_cond import reduce_evaluator_
+    from video_latent_diffusion_panoptic_segmentation_b200.tools import main_ldm
+
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L.lib()  # fails loudly if the CUDA library is missing or the device is not sm_100
+
+    import copy
+    p = copy.deepcopy(main_ldm.BASE)
+    p["sampling_kwargs"]["num_inference_steps"] = args.ddim_steps
+    B, (H, W), T = args.frames_per_gpu, FRAME, args.ddim_steps
+    h, w = H // 8, W // 8
+    vae, unet, sched = main_ldm.build_models(p, dev, seed=0)
+    tr = TrainerDiffusion(p=p, vae_semseg=vae, unet_model=unet, noise_scheduler=sched, args={"gpu": local})
+    sched.set_timesteps_inference(T)
+    sched.move_timesteps_to(dev)
+
+    # synthetic inputs: host (pinned) copies for the e2e arm, device-resident copies for `value`
+    g = torch.Generator().manual_seed(1234 + rank)
+    rgb_host = (0.18215 * torch.randn((B, 4, h, w), generator=g)).pin_memory()
+    noise_host = torch.randn((B, 4, h, w), generator=torch.Generator().manual_seed(42)).pin_memory()
+    rng = np.random.default_rng(7 + rank)
+    gt_host = torch.from_numpy(np.stack([main_ldm._voronoi_semantic(rng, H, W) for _ in range(B)]).astype(np.int32)).pin_memory()
+    rgb_dev, noise_dev, gt_dev = rgb_host.to(dev), noise_host.to(dev), gt_host.to(dev)
+    ids_host = torch.empty((B, H, W), dtype=torch.int32).pin_memory()
+
+    evaluator = CityscapesPanopticEvaluator(device=dev)
+
+    def step(resident):
+        evaluator.reset()
+        if resident:
+            rgb, noise, gt = rgb_dev, noise_dev, gt_dev
+        else:
+            rgb, noise, gt = rgb_host.to(dev, non_blocking=True), noise_host, gt_host.to(dev, non_blocking=True)
+        lat = tr.sample([""] * B, T, seed=None, rgb_latents=rgb, scheduler=sched, noise=noise)
+        _, cleaned, _ = tr.panoptic_ids(lat)
+        for b in range(B):
+            evaluator.add_image(cleaned[b], gt[b])
+        if world > 1:
+            reduce_evaluator_(evaluator, dev)
+        res = evaluator.evaluate()
+        if not resident:
+            ids_host.copy_(cleaned, non_blocking=True)  # the panoptic ids a caller reads back
+            torch.cuda.current_stream().synchronize()
+        return res
+
+    def timed(resident, warmup, steps, sample_clocks=False):
+        for _ in range(warmup):
+            step(resident)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        cs = ClockSampler(local) if sample_clocks else None
+        if cs:
+            cs.start()
+        n0 = L.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            res = step(resident)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = cs.stop() if cs else None
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, res, L.launch_count() - n0, clocks
+
+    ms, res, eager_launches, clocks = timed(True, args.warmup, args.steps, sample_clocks=True)
+    plan = tr._loop_state(B, h, w)["plan"]
+    graph_launches = plan.launches_per_forward * T * args.steps if plan.graph is not None else 0
+    fps = world * B * args.steps / (ms / 1e3)
+    ms_e2e, _, _, _ = timed(False, 1, max(1, min(args.steps, 3)))
+    fps_e2e = world * B * max(1, min(args.steps, 3)) / (ms_e2e / 1e3)
+
+    hbm, tf_burst, tf_sus, which = peaks()
+    line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"LDMSeg sampler, batch {B} frames 384x1248 per GPU, DDIM {T} steps, random-init UNet "
+                                   "(815M, SD-1.4 topology, self-attn only) + seg-AE, bf16 storage / fp32 accumulate, "
+                                   "incl. AE decode, ids, merge, PQ stats",
+                       "frames_per_gpu": B, "ddim_steps": T, "parallelism": f"frames sharded over {world} GPU(s)",
+                       "l2": "per-step working set (weights 1.6 GB + activations) exceeds the 126 MB L2"},
+            "e2e": {"value": fps_e2e, "unit": "frames/s",
+                    "h2d_bytes_per_step": int(rgb_host.numel() * 4 + noise_host.numel() * 4 + gt_host.numel() * 4),
+                    "d2h_bytes_per_step": int(ids_host.numel() * 4)},
+            "gpu_launches": int(graph_launches + eager_launches),
+            "clocks": clocks, "pq": {k: res[k] for k in ("pq", "tp", "fp", "fn")}}
+
+    if rank == 0:
+        # roofline of the dominant kernel (gemm_tc_kernel: linear / conv1x1 / implicit conv3x3), measured live with
+        # CUDA events around every launch of one eager UNet forward
+        prof = unet.profile_plan(plan, iters=2)
+        by = {}
+        for r in prof:
+            d = by.setdefault(r["op"], {"ms": 0.0, "flops": 0, "n": 0})
+            d["ms"] += r["ms"]; d["flops"] += r["flops"]; d["n"] += 1
+        tot_ms = sum(d["ms"] for d in by.values())
+        gm = by.get("gemm", {"ms": 1e-9, "flops": 0, "n": 1})
+        ach = gm["flops"] / (gm["ms"] / 1e3) / 1e12
+        line["roofline"] = {"bound": "tensor", "kernel": "gemm_tc_kernel", "achieved": ach, "peak": tf_sus,
+                            "unit": "TFLOP/s", "frac": ach / tf_sus, "peak_source": f"{which} (sustained bf16)",
+                            "traffic": None, "launches": gm["n"],
+                            "avg_launch_us": gm["ms"] * 1e3 / max(1, gm["n"]),
+                            "share_of_unet_step": gm["ms"] / tot_ms,
+                            "whole_job_frac": fps / world * (T * FLOP_PER_FRAME_STEP + FLOP_AE_PER_FRAME) / (tf_sus * 1e12)}
+        line["breakdown_ms_per_unet_forward"] = {k: round(v["ms"], 3) for k, v in sorted(by.items(), key=lambda kv: -kv[1]["ms"])}
+        at = by.get("flash_attn")
+        if at:
+            line["attention_tflops"] = at["flops"] / (at["ms"] / 1e3) / 1e12
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                cb = cpu_reference_sample(T, unet_iters=1)
+                line["cpu_baseline"] = {"value": cb["fps"], "unit": "frames/s", "cores": cb["cores"], "kind": "port",
+                                        "sample": cb["sample"]}
+            except Exception as e:  # the checker must not take the measurement down
+                line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                                        "sample": f"failed: {e!r}"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ddim-steps", type=int, default=50)
+    ap.add_argument("--frames-per-gpu", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

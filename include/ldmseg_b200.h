@@ -207,6 +207,14 @@ int ldm_ccl_label4(const int32_t* sem, int32_t target, int32_t* labels, int32_t*
 int ldm_joint_hist(const int32_t* a, const int32_t* b, int64_t n, unsigned long long* keys, int32_t* counts,
                    int32_t capacity, int32_t* overflow, ldm_stream_t stream);
 
+/* id-map helpers of CityscapesPanopticEvaluator.add_image (cityscapes_pap_eval.py:66-110):
+ *   ldm_pan_insert: pan[i] = target*max_ins + labels[i] where sem[i] == target   (thing -> sem*max_ins + instance)
+ *   ldm_id_mask   : x[i] = fill where a[i] == va or (b != NULL and b[i] == vb)     (ignore regions -> -1)        */
+int ldm_pan_insert(const int32_t* sem, const int32_t* labels, int32_t target, int32_t max_ins, int32_t* pan,
+                   int64_t n, ldm_stream_t stream);
+int ldm_id_mask(int32_t* x, const int32_t* a, int32_t va, const int32_t* b, int32_t vb, int32_t fill, int64_t n,
+                ldm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

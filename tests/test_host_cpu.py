@@ -1,0 +1,153 @@
+"""CPU tests of the host-side logic (no kernels are launched): parameter shapes vs the oracle modules, the scheduler
+mirror's host schedule vs the reference golden fixture, modify_encoder, the cross-rank statistics reduction
+(world_size 2, gloo), and the loud failure when compute is attempted without a GPU."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from oracle import ldmseg_oracle as LO
+from oracle import unet_oracle as UO
+from video_latent_diffusion_panoptic_segmentation_b200 import _lib as L
+from video_latent_diffusion_panoptic_segmentation_b200.ldmseg.models import unet_init
+from video_latent_diffusion_panoptic_segmentation_b200.ldmseg.models.unet import UNet
+from video_latent_diffusion_panoptic_segmentation_b200.ldmseg.schedulers import DDIMNoiseScheduler
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GOLD = json.load(open(os.path.join(G, "golden.json")))
+SCHED_KW = dict(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                clip_sample=False, set_alpha_to_one=False, steps_offset=1, prediction_type="epsilon", weight="none")
+
+
+def test_unet_param_shapes_match_oracle_module():
+    cfg = dict(block_out_channels=(64, 128, 256, 256))
+    net = UO.UNetOracle(**cfg)
+    want = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    got = unet_init.unet_param_shapes(**cfg)
+    assert got == want
+    assert list(got) == list(want)  # same order as well
+
+
+def test_full_size_unet_parameter_count():
+    shapes = unet_init.unet_param_shapes(in_channels=8)
+    n = sum(int(np.prod(s)) for s in shapes.values())
+    assert abs(n - 815.4e6) < 0.5e6  # ~815.4 M with cross-attention removed and 8-ch conv_in
+
+
+def test_seg_decoder_param_shapes_match_oracle_module():
+    kw = dict(out_channels=128, int_channels=256, num_upscalers=2, upscale_channels=256)
+    dec = LO.SegDecoderOracle(**kw)
+    assert unet_init.seg_decoder_param_shapes(**kw) == {k: tuple(v.shape) for k, v in dec.state_dict().items()}
+    sd = unet_init.random_seg_decoder_state_dict(seed=3, **kw)
+    dec.load_state_dict(sd, strict=True)
+    assert sum(v.numel() for v in sd.values()) == 830848  # 0.830848 M params
+
+
+def test_scheduler_mirror_host_schedule_matches_reference():
+    s = DDIMNoiseScheduler(**SCHED_KW)
+    z = np.load(os.path.join(G, "ddim_steps.npz"))
+    assert np.array_equal(s.alphas_cumprod.numpy(), z["alphas_cumprod"])
+    for T in (10, 50):
+        s.set_timesteps_inference(T)
+        assert s.timesteps.tolist() == GOLD["scheduler"][f"timesteps_{T}"]
+    s.set_timesteps_inference(50)
+    coef = s.step_coefficients()
+    o = LO.DDIMOracle()
+    o.set_timesteps_inference(50)
+    for t in (999, 499, 19, 0):
+        assert [float(c) for c in o.coefficients(t)] == coef[t].tolist()
+    # the fused kernel's formula, evaluated with torch on the CPU, reproduces the reference's step bit for bit
+    eps, x = torch.from_numpy(z["eps"]), torch.from_numpy(z["x"])
+    for t in (999, 499, 19):
+        c = coef[t]
+        x0 = (x - c[0] * eps) / c[1]
+        prev = c[2] * x0 + c[3] * eps
+        assert np.array_equal(x0.numpy(), z[f"x0_{t}"]) and np.array_equal(prev.numpy(), z[f"prev_{t}"])
+    assert s.init_noise_sigma == 1.0 and len(s) == 1000 and s.weights.shape == (1000,)
+
+
+def test_scheduler_mirror_rejects_unbuilt_modes_and_cpu_tensors():
+    s = DDIMNoiseScheduler(**SCHED_KW)
+    s.set_timesteps_inference(10)
+    with pytest.raises(L.LdmError):
+        s.step(torch.zeros(4), 999, torch.zeros(4))  # CPU tensors: no fallback
+    s2 = DDIMNoiseScheduler(**{**SCHED_KW, "prediction_type": "v_prediction"})
+    s2.set_timesteps_inference(10)
+    with pytest.raises(NotImplementedError):
+        s2.step(torch.zeros(4), 999, torch.zeros(4))
+    with pytest.raises(NotImplementedError):
+        DDIMNoiseScheduler(beta_schedule="nope")
+
+
+def test_modify_encoder_matches_oracle():
+    cfg = dict(block_out_channels=(64, 128, 256, 256))
+    torch.manual_seed(0)
+    o = UO.UNetOracle(**cfg)
+    sd = {k: v.clone() for k, v in o.state_dict().items()}
+    m = UNet(device="cpu", **cfg)
+    m.load_state_dict(sd)
+    m.remove_cross_attention()
+    torch.manual_seed(5)
+    o.modify_encoder(in_channels=8, init_mode_seg="copy", init_mode_image="zero", cond_channels=4)
+    torch.manual_seed(5)
+    m.modify_encoder(in_channels=8, init_mode_seg="copy", init_mode_image="zero", cond_channels=4)
+    assert m.conv_in.in_channels == 12 and m.conv_in.out_channels == 64
+    assert torch.equal(m.state_dict()["conv_in.weight"], o.conv_in.weight.detach())
+    assert torch.equal(m.state_dict()["new_conv.bias"], o.conv_in.bias.detach())
+    assert bool((m.conv_in.weight[:, 4:8] == 0).all()) and torch.equal(m.conv_in.weight[:, :4], sd["conv_in.weight"])
+    assert tuple(m.config.block_out_channels) == (64, 128, 256, 256)
+
+
+def test_unet_forward_without_gpu_fails_loudly():
+    cfg = dict(block_out_channels=(64, 128, 256, 256))
+    m = UNet(device="cpu", **cfg)
+    m.load_state_dict(unet_init.random_unet_state_dict(0, in_channels=8, **cfg))
+    with pytest.raises(L.LdmError):
+        m(torch.zeros(1, 8, 8, 8), torch.tensor(999), encoder_hidden_states=None)
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(1, 8, 8, 8), torch.tensor(999), encoder_hidden_states=torch.zeros(1, 77, 768))
+
+
+def _reduce_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from video_latent_diffusion_panoptic_segmentation_b200.ldmseg.trainers.trainers_ldm_cond import reduce_evaluator_
+
+    class Ev:
+        pass
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    ev = Ev()
+    ev.TP, ev.FP, ev.FN, ev.iou_sum = 3 + rank, 10 * (rank + 1), rank, 0.1 + rank * 0.7
+    ev.TP_per_class = {11: 1 + rank, 3: 2} if rank == 0 else {11: 1 + rank, 7: 1}
+    ev.FP_per_class = {11: 4, 3: 6} if rank == 0 else {11: 5, 7: 15, 2: 1}
+    ev.FN_per_class = {11: 0, 3: 0} if rank == 0 else {11: 1, 7: 0}
+    ev.iou_sum_per_class = {11: 0.05, 3: 0.05} if rank == 0 else {11: 0.4, 7: 0.4}
+    reduce_evaluator_(ev, torch.device("cpu"))
+    q.put((rank, ev.TP, ev.FP, ev.FN, ev.iou_sum, ev.TP_per_class, ev.FP_per_class, ev.FN_per_class,
+           ev.iou_sum_per_class))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_stats_reduction_world_size_2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_reduce_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in res:
+        _, tp, fp, fn, iou, tpc, fpc, fnc, iouc = r
+        assert (tp, fp, fn) == (7, 30, 1)
+        assert iou == (0.0 + 0.1) + (0.1 + 1 * 0.7)  # summed in rank order
+        assert tpc == {3: 2, 7: 1, 11: 3}
+        assert fpc[11] == 9 and fpc[7] == 15 and fpc[3] == 6 and fpc[2] == 1
+        assert fnc == {3: 0, 7: 0, 11: 1}
+        assert iouc[11] == 0.05 + 0.4
+    assert res[0][1:] == res[1][1:]

@@ -72,6 +72,8 @@ SIGNATURES = {
     "ldm_ccl_scratch_bytes": (C.c_size_t, [c_i32, c_i32, c_i32]),
     "ldm_ccl_label4": (C.c_int, [c_vp, c_i32, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
     "ldm_joint_hist": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i32, c_vp, c_vp]),
+    "ldm_pan_insert": (C.c_int, [c_vp, c_vp, c_i32, c_i32, c_vp, c_i64, c_vp]),
+    "ldm_id_mask": (C.c_int, [c_vp, c_vp, c_i32, c_vp, c_i32, c_i32, c_i64, c_vp]),
 }
 
 _lib = None

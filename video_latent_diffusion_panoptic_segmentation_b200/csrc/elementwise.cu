@@ -9,9 +9,10 @@ using namespace ldm;
 // ---------------------------------------------------------------- DDIM update (ddim_scheduler.py:234-267)
 // Explicit round-to-nearest mul/sub/div/add intrinsics keep the reference's op order (no FMA contraction) so the
 // fp32 result is bit-identical to torch eager on the CPU.
-__global__ void ddim_step_kernel(const float* __restrict__ eps, const float* __restrict__ sample,
+// `prev` / `x0out` may alias `sample` (in-place update by the sampler loop): no __restrict__ on those.
+__global__ void ddim_step_kernel(const float* __restrict__ eps, const float* sample,
                                  const float* __restrict__ coef, const int32_t* __restrict__ t_index,
-                                 float* __restrict__ prev, float* __restrict__ x0out, long long n) {
+                                 float* prev, float* x0out, long long n) {
   const int ti = t_index ? *t_index : 0;
   const float s1m_at = coef[ti * 4 + 0];   // sqrt(1 - alpha_t)
   const float s_at = coef[ti * 4 + 1];     // sqrt(alpha_t)
@@ -20,7 +21,7 @@ __global__ void ddim_step_kernel(const float* __restrict__ eps, const float* __r
   const long long nv = n / 4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
     const float4 e = __ldg(reinterpret_cast<const float4*>(eps) + i);
-    const float4 x = __ldg(reinterpret_cast<const float4*>(sample) + i);
+    const float4 x = reinterpret_cast<const float4*>(sample)[i];
     const float ev[4] = {e.x, e.y, e.z, e.w};
     const float xv[4] = {x.x, x.y, x.z, x.w};
     float p0[4], pv[4];

@@ -359,6 +359,19 @@ __global__ void joint_hist_kernel(const int32_t* __restrict__ a, const int32_t* 
   }
 }
 
+
+// ---------------------------------------------------------------- small id-map helpers of the PQ evaluators
+__global__ void pan_insert_kernel(const int32_t* __restrict__ sem, const int32_t* __restrict__ labels, int target,
+                                  int max_ins, int32_t* __restrict__ pan, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    if (sem[i] == target) pan[i] = target * max_ins + labels[i];
+}
+__global__ void id_mask_kernel(int32_t* x, const int32_t* a, int va,
+                               const int32_t* b, int vb, int fill, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    if (a[i] == va || (b != nullptr && b[i] == vb)) x[i] = fill;
+}
+
 int grid1d(long long work, int threads, int mult = 16) {
   long long g = (work + threads - 1) / threads;
   const long long cap = (long long)ldm_host::num_sms() * mult;
@@ -467,4 +480,23 @@ extern "C" int ldm_joint_hist(const int32_t* a, const int32_t* b, int64_t n, uns
   joint_hist_kernel<<<grid1d(n, 256, 8), 256, 0, s>>>(a, b, n, keys, counts, capacity, overflow);
   count_launch(2);
   return check_launch("joint_hist_kernel");
+}
+
+extern "C" int ldm_pan_insert(const int32_t* sem, const int32_t* labels, int32_t target, int32_t max_ins, int32_t* pan,
+                              int64_t n, ldm_stream_t stream) {
+  using namespace ldm_host;
+  LDM_REQUIRE(sem && labels && pan && n > 0, LDM_ERR_BAD_ARG, "ldm_pan_insert: bad arg");
+  LDM_REQUIRE((long long)target * max_ins + n < (1ll << 31), LDM_ERR_BAD_SHAPE, "ldm_pan_insert: id overflows int32");
+  pan_insert_kernel<<<grid1d(n, 256), 256, 0, as_stream(stream)>>>(sem, labels, target, max_ins, pan, n);
+  count_launch();
+  return check_launch("pan_insert_kernel");
+}
+
+extern "C" int ldm_id_mask(int32_t* x, const int32_t* a, int32_t va, const int32_t* b, int32_t vb, int32_t fill,
+                           int64_t n, ldm_stream_t stream) {
+  using namespace ldm_host;
+  LDM_REQUIRE(x && a && n > 0, LDM_ERR_BAD_ARG, "ldm_id_mask: bad arg");
+  id_mask_kernel<<<grid1d(n, 256), 256, 0, as_stream(stream)>>>(x, a, va, b, vb, fill, n);
+  count_launch();
+  return check_launch("id_mask_kernel");
 }

@@ -1,0 +1,129 @@
+"""Shapes and random initialisation of the UNet / seg-AE parameters with the reference's state-dict key names.
+
+There is no network for the SD-1.4 checkpoint that ``UNet.from_pretrained`` loads in the reference
+(tools/main_ldm.py:147), so benchmarks and smoke tests use random weights of the same architecture
+(SD-1.4 unet/config.json with cross-attention removed). Initialisation follows torch's defaults
+(Conv/Linear: U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for weight and bias; norms: weight 1, bias 0).
+"""
+import math
+
+import torch
+
+
+def unet_param_shapes(block_out_channels=(320, 640, 1280, 1280), layers_per_block=2, in_channels=4, out_channels=4,
+                      attn_levels=(True, True, True, False), temb_mult=4):
+    """Ordered {key: shape} of diffusers' UNet2DConditionModel without attn2/norm2 (unet.py:83-105)."""
+    ch = list(block_out_channels)
+    temb = ch[0] * temb_mult
+    S = {}
+
+    def conv(name, cin, cout, k):
+        S[name + ".weight"], S[name + ".bias"] = (cout, cin, k, k), (cout,)
+
+    def lin(name, cin, cout, bias=True):
+        S[name + ".weight"] = (cout, cin)
+        if bias:
+            S[name + ".bias"] = (cout,)
+
+    def norm(name, c):
+        S[name + ".weight"], S[name + ".bias"] = (c,), (c,)
+
+    def resnet(name, cin, cout):
+        norm(name + ".norm1", cin)
+        conv(name + ".conv1", cin, cout, 3)
+        lin(name + ".time_emb_proj", temb, cout)
+        norm(name + ".norm2", cout)
+        conv(name + ".conv2", cout, cout, 3)
+        if cin != cout:
+            conv(name + ".conv_shortcut", cin, cout, 1)
+
+    def transformer(name, c):
+        norm(name + ".norm", c)
+        conv(name + ".proj_in", c, c, 1)
+        tb = name + ".transformer_blocks.0"
+        norm(tb + ".norm1", c)
+        for p in ("to_q", "to_k", "to_v"):
+            lin(f"{tb}.attn1.{p}", c, c, bias=False)
+        lin(tb + ".attn1.to_out.0", c, c)
+        norm(tb + ".norm3", c)
+        lin(tb + ".ff.net.0.proj", c, 8 * c)
+        lin(tb + ".ff.net.2", 4 * c, c)
+        conv(name + ".proj_out", c, c, 1)
+
+    conv("conv_in", in_channels, ch[0], 3)
+    lin("time_embedding.linear_1", ch[0], temb)
+    lin("time_embedding.linear_2", temb, temb)
+    prev = ch[0]
+    for i, co in enumerate(ch):
+        for j in range(layers_per_block):
+            resnet(f"down_blocks.{i}.resnets.{j}", prev if j == 0 else co, co)
+        if attn_levels[i]:
+            for j in range(layers_per_block):
+                transformer(f"down_blocks.{i}.attentions.{j}", co)
+        if i < len(ch) - 1:
+            conv(f"down_blocks.{i}.downsamplers.0.conv", co, co, 3)
+        prev = co
+    resnet("mid_block.resnets.0", ch[-1], ch[-1])
+    resnet("mid_block.resnets.1", ch[-1], ch[-1])
+    transformer("mid_block.attentions.0", ch[-1])
+    rev = ch[::-1]
+    prev = rev[0]
+    for i, co in enumerate(rev):
+        skip_in = rev[min(i + 1, len(ch) - 1)]
+        for j in range(layers_per_block + 1):
+            res_skip = skip_in if j == layers_per_block else co
+            res_in = prev if j == 0 else co
+            resnet(f"up_blocks.{i}.resnets.{j}", res_in + res_skip, co)
+        if attn_levels[::-1][i]:
+            for j in range(layers_per_block + 1):
+                transformer(f"up_blocks.{i}.attentions.{j}", co)
+        if i < len(ch) - 1:
+            conv(f"up_blocks.{i}.upsamplers.0.conv", co, co, 3)
+        prev = co
+    norm("conv_norm_out", ch[0])
+    conv("conv_out", ch[0], out_channels, 3)
+    return S
+
+
+def seg_decoder_param_shapes(out_channels=128, int_channels=256, latent_channels=4, num_upscalers=2,
+                             upscale_channels=256, **unused):
+    """decoder.* keys of GeneralVAESeg (ldmseg/models/vae.py:124-173) with num_mid_blocks=0."""
+    S = {"decoder.0.weight": (int_channels, latent_channels, 3, 3), "decoder.0.bias": (int_channels,)}
+    idx, dim = 2, upscale_channels
+    for i in range(num_upscalers):
+        cin = int_channels if i == 0 else dim
+        S[f"decoder.{idx}.weight"], S[f"decoder.{idx}.bias"] = (cin, dim, 2, 2), (dim,)       # ConvTranspose2d
+        S[f"decoder.{idx + 1}.weight"], S[f"decoder.{idx + 1}.bias"] = (dim,), (dim,)         # LayerNorm2d
+        idx += 3
+    S[f"decoder.{idx}.weight"], S[f"decoder.{idx}.bias"] = (dim,), (dim,)                     # GroupNorm
+    S[f"decoder.{idx + 2}.weight"], S[f"decoder.{idx + 2}.bias"] = (out_channels, dim, 3, 3), (out_channels,)
+    return S
+
+
+def random_state_dict(shapes, seed=0, transposed_conv_keys=()):
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for key, shape in shapes.items():
+        base = key.rsplit(".", 1)[0]
+        wshape = shapes.get(base + ".weight", shape)
+        if len(wshape) == 1:  # normalisation layer
+            sd[key] = torch.ones(shape) if key.endswith(".weight") else torch.zeros(shape)
+            continue
+        if base in transposed_conv_keys:  # ConvTranspose2d: fan_in is computed from dim 1 by torch
+            fan_in = wshape[1] * math.prod(wshape[2:])
+        else:
+            fan_in = math.prod(wshape[1:])
+        bound = 1.0 / math.sqrt(fan_in)
+        sd[key] = (torch.rand(shape, generator=g) * 2 - 1) * bound
+    return sd
+
+
+def random_unet_state_dict(seed=0, **cfg):
+    return random_state_dict(unet_param_shapes(**cfg), seed)
+
+
+def random_seg_decoder_state_dict(seed=1, **cfg):
+    shapes = seg_decoder_param_shapes(**cfg)
+    n_up = cfg.get("num_upscalers", 2)
+    tkeys = tuple(f"decoder.{2 + 3 * i}" for i in range(n_up))
+    return random_state_dict(shapes, seed, transposed_conv_keys=tkeys)

@@ -1,0 +1,269 @@
+"""B200 mirror of the SAMPLING half of ``TrainerDiffusion`` (ldmseg/trainers/trainers_ldm_cond.py):
+``sample`` (:1048-1173), ``decode_latents`` (:398-444), ``crop_padding`` (:1175-1181), ``compute_pq`` (:1184-1375),
+``compute_metrics`` (:990-1045). The training half (loss, optimiser, logging, checkpoints) is out of scope.
+
+Data flow of one batch, all on the GPU:
+  noise (CPU generator, as the reference) -> H2D
+  T x [ UNet CUDA graph (concat+cast fused into conv_in)  ->  fused DDIM update kernel ]      no host sync inside
+  seg-AE decoder (NHWC fp32 logits at 4h x 4w)
+  fused bilinear x2 + argmax + softmax-max threshold + per-class areas  ->  merge filter  ->  int32 panoptic ids
+  PQ / DVPQ statistics from joint id histograms
+"""
+from typing import Callable, List, Optional
+
+import numpy as np
+import torch
+
+from ..evaluations.cityscapes_pap_eval import CityscapesPanopticEvaluator
+from ..utils import get_world_size, is_dist_avail_and_initialized, is_main_process
+from ... import _lib as L
+from ... import ops
+
+f32, i32 = torch.float32, torch.int32
+
+
+class TrainerDiffusion:
+    def __init__(self, p: dict = None, vae_image=None, vae_semseg=None, unet_model=None, tokenizer=None,
+                 text_encoder=None, noise_scheduler=None, image_descriptor_model=None, ema_unet=None, args=None,
+                 results_folder=None, save_and_sample_every=1000, cudnn_on=False, fp16=False, ema_on=False,
+                 weight_dtype=torch.float32):
+        p = p or {}
+        self.p = p
+        self.args = args or {"gpu": torch.cuda.current_device() if torch.cuda.is_available() else 0}
+        self.vae_image, self.vae_semseg, self.unet_model = vae_image, vae_semseg, unet_model
+        self.noise_scheduler = noise_scheduler
+        if image_descriptor_model is not None or text_encoder is not None:
+            raise NotImplementedError("image descriptors / text encoders imply cross-attention, which is removed on "
+                                      "the default path (base.yaml:71); SURVEY section 8(f) rank 4")
+        self.image_descriptor_model, self.textencoder, self.tokenizer = None, None, None
+        ek = p.get("eval_kwargs", {})
+        self.mask_th = ek.get("mask_th", 0.5)
+        self.count_th = ek.get("count_th", 512)
+        self.overlap_th = ek.get("overlap_th", 0.5)
+        tk = p.get("train_kwargs", {})
+        self.self_condition = bool(tk.get("self_condition", False))
+        self.ignore_label = p.get("ignore_label", 127)
+        self.num_classes = p.get("num_classes", 128)
+        self.fp16_scaler = None
+        self.weight_dtype = weight_dtype
+        self.unet_dtype = torch.float32
+        self.latent_size = p.get("latent_size", None)
+        self.dl_val = None
+        self.best_pq = 0.0
+        self.last_results = None
+        self.device = torch.device("cuda", self.args["gpu"]) if isinstance(self.args["gpu"], int) else torch.device(
+            self.args["gpu"])
+        self._loop = {}
+
+    # ------------------------------------------------------------------ sample (:1048-1173)
+    def _loop_state(self, B, h, w):
+        """Static buffers + UNet plan for the DDIM loop at this shape (built once, reused for every batch)."""
+        key = (B, h, w, self.self_condition)
+        st = self._loop.get(key)
+        if st is None:
+            dev = self.device
+            st = {"latents": torch.empty((B, 4, h, w), dtype=f32, device=dev),
+                  "rgb": torch.empty((B, 4, h, w), dtype=f32, device=dev)}
+            parts = [st["latents"], st["rgb"]]
+            if self.self_condition:
+                st["cond"] = torch.zeros((B, 4, h, w), dtype=f32, device=dev)
+                parts.append(st["cond"])
+            st["plan"] = self.unet_model._get_plan(B, h, w, 4 * len(parts), parts=parts)
+            self._loop[key] = st
+        return st
+
+    @torch.no_grad()
+    def sample(self, prompts: List[str], num_inference_steps: int = 50, guidance_scale: float = 7.5,
+               seed: Optional[int] = None, rgb_latents: Optional[torch.Tensor] = None,
+               return_all_latents: bool = False, disable_progress_bar: bool = False,
+               rgb_images: Optional[torch.Tensor] = None, scheduler: Optional[Callable] = None,
+               repeat_noise: Optional[bool] = None, noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if scheduler is None:
+            scheduler = self.noise_scheduler
+            scheduler.set_timesteps_inference(num_inference_steps)
+        if rgb_latents is None:
+            raise NotImplementedError("unconditional sampling (rgb_latents=None) is not on the eval path")
+        if repeat_noise is None:
+            repeat_noise = False
+        batch_size = len(prompts) if prompts is not None else rgb_latents.shape[0]
+        dev = self.device
+        h, w = rgb_latents.shape[-2:]  # the reference's (latent_size, latent_size) generalised
+        if noise is None:
+            rng_generator = torch.Generator().manual_seed(seed) if seed is not None else None
+            noise = torch.randn((batch_size, 4, h, w), generator=rng_generator)  # CPU generator, as :1091-1094
+        if repeat_noise:
+            noise = noise[0:1].repeat(batch_size, 1, 1, 1)
+        st = self._loop_state(batch_size, h, w)
+        latents, plan = st["latents"], st["plan"]
+        latents.copy_(noise.to(dev, non_blocking=True))           # H2D (:1095)
+        if scheduler.init_noise_sigma != 1.0:
+            latents.mul_(scheduler.init_noise_sigma)
+        original_noise = latents.clone() if repeat_noise else None
+        st["rgb"].copy_(rgb_latents.to(dev, f32))
+        if self.self_condition:
+            st["cond"].zero_()
+        timesteps = scheduler.timesteps.to(dev)
+        coef = scheduler.coef_table(dev)
+        unet = self.unet_model
+        all_latents = []
+        n = timesteps.numel()
+        for i in range(n):
+            t = timesteps[i:i + 1]
+            plan.timestep.copy_(t)                                  # device-side timestep: no host sync in the loop
+            if plan.graph is not None:
+                plan.graph.replay()                                 # UNet (:1143-1144), concat fused into conv_in
+            else:
+                unet._run_plan(plan)
+            t_index = t.view(torch.int32)[:1]
+            last = i == n - 1
+            # DDIM update (:1152-1162): prev_sample, or pred_original_sample on the last step, written in place
+            ops.ddim_step(plan.out, latents, coef, t_index,
+                          prev_sample=None if last else latents,
+                          pred_x0=latents if last else (st["cond"] if self.self_condition else None))
+            if return_all_latents:
+                all_latents.append(latents.clone())
+        if return_all_latents:
+            return torch.cat(all_latents, dim=0)
+        out = latents.clone()
+        if repeat_noise:
+            return out, original_noise
+        return out
+
+    # ------------------------------------------------------------------ decode_latents (:398-444)
+    @torch.no_grad()
+    def decode_latents(self, latents, return_logits=False, threshold_output=False, rgb_latents=None,
+                       weight_dtype=torch.float32):
+        logits = self.vae_semseg.decode_nhwc(latents, scale=1.0 / self.vae_semseg.scaling_factor)
+        up = self.vae_semseg.interpolation_factor
+        B, H, W, C = logits.shape
+        if return_logits:
+            images = torch.empty((B, C, H * up, W * up), dtype=f32, device=logits.device)
+            ops.bilinear_up_nchw(logits, images, up)
+            return images
+        ids = torch.empty((B, H * up, W * up), dtype=i32, device=logits.device)
+        counts = torch.empty((B, 2, C), dtype=i32, device=logits.device)
+        ops.logits_to_ids(logits, ids, counts, up=up, mask_th=self.mask_th if threshold_output else -1.0,
+                          ignore_label=self.ignore_label)
+        return ids.cpu().numpy()
+
+    @torch.no_grad()
+    def panoptic_ids(self, latents):
+        """Fused tail (:1255-1325 with identity resizes): latents -> (ids before the merge, cleaned ids with -1 = void,
+        per-class [argmax area, sigmoid area]) as int32 device tensors."""
+        logits = self.vae_semseg.decode_nhwc(latents, scale=1.0 / self.vae_semseg.scaling_factor)
+        up = self.vae_semseg.interpolation_factor
+        B, H, W, C = logits.shape
+        ids = torch.empty((B, H * up, W * up), dtype=i32, device=logits.device)
+        counts = torch.empty((B, 2, C), dtype=i32, device=logits.device)
+        ops.logits_to_ids(logits, ids, counts, up=up, mask_th=self.mask_th, ignore_label=self.ignore_label)
+        cleaned = torch.empty_like(ids)
+        ops.segment_filter(ids, counts, cleaned, count_th=self.count_th, overlap_th=self.overlap_th,
+                           ignore_label=self.ignore_label)
+        return ids, cleaned, counts
+
+    def crop_padding(self, prediction, padding_mask):
+        co = padding_mask.nonzero()
+        y0, y1 = co[:, 0].min(), co[:, 0].max()
+        x0, x1 = co[:, 1].min(), co[:, 1].max()
+        return prediction[:, y0:y1 + 1, x0:x1 + 1]
+
+    # ------------------------------------------------------------------ compute_pq (:1184-1375)
+    @torch.no_grad()
+    def compute_pq(self, num_inference_steps=50, guidance_scale=7.5, seed=None, threshold_output=True,
+                   save_images=False, max_iter=None, dataloader=None, threshold_mode="max", save_model=False):
+        """`dataloader` yields dicts with 'rgb_latents' [B,4,h,w] (the RGB-VAE encode is the step before this path,
+        SURVEY section 8(f) rank 1), 'semseg' [B,H,W] ground-truth labels, optional 'mask' [B,H,W] and 'meta'."""
+        if threshold_mode != "max" or not threshold_output:
+            raise NotImplementedError("only threshold_mode='max' with threshold_output=True is built")
+        if is_main_process():
+            print("Computing PQ metric for Cityscapes ...")
+        dataloader = dataloader if dataloader is not None else self.dl_val
+        thing_ids = {11, 12, 13, 14, 15, 16, 17, 18}
+        evaluator = CityscapesPanopticEvaluator(thing_ids=thing_ids, device=self.device)
+        evaluator.reset()
+        scheduler = self.noise_scheduler
+        scheduler.set_timesteps_inference(num_inference_steps=num_inference_steps)
+        scheduler.move_timesteps_to(self.device)
+        all_cleaned = []
+        for batch_idx, data in enumerate(dataloader):
+            rgb_latents = data["rgb_latents"].to(self.device)
+            gt_semseg = data["semseg"].to(self.device)
+            B = rgb_latents.shape[0]
+            latents = self.sample([""] * B, num_inference_steps, guidance_scale, seed, rgb_latents=rgb_latents,
+                                  scheduler=scheduler, disable_progress_bar=True)
+            ids, cleaned, _ = self.panoptic_ids(latents)
+            H, W = cleaned.shape[-2:]
+            if tuple(gt_semseg.shape[-2:]) != (H, W):
+                raise NotImplementedError("non-identity resize to meta.im_size / padding crop (:1264-1284) is not built")
+            if "mask" in data and not bool(data["mask"].to(torch.bool).all()):
+                raise NotImplementedError("padding-mask crop (:1175-1181,1276) is not built (synthetic masks are all ones)")
+            for b in range(B):
+                evaluator.add_image(cleaned[b], gt_semseg[b])
+            all_cleaned.append(cleaned)
+            if max_iter is not None and batch_idx > max_iter:
+                break
+        self.last_cleaned = all_cleaned
+        # the reference never reduces PQ across ranks; with a process group we all-reduce the
+        # integer statistics exactly and gather the float64 IoU sums in rank order
+        if is_dist_avail_and_initialized() and get_world_size() > 1:
+            reduce_evaluator_(evaluator, self.device)
+        results = evaluator.evaluate()
+        self.last_results = results
+        if is_main_process():
+            print(f"Panoptic Quality (PQ): {results['pq']:.2f}")
+            print(f"Segmentation Quality (SQ): {results['sq']:.2f}")
+            print(f"Recognition Quality (RQ): {results['rq']:.2f}")
+            if "thing_pq" in results:
+                print(f"Things PQ: {results['thing_pq']:.2f}")
+                print(f"Stuff PQ: {results['stuff_pq']:.2f}")
+        return
+
+    @torch.no_grad()
+    def compute_metrics(self, metrics=("pq",), threshold_output=True, save_images=False, seed=None, max_iter=None,
+                        dataloader=None, models_to_eval=None, num_inference_steps=50, **kwargs):
+        for m in metrics:
+            if m != "pq":
+                raise NotImplementedError(f"metric {m} is not on the sampling path")
+            self.compute_pq(num_inference_steps=num_inference_steps, seed=seed, threshold_output=threshold_output,
+                            save_images=save_images, max_iter=max_iter, dataloader=dataloader)
+        if is_dist_avail_and_initialized():
+            torch.distributed.barrier()
+        return self.last_results
+
+
+def reduce_evaluator_(evaluator, device):
+    """Cross-rank reduction of a CityscapesPanopticEvaluator (pattern: SemsegMeter.synchronize_between_processes,
+    ldmseg/evaluations/semseg_evaluation.py:59-70). Integers (TP/FP/FN, per class) are all-reduced exactly; the
+    float64 IoU sums are all-gathered and added in rank order so the result does not depend on reduction order."""
+    import torch.distributed as dist
+    backend_dev = device if dist.get_backend() == "nccl" else torch.device("cpu")
+    ncls = 256
+    ints = torch.zeros((3, ncls + 1), dtype=torch.int64, device=backend_dev)
+    ious = torch.zeros((ncls + 1,), dtype=torch.float64, device=backend_dev)
+    seen = torch.zeros((ncls,), dtype=torch.int64, device=backend_dev)
+    ints[0, ncls], ints[1, ncls], ints[2, ncls] = evaluator.TP, evaluator.FP, evaluator.FN
+    ious[ncls] = evaluator.iou_sum
+    for c, v in evaluator.TP_per_class.items():
+        ints[0, c] = v
+        seen[c] = 1
+    for c, v in evaluator.FP_per_class.items():
+        ints[1, c] = v
+    for c, v in evaluator.FN_per_class.items():
+        ints[2, c] = v
+    for c, v in evaluator.iou_sum_per_class.items():
+        ious[c] = v
+    dist.all_reduce(ints, op=dist.ReduceOp.SUM)
+    dist.all_reduce(seen, op=dist.ReduceOp.SUM)
+    gathered = [torch.zeros_like(ious) for _ in range(dist.get_world_size())]
+    dist.all_gather(gathered, ious)
+    tot = torch.zeros_like(ious)
+    for g in gathered:  # rank order
+        tot = tot + g
+    ints, tot, seen = ints.cpu(), tot.cpu(), seen.cpu()
+    evaluator.TP, evaluator.FP, evaluator.FN = int(ints[0, ncls]), int(ints[1, ncls]), int(ints[2, ncls])
+    evaluator.iou_sum = float(tot[ncls])
+    evaluator.TP_per_class = {c: int(ints[0, c]) for c in range(ncls) if seen[c] > 0}
+    evaluator.FP_per_class = {c: int(ints[1, c]) for c in range(ncls) if seen[c] > 0 or ints[1, c] > 0}
+    evaluator.FN_per_class = {c: int(ints[2, c]) for c in range(ncls) if seen[c] > 0}
+    evaluator.iou_sum_per_class = {c: float(tot[c]) for c in range(ncls) if seen[c] > 0}
+    return evaluator

@@ -237,3 +237,16 @@ def joint_hist(a, b, capacity=1 << 14):
     bv = (k & np.uint64(0xFFFFFFFF)).astype(np.uint32).view(np.int32).astype(np.int64)
     order = np.lexsort((bv, av))
     return av[order], bv[order], c[order]
+
+
+def pan_insert(sem, labels, target, max_ins, pan):
+    _chk(sem, i32, "sem"); _chk(labels, i32, "labels"); _chk(pan, i32, "pan")
+    L.check(L.lib().ldm_pan_insert(_p(sem), _p(labels), target, max_ins, _p(pan), sem.numel(), _stream()),
+            "ldm_pan_insert")
+    return pan
+
+
+def id_mask(x, a, va, b=None, vb=0, fill=-1):
+    _chk(x, i32, "x"); _chk(a, i32, "a"); _chk(b, i32, "b")
+    L.check(L.lib().ldm_id_mask(_p(x), _p(a), va, _p(b), vb, fill, x.numel(), _stream()), "ldm_id_mask")
+    return x
