@@ -273,6 +273,9 @@ def run_ours(args):
         # roofline of the dominant kernel (gemm_tc_kernel: linear / conv1x1 / implicit conv3x3), measured live with
         # CUDA events around every launch of one eager UNet forward
         prof = unet.profile_plan(plan, iters=2)
+        if args.profile_out:
+            with open(args.profile_out, "w") as f:
+                json.dump(prof, f, default=str)
         by = {}
         for r in prof:
             d = by.setdefault(r["op"], {"ms": 0.0, "flops": 0, "n": 0})
@@ -313,6 +316,7 @@ def main():
     ap.add_argument("--ddim-steps", type=int, default=50)
     ap.add_argument("--frames-per-gpu", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-out", default=None, help="write the per-launch CUDA-event profile of one UNet forward")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

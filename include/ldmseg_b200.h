@@ -57,6 +57,8 @@ enum ldm_gemm_flags {
                                /* out[rows, N/2] = value * gelu_erf(gate)   (diffusers GEGLU)                  */
   LDM_GEMM_QKV_SPLIT = 1 << 2, /* N = 3*heads*head_dim; scatter to q/k [B*heads, seq, dpad], vt [B*heads, d, seq_pad] */
   LDM_GEMM_SILU = 1 << 3,      /* out = silu(acc + bias ...)                                                   */
+  LDM_GEMM_OUT_NCHW_F32 = 1 << 5, /* out is planar f32 [B, n_store, H, W] (UNet conv_out, unet.py:431): only the first
+                                     n_store (<= N) output channels are stored; weights may be zero-padded to N % 8 == 0 */
   LDM_GEMM_CONVT_LN_SILU = 1 << 4 /* N = 4*Cout: ConvTranspose2d(k2,s2) pixel-shuffle + LayerNorm2d + SiLU
                                      (vae.py:156-158,310-323); block_n must equal Cout (<= 256)               */
 };
@@ -82,6 +84,8 @@ typedef struct ldm_gemm_desc {
   int32_t block_n;      /* 0 = choose; else multiple of 32 in [32,256]                           */
   int32_t flags;
   int32_t heads, head_dim, dpad, seq, seq_pad; /* QKV_SPLIT geometry (seq = tokens per image)    */
+  int32_t vt_rows;      /* rows per head of vt (ldm_attn_vt_rows(head_dim)); 0 = head_dim         */
+  int32_t n_store;      /* OUT_NCHW_F32: channels stored (0 = N)                                 */
 } ldm_gemm_desc;
 
 int ldm_gemm_bf16(const ldm_gemm_desc* d, ldm_stream_t stream);
@@ -91,7 +95,9 @@ int ldm_gemm_bf16(const ldm_gemm_desc* d, ldm_stream_t stream);
  * Replaces: diffusers Attention / AttnProcessor2_0 (F.scaled_dot_product_attention) in BasicTransformerBlock.attn1
  * (cross-attention removed by ldmseg/models/unet.py:83-105).
  *   q, k : bf16 [B*heads, seq, dpad]   (dpad = 64*ceil(d/64), columns >= d are zero)
- *   vt   : bf16 [B*heads, d, seq_pad]  (V transposed; seq_pad % 8 == 0)
+ *   vt   : bf16 [B*heads, vt_rows, seq_pad]  (V transposed; seq_pad % 8 == 0; vt_rows = ldm_attn_vt_rows(d) =
+ *          16*ceil(d/16); when d % 16 != 0 row d of every head must hold 1.0 for the valid keys and rows > d zero:
+ *          the P.V MMA then also yields the softmax row sums)
  *   out  : bf16 [B*seq, heads*d]
  * ---------------------------------------------------------------------------------------------------------- */
 typedef struct ldm_attn_desc {
@@ -99,9 +105,11 @@ typedef struct ldm_attn_desc {
   const void* k;
   const void* vt;
   void* out;
-  int32_t B, heads, seq, head_dim, dpad, seq_pad;
+  int32_t B, heads, seq, head_dim, dpad, seq_pad, vt_rows;
   float scale; /* head_dim^-0.5 */
 } ldm_attn_desc;
+
+int ldm_attn_vt_rows(int head_dim);
 
 int ldm_flash_attn_fwd(const ldm_attn_desc* d, ldm_stream_t stream);
 
@@ -109,7 +117,8 @@ int ldm_flash_attn_fwd(const ldm_attn_desc* d, ldm_stream_t stream);
  * GroupNorm (+ optional SiLU) over the channel concatenation of x1 (c1) and x2 (c2), NHWC bf16.
  * Replaces: torch.nn.GroupNorm + SiLU in ResnetBlock2D.norm1/norm2, Transformer2DModel.norm,
  * UNet.conv_norm_out (unet.py:428-430), seg-AE decoder GroupNorm (vae.py:163-164).
- * stats: caller-provided scratch, f64 [B, groups, 2], zeroed by the call.
+ * stats: caller-provided scratch of ldm_groupnorm_scratch_bytes(B, groups) bytes (per-chunk partial moments; the
+ * reduction order is fixed, so results are bit-reproducible run to run).
  * ---------------------------------------------------------------------------------------------------------- */
 typedef struct ldm_groupnorm_desc {
   const void* x1;
@@ -117,12 +126,13 @@ typedef struct ldm_groupnorm_desc {
   const float* gamma;
   const float* beta;
   void* out;     /* bf16 [B, HW, c1+c2] */
-  double* stats; /* [B, groups, 2] */
+  void* stats;   /* scratch, ldm_groupnorm_scratch_bytes(B, groups) bytes */
   int32_t B, HW, c1, c2, groups;
   float eps;
   int32_t silu;
 } ldm_groupnorm_desc;
 
+size_t ldm_groupnorm_scratch_bytes(int32_t B, int32_t groups);
 int ldm_groupnorm_silu(const ldm_groupnorm_desc* d, ldm_stream_t stream);
 
 /* LayerNorm over the last dim of bf16 [rows, C] (BasicTransformerBlock.norm1 / norm3). */

@@ -84,7 +84,7 @@ def check_groupnorm(c1=320, c2=0, HW=468, B=2, silu=True, eps=1e-5):
     C = c1 + c2
     g, b = _randn((C,), 8) * 0.2 + 1, _randn((C,), 9) * 0.1
     out = torch.empty((B, HW, C), dtype=bf16, device=DEV)
-    stats = torch.empty(B * 32 * 2, dtype=torch.float64, device=DEV)
+    stats = ops.gn_scratch(B, 32, DEV)
     ops.groupnorm(x1, g, b, out, stats, x2=x2, groups=32, eps=eps, silu=silu)
     xin = x1 if x2 is None else torch.cat([x1, x2], dim=-1)
     ref = F.group_norm(xin.float().permute(0, 2, 1), 32, g, b, eps)
@@ -147,6 +147,21 @@ def check_conv_out():
     ops.conv_out(x, wt, bias, out)
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt, bias, padding=1)
     return _stats(out, ref, "conv_out", 2e-3, 1e-3)
+
+
+def check_gemm_conv_out_nchw():
+    B, h, w, cin = 2, 12, 39, 320
+    x = _randn((B, h, w, cin), 21, dtype=bf16)
+    wt, bias = _randn((4, cin, 3, 3), 22, 0.05), _randn((4,), 23)
+    wp = torch.zeros((8, 9 * cin), device=DEV)
+    wp[:4] = wt.permute(0, 2, 3, 1).reshape(4, -1)
+    bp = torch.zeros(8, device=DEV)
+    bp[:4] = bias
+    out = torch.full((B, 4, h, w), float("nan"), device=DEV)
+    ops.gemm(x, wp.to(bf16), out, taps=9, bias=bp, flags=L.LDM_GEMM_OUT_NCHW_F32, block_n=32, n_store=4)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wp[:4].to(bf16).float().view(4, 3, 3, cin).permute(0, 3, 1, 2), bias,
+                   padding=1)
+    return _stats(out, ref, "conv_out via implicit GEMM (NCHW f32)", 2e-3, 1e-3)
 
 
 def check_upsample_im2col():
@@ -263,12 +278,8 @@ def check_gemm_geglu():
 
 
 def _alloc_qkv(B, heads, seq, d):
-    dpad = ((d + 63) // 64) * 64
-    seq_pad = ((seq + 7) // 8) * 8
-    q = torch.zeros((B * heads, seq, dpad), dtype=bf16, device=DEV)
-    k = torch.zeros_like(q)
-    vt = torch.zeros((B * heads, d, seq_pad), dtype=bf16, device=DEV)
-    return q, k, vt, dpad, seq_pad
+    q = ops.alloc_qkv(B, heads, seq, d, DEV)
+    return q["q"], q["k"], q["vt"], q["dpad"], q["seq_pad"]
 
 
 def check_gemm_qkv(B=2, heads=8, d=40, seq=300):
@@ -282,10 +293,12 @@ def check_gemm_qkv(B=2, heads=8, d=40, seq=300):
     qr = ref[:, :, 0].permute(0, 2, 1, 3).reshape(B * heads, seq, d)
     kr = ref[:, :, 1].permute(0, 2, 1, 3).reshape(B * heads, seq, d)
     vr = ref[:, :, 2].permute(0, 2, 3, 1).reshape(B * heads, d, seq)
+    if vt.shape[1] != d:  # ones row (softmax row sums come out of the PV MMA) + zero rows must be untouched
+        assert float((vt[:, d, :seq] - 1).abs().max()) == 0.0 and float(vt[:, d + 1:].abs().max()) == 0.0
     _stats(q[:, :, :d], qr, "qkv q", 3e-2, 1e-2)
     _stats(k[:, :, :d], kr, "qkv k", 3e-2, 1e-2)
     assert float(q[:, :, d:].abs().max()) == 0.0, "q padding overwritten"
-    return _stats(vt[:, :, :seq], vr, f"qkv vt d={d}", 3e-2, 1e-2)
+    return _stats(vt[:, :d, :seq], vr, f"qkv vt d={d}", 3e-2, 1e-2)
 
 
 def check_gemm_convt():
@@ -315,7 +328,7 @@ def check_attention(B=1, heads=2, d=40, seq=300):
     vf = _randn((B * heads, seq, d), 57, 1.0, bf16)
     q[:, :, :d] = qf
     k[:, :, :d] = kf
-    vt[:, :, :seq] = vf.transpose(1, 2)
+    vt[:, :d, :seq] = vf.transpose(1, 2)
     out = torch.empty((B * seq, heads * d), dtype=bf16, device=DEV)
     ops.flash_attn(q, k, vt, out, B=B, heads=heads, seq=seq, head_dim=d, dpad=dpad, seq_pad=seq_pad, scale=d ** -0.5)
     ref = F.scaled_dot_product_attention(qf.float(), kf.float(), vf.float())  # [BH, seq, d]
@@ -433,6 +446,7 @@ CHECKS = {
     "timestep_sinusoid": check_timestep_sinusoid,
     "conv_small_cin": check_conv_small_cin,
     "conv_out": check_conv_out,
+    "gemm_conv_out_nchw": check_gemm_conv_out_nchw,
     "upsample_im2col": check_upsample_im2col,
     "gemm_tiny": check_gemm_tiny,
     "gemm_plain_320": check_gemm_plain,

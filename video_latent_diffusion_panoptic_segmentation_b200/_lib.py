@@ -16,6 +16,7 @@ LDM_GEMM_GEGLU = 1 << 1
 LDM_GEMM_QKV_SPLIT = 1 << 2
 LDM_GEMM_SILU = 1 << 3
 LDM_GEMM_CONVT_LN_SILU = 1 << 4
+LDM_GEMM_OUT_NCHW_F32 = 1 << 5
 
 HASH_EMPTY = 0x8000000000000000
 
@@ -28,6 +29,7 @@ class GemmDesc(C.Structure):
         ("B", c_i32), ("H", c_i32), ("W", c_i32), ("c1", c_i32), ("c2", c_i32), ("N", c_i32), ("taps", c_i32),
         ("block_n", c_i32), ("flags", c_i32),
         ("heads", c_i32), ("head_dim", c_i32), ("dpad", c_i32), ("seq", c_i32), ("seq_pad", c_i32),
+        ("vt_rows", c_i32), ("n_store", c_i32),
     ]
 
 
@@ -35,7 +37,7 @@ class AttnDesc(C.Structure):
     _fields_ = [
         ("q", c_vp), ("k", c_vp), ("vt", c_vp), ("out", c_vp),
         ("B", c_i32), ("heads", c_i32), ("seq", c_i32), ("head_dim", c_i32), ("dpad", c_i32), ("seq_pad", c_i32),
-        ("scale", c_f32),
+        ("vt_rows", c_i32), ("scale", c_f32),
     ]
 
 
@@ -54,7 +56,9 @@ SIGNATURES = {
     "ldm_launch_count": (C.c_longlong, []),
     "ldm_gemm_bf16": (C.c_int, [C.POINTER(GemmDesc), c_vp]),
     "ldm_flash_attn_fwd": (C.c_int, [C.POINTER(AttnDesc), c_vp]),
+    "ldm_attn_vt_rows": (C.c_int, [C.c_int]),
     "ldm_groupnorm_silu": (C.c_int, [C.POINTER(GroupNormDesc), c_vp]),
+    "ldm_groupnorm_scratch_bytes": (C.c_size_t, [c_i32, c_i32]),
     "ldm_layernorm": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_f32, c_vp]),
     "ldm_timestep_sinusoid": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i32, c_vp]),
     "ldm_gemv_bf16": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),

@@ -8,8 +8,9 @@
 //                                        PV MMA); O is accumulated in registers from the per-block O_part so no
 //                                        TMEM read-modify-write rescale is needed.
 //   With NQ = 2 the tensor core computes group B's S / PV while group A is in its softmax.
-//   Layouts: q,k [B*heads, seq, dpad] (dpad = 64*ceil(d/64), zero padded), vt [B*heads, d, seq_pad] (V transposed so
-//   that both MMAs see K-major operands), out [B*seq, heads*d]; all bf16.
+//   Layouts: q,k [B*heads, seq, dpad] (dpad = 64*ceil(d/64), zero padded), vt [B*heads, vt_rows, seq_pad] (V transposed
+//   so that both MMAs see K-major operands; vt_rows = 16*ceil(d/16); when d % 16 != 0 the caller keeps row d of every
+//   head at 1.0 so the PV MMA also produces the softmax row sums), out [B*seq, heads*d]; all bf16.
 #include "common.cuh"
 #include "host_util.h"
 
@@ -33,6 +34,7 @@ struct AttnCfg {
   static constexpr int kAtoms = (D + 63) / 64;         // 64-wide K atoms of Q / K tiles
   static constexpr int kSteps = (D + 15) / 16;         // UMMA k-steps for S = Q K^T
   static constexpr int kDN = ((D + 15) / 16) * 16;     // UMMA N for O = P V
+  static constexpr bool kOnesRow = (D % 16) != 0;      // spare V^T row D holds ones -> O_part[:, D] = row sum of P
   static constexpr int kQBytes = kAtoms * 128 * 128;   // per group
   static constexpr int kKBytes = kAtoms * BKV * 128;
   static constexpr int kVAtoms = BKV / 64;
@@ -196,35 +198,40 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 #pragma unroll
     for (int i = 0; i < Cfg::kDN; ++i) o_acc[i] = 0.f;
     float m = -INFINITY, l = 0.f;
+    constexpr bool kOnes = Cfg::kOnesRow;  // row sums come out of the PV MMA (ones row of V^T at index D)
 
+    // O_acc = (O_acc + O_part) * alpha; all TMEM loads are issued before the single wait
     auto add_o_part = [&](float alpha) {
+      uint32_t v[Cfg::kDN];
 #pragma unroll
-      for (int c = 0; c < Cfg::kDN; c += 16) {
-        uint32_t v[16];
-        tmem_ld16(t_o + c, v);
-        tmem_ld_wait();
+      for (int c = 0; c < Cfg::kDN; c += 16) tmem_ld16(t_o + c, v + c);
+      tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) o_acc[c + i] = (o_acc[c + i] + __uint_as_float(v[i])) * alpha;
-      }
+      for (int i = 0; i < Cfg::kDN; ++i) o_acc[i] = (o_acc[i] + __uint_as_float(v[i])) * alpha;
     };
 
     for (int j = 0; j < nblk; ++j) {
-      const int kv0 = j * BKV;
-      const int nvalid = p.seq - kv0;  // keys of this block inside the sequence (>= 1)
+      const int nvalid = p.seq - j * BKV;  // keys of this block inside the sequence (>= 1)
       mbar_wait(&s_full[g], j & 1);
       tc_fence_after();
-      float mx = -INFINITY;
+      uint32_t sv[BKV];  // the whole score row of this block stays in registers: one TMEM pass
 #pragma unroll
-      for (int c = 0; c < BKV; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(t_s + c, v);
-        tmem_ld_wait();
+      for (int c = 0; c < BKV; c += 32) tmem_ld32(t_s + c, sv + c);
+      tmem_ld_wait();
+      if (nvalid < BKV) {  // only the last block of a ragged sequence
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float s = (c + i < nvalid) ? __uint_as_float(v[i]) : -INFINITY;
-          mx = fmaxf(mx, s);
-        }
+        for (int i = 0; i < BKV; ++i)
+          if (i >= nvalid) sv[i] = 0xff800000u;  // -inf
       }
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < BKV; i += 4) {
+        mx0 = fmaxf(mx0, __uint_as_float(sv[i]));
+        mx1 = fmaxf(mx1, __uint_as_float(sv[i + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(sv[i + 2]));
+        mx3 = fmaxf(mx3, __uint_as_float(sv[i + 3]));
+      }
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
       const float m_new = fmaxf(m, mx * p.scale_log2);
       const float alpha = ex2(m - m_new);
       if (j > 0) {
@@ -232,33 +239,28 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         tc_fence_after();
         add_o_part(alpha);
       }
-      l *= alpha;
+      if (!kOnes) l *= alpha;
       m = m_new;
+      float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-      for (int c = 0; c < BKV; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(t_s + c, v);
-        tmem_ld_wait();
-        float pv[32];
+      for (int c = 0; c < BKV; c += 8) {
+        float e[8];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float e = ex2(fmaf(__uint_as_float(v[i]), p.scale_log2, -m));
-          pv[i] = (c + i < nvalid) ? e : 0.f;
-          l += pv[i];
+        for (int i = 0; i < 8; ++i) e[i] = ex2(fmaf(__uint_as_float(sv[c + i]), p.scale_log2, -m));
+        if (!kOnes) {
+          l0 += (e[0] + e[1]) + (e[2] + e[3]);
+          l1 += (e[4] + e[5]) + (e[6] + e[7]);
         }
+        uint4 u;
+        u.x = pack_bf16(e[0], e[1]);
+        u.y = pack_bf16(e[2], e[3]);
+        u.z = pack_bf16(e[4], e[5]);
+        u.w = pack_bf16(e[6], e[7]);
         // row r of the K-major SWIZZLE_128B tile: 16-byte chunk index XOR (r & 7)
         uint8_t* rowp = myP + (c >> 6) * (128 * 128) + r * 128;
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const int chunk = ((c & 63) >> 3) + q4;
-          uint4 u;
-          u.x = pack_bf16(pv[q4 * 8 + 0], pv[q4 * 8 + 1]);
-          u.y = pack_bf16(pv[q4 * 8 + 2], pv[q4 * 8 + 3]);
-          u.z = pack_bf16(pv[q4 * 8 + 4], pv[q4 * 8 + 5]);
-          u.w = pack_bf16(pv[q4 * 8 + 6], pv[q4 * 8 + 7]);
-          *reinterpret_cast<uint4*>(rowp + ((chunk ^ (r & 7)) << 4)) = u;
-        }
+        *reinterpret_cast<uint4*>(rowp + ((((c & 63) >> 3) ^ (r & 7)) << 4)) = u;
       }
+      if (!kOnes) l += l0 + l1;
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&p_full[g]);
@@ -266,6 +268,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     mbar_wait(&o_full[g], (nblk - 1) & 1);
     tc_fence_after();
     add_o_part(1.0f);
+    if (kOnes) l = o_acc[D];
     if (qrow < p.seq) {
       const float inv = 1.0f / l;
       const int b = bh / p.heads, head = bh - b * p.heads;
@@ -307,8 +310,8 @@ int launch_attn(const ldm_attn_desc* d, cudaStream_t s) {
     if (rc) return rc;
   }
   {
-    const uint64_t dims[3] = {(uint64_t)d->seq, (uint64_t)d->head_dim, (uint64_t)BH};
-    const uint64_t str[2] = {(uint64_t)d->seq_pad * 2, (uint64_t)d->seq_pad * 2 * d->head_dim};
+    const uint64_t dims[3] = {(uint64_t)d->seq, (uint64_t)d->vt_rows, (uint64_t)BH};
+    const uint64_t str[2] = {(uint64_t)d->seq_pad * 2, (uint64_t)d->seq_pad * 2 * d->vt_rows};
     const uint32_t box[3] = {64, (uint32_t)Cfg::kDN, 1};
     int rc = make_tmap(&tmV, d->vt, 3, dims, str, box, 2, true);
     if (rc) return rc;
@@ -334,10 +337,15 @@ int launch_attn(const ldm_attn_desc* d, cudaStream_t s) {
 
 }  // namespace
 
+extern "C" int ldm_attn_vt_rows(int head_dim) { return ((head_dim + 15) / 16) * 16; }
+
 extern "C" int ldm_flash_attn_fwd(const ldm_attn_desc* d, ldm_stream_t stream) {
   using namespace ldm_host;
   LDM_REQUIRE(d && d->q && d->k && d->vt && d->out, LDM_ERR_BAD_ARG, "ldm_flash_attn_fwd: null arg");
   LDM_REQUIRE(d->B > 0 && d->heads > 0 && d->seq > 0, LDM_ERR_BAD_SHAPE, "ldm_flash_attn_fwd: bad B/heads/seq");
+  LDM_REQUIRE(d->vt_rows == ldm_attn_vt_rows(d->head_dim), LDM_ERR_BAD_SHAPE,
+              "ldm_flash_attn_fwd: vt_rows=%d, expected ldm_attn_vt_rows(%d)=%d", d->vt_rows, d->head_dim,
+              ldm_attn_vt_rows(d->head_dim));
   LDM_REQUIRE(d->dpad == ((d->head_dim + 63) / 64) * 64 && d->seq_pad % 8 == 0 && d->seq_pad >= d->seq,
               LDM_ERR_BAD_SHAPE, "ldm_flash_attn_fwd: dpad=%d seq_pad=%d inconsistent with head_dim=%d seq=%d", d->dpad,
               d->seq_pad, d->head_dim, d->seq);

@@ -41,7 +41,9 @@ struct GemmParams {
   const float* ln_gamma;
   const float* ln_beta;
   float ln_eps;
-  int heads, head_dim, dpad, seq, seq_pad;
+  int heads, head_dim, dpad, seq, seq_pad, vt_rows;
+  int n_store;      // OUT_NCHW_F32: leading output channels actually stored
+  long long img_px; // pixels per image of the un-flattened problem (H*W)
 };
 
 __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* dst, const float* v) {
@@ -286,7 +288,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                 __nv_bfloat16* dst = (which == 0 ? p.q : p.k) + (bh * p.seq + s) * p.dpad + e;
                 store_bf16x8(dst, f + g * 8);
               } else {
-                __nv_bfloat16* dst = p.vt + (bh * p.head_dim + e) * p.seq_pad + s;
+                __nv_bfloat16* dst = p.vt + (bh * p.vt_rows + e) * p.seq_pad + s;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) dst[(long long)j * p.seq_pad] = __float2bfloat16_rn(f[g * 8 + j]);
               }
@@ -307,6 +309,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           if (p.flags & LDM_GEMM_SILU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = silu_f(f[j]);
+          }
+          if (p.flags & LDM_GEMM_OUT_NCHW_F32) {
+            // planar fp32 output [B, n_store, H, W]: lanes hold consecutive pixels -> coalesced per channel
+            const long long bi = grow / p.img_px, pix = grow - bi * p.img_px;
+            float* dst = reinterpret_cast<float*>(p.out) + (bi * p.n_store) * p.img_px + pix;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nc + j < p.n_store) dst[(long long)(nc + j) * p.img_px] = f[j];
+            continue;
           }
           if (p.flags & LDM_GEMM_OUT_F32) {
             float* dst = reinterpret_cast<float*>(p.out) + grow * p.N + nc;
@@ -456,6 +467,9 @@ extern "C" int ldm_gemm_bf16(const ldm_gemm_desc* d, ldm_stream_t stream) {
   p.dpad = d->dpad;
   p.seq = d->seq;
   p.seq_pad = d->seq_pad;
+  p.vt_rows = d->vt_rows > 0 ? d->vt_rows : d->head_dim;
+  p.n_store = d->n_store > 0 ? d->n_store : d->N;
+  p.img_px = (long long)d->H * d->W;
 
   CUtensorMap tmA1, tmA2, tmB;
   {

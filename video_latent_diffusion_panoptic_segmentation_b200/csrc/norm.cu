@@ -8,21 +8,19 @@ namespace {
 using namespace ldm;
 
 // ---------------------------------------------------------------------------------------------------------
-// GroupNorm pass 1: per-(image, group) sum and sum of squares.
+// GroupNorm pass 1: per-(image, chunk, group) partial sum and sum of squares, fully deterministic (no atomics).
 // grid = (chunks, B); block = (C/8 vectors, ppb pixels). Each thread owns one 8-channel vector position and walks
-// pixels with stride ppb*chunks, so every warp reads contiguous 16-byte vectors of one pixel row.
+// pixels with stride ppb*chunks (4 independent 16-byte loads in flight); per-thread sums go to shared memory and one
+// thread per group folds its channels x pixel-lanes in a fixed order. partial: f32 [B, chunks, groups, 2].
 // ---------------------------------------------------------------------------------------------------------
 __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, const __nv_bfloat16* __restrict__ x2, int c1,
-                                int c2, int HW, int groups, double* __restrict__ stats) {
-  extern __shared__ float sh[];  // [groups*2]
+                                int c2, int HW, int groups, float* __restrict__ partial) {
+  extern __shared__ float sh[];  // [ppb][C] sums, then [ppb][C] sums of squares
   const int C = c1 + c2;
   const int cpg = C / groups;
   const int b = blockIdx.y;
-  const int v = threadIdx.x;  // vector index within the pixel
-  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  for (int i = tid; i < groups * 2; i += blockDim.x * blockDim.y) sh[i] = 0.f;
-  __syncthreads();
-
+  const int v = threadIdx.x;
+  const int ppb = blockDim.y;
   const int c0 = v * 8;
   const __nv_bfloat16* src;
   int cs, coff;
@@ -31,44 +29,57 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, const __nv
   } else {
     src = x2; cs = c2; coff = c0 - c1;
   }
+  src += (long long)b * HW * cs + coff;
   float s[8], ss[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
-  for (int pix = blockIdx.x * blockDim.y + threadIdx.y; pix < HW; pix += gridDim.x * blockDim.y) {
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + ((long long)b * HW + pix) * cs + coff));
+  const int stride = gridDim.x * ppb;
+  int pix = blockIdx.x * ppb + threadIdx.y;
+  auto acc8 = [&](const uint4& u) {
     const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
     const float f[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       s[j] += f[j];
-      ss[j] += f[j] * f[j];
+      ss[j] = fmaf(f[j], f[j], ss[j]);
     }
+  };
+  for (; pix + 3 * stride < HW; pix += 4 * stride) {
+    const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(src + (long long)pix * cs));
+    const uint4 u1 = __ldg(reinterpret_cast<const uint4*>(src + (long long)(pix + stride) * cs));
+    const uint4 u2 = __ldg(reinterpret_cast<const uint4*>(src + (long long)(pix + 2 * stride) * cs));
+    const uint4 u3 = __ldg(reinterpret_cast<const uint4*>(src + (long long)(pix + 3 * stride) * cs));
+    acc8(u0); acc8(u1); acc8(u2); acc8(u3);
   }
-  // fold the 8 channels into their groups (a vector may straddle two groups when cpg % 8 != 0)
-  int g_prev = c0 / cpg;
-  float acc_s = 0.f, acc_ss = 0.f;
+  for (; pix < HW; pix += stride) acc8(__ldg(reinterpret_cast<const uint4*>(src + (long long)pix * cs)));
+  float* shs = sh + threadIdx.y * C + c0;
+  float* shq = sh + ppb * C + threadIdx.y * C + c0;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const int g = (c0 + j) / cpg;
-    if (g != g_prev) {
-      atomicAdd(&sh[g_prev * 2], acc_s);
-      atomicAdd(&sh[g_prev * 2 + 1], acc_ss);
-      acc_s = acc_ss = 0.f;
-      g_prev = g;
-    }
-    acc_s += s[j];
-    acc_ss += ss[j];
+    shs[j] = s[j];
+    shq[j] = ss[j];
   }
-  atomicAdd(&sh[g_prev * 2], acc_s);
-  atomicAdd(&sh[g_prev * 2 + 1], acc_ss);
   __syncthreads();
-  for (int i = tid; i < groups * 2; i += blockDim.x * blockDim.y)
-    atomicAdd(&stats[(long long)b * groups * 2 + i], (double)sh[i]);
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  if (tid < groups) {
+    float a = 0.f, q = 0.f;
+    for (int y = 0; y < ppb; ++y) {
+      const float* rs = sh + y * C + tid * cpg;
+      const float* rq = sh + ppb * C + y * C + tid * cpg;
+      for (int c = 0; c < cpg; ++c) {
+        a += rs[c];
+        q += rq[c];
+      }
+    }
+    float* dst = partial + (((long long)b * gridDim.x + blockIdx.x) * groups + tid) * 2;
+    dst[0] = a;
+    dst[1] = q;
+  }
 }
 
-// GroupNorm pass 2: normalise + affine (+ SiLU), one 16-byte vector per thread-iteration.
+// GroupNorm pass 2: fold the partials (fixed order, fp64), then normalise + affine (+ SiLU), 16 bytes per thread-iteration.
 __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, const __nv_bfloat16* __restrict__ x2, int c1,
-                                int c2, int HW, int groups, const double* __restrict__ stats,
+                                int c2, int HW, int groups, const float* __restrict__ partial, int chunks,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
                                 __nv_bfloat16* __restrict__ out) {
   extern __shared__ float sh[];  // mean[groups], rstd[groups]
@@ -77,8 +88,14 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, const __nv
   const int b = blockIdx.y;
   const double n = (double)cpg * (double)HW;
   for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-    const double m = stats[((long long)b * groups + g) * 2] / n;
-    double var = stats[((long long)b * groups + g) * 2 + 1] / n - m * m;
+    double a = 0.0, q = 0.0;
+    const float* pp = partial + ((long long)b * chunks * groups + g) * 2;
+    for (int k = 0; k < chunks; ++k) {
+      a += (double)pp[(long long)k * groups * 2];
+      q += (double)pp[(long long)k * groups * 2 + 1];
+    }
+    const double m = a / n;
+    double var = q / n - m * m;
     if (var < 0.0) var = 0.0;
     sh[g] = (float)m;
     sh[groups + g] = (float)(1.0 / sqrt(var + (double)eps));
@@ -182,6 +199,18 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, const floa
 
 }  // namespace
 
+static int gn_chunks(int B, int HW, int ppb) {
+  int chunks = (2 * ldm_host::num_sms() + B - 1) / B;
+  const int max_chunks = (HW + ppb - 1) / ppb;
+  if (chunks > max_chunks) chunks = max_chunks;
+  return chunks < 1 ? 1 : chunks;
+}
+
+extern "C" size_t ldm_groupnorm_scratch_bytes(int32_t B, int32_t groups) {
+  // upper bound of chunks over all shapes: 2 * SM count per image
+  return sizeof(float) * 2 * (size_t)groups * (size_t)B * (size_t)(2 * ldm_host::num_sms());
+}
+
 extern "C" int ldm_groupnorm_silu(const ldm_groupnorm_desc* d, ldm_stream_t stream) {
   using namespace ldm_host;
   LDM_REQUIRE(d && d->x1 && d->gamma && d->beta && d->out && d->stats, LDM_ERR_BAD_ARG, "ldm_groupnorm_silu: null arg");
@@ -192,29 +221,31 @@ extern "C" int ldm_groupnorm_silu(const ldm_groupnorm_desc* d, ldm_stream_t stre
   LDM_REQUIRE(d->c1 % 8 == 0 && c2 % 8 == 0 && C / 8 <= 1024, LDM_ERR_ALIGNMENT,
               "ldm_groupnorm_silu: channels must be multiples of 8 and <= 8192");
   cudaStream_t s = as_stream(stream);
-  cudaError_t e = cudaMemsetAsync(d->stats, 0, sizeof(double) * 2 * d->groups * d->B, s);
-  if (e != cudaSuccess) return set_error(LDM_ERR_CUDA, "memset stats: %s", cudaGetErrorString(e));
   const int vpp = C / 8;
   int ppb = 512 / vpp;
   if (ppb < 1) ppb = 1;
   if (ppb > d->HW) ppb = d->HW;
-  int chunks = (2 * num_sms() + d->B - 1) / d->B;
-  const int max_chunks = (d->HW + ppb - 1) / ppb;
-  if (chunks > max_chunks) chunks = max_chunks;
-  if (chunks < 1) chunks = 1;
-  const size_t shb = sizeof(float) * 2 * d->groups;
-  gn_stats_kernel<<<dim3(chunks, d->B), dim3(vpp, ppb), shb, s>>>(
+  const int chunks = gn_chunks(d->B, d->HW, ppb);
+  float* partial = reinterpret_cast<float*>(d->stats);
+  const size_t sh1 = sizeof(float) * 2 * (size_t)ppb * C;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    attr_set = true;
+  }
+  LDM_REQUIRE(sh1 <= 96 * 1024, LDM_ERR_BAD_SHAPE, "ldm_groupnorm_silu: C=%d too large", C);
+  gn_stats_kernel<<<dim3(chunks, d->B), dim3(vpp, ppb), sh1, s>>>(
       reinterpret_cast<const __nv_bfloat16*>(d->x1), reinterpret_cast<const __nv_bfloat16*>(d->x2), d->c1, c2, d->HW,
-      d->groups, d->stats);
+      d->groups, partial);
   count_launch();
   int rc = check_launch("gn_stats_kernel");
   if (rc) return rc;
   const long long total = (long long)d->HW * vpp;
   int gx = (int)((total + 256 * 4 - 1) / (256 * 4));
   if (gx < 1) gx = 1;
-  gn_apply_kernel<<<dim3(gx, d->B), 256, shb, s>>>(
+  gn_apply_kernel<<<dim3(gx, d->B), 256, sizeof(float) * 2 * d->groups, s>>>(
       reinterpret_cast<const __nv_bfloat16*>(d->x1), reinterpret_cast<const __nv_bfloat16*>(d->x2), d->c1, c2, d->HW,
-      d->groups, d->stats, d->gamma, d->beta, d->eps, d->silu, reinterpret_cast<__nv_bfloat16*>(d->out));
+      d->groups, partial, chunks, d->gamma, d->beta, d->eps, d->silu, reinterpret_cast<__nv_bfloat16*>(d->out));
   count_launch();
   return check_launch("gn_apply_kernel");
 }

@@ -200,7 +200,13 @@ class UNet:
             return dv(sd[name + ".weight"]), dv(sd[name + ".bias"])
 
         P["conv_in"] = (dv(sd["conv_in.weight"]), dv(sd["conv_in.bias"]))
-        P["conv_out"] = (dv(sd["conv_out.weight"]), dv(sd["conv_out.bias"]))
+        wo, bo = sd["conv_out.weight"], sd["conv_out.bias"]  # [4, C, 3, 3] -> tap-major rows, zero-padded to 8 outputs
+        npad = (wo.shape[0] + 7) // 8 * 8
+        wop = torch.zeros((npad, 9 * wo.shape[1]))
+        wop[: wo.shape[0]] = wo.permute(0, 2, 3, 1).reshape(wo.shape[0], -1)
+        bop = torch.zeros((npad,))
+        bop[: wo.shape[0]] = bo
+        P["conv_out"] = (dv(wop, bf16), dv(bop))
         P["conv_norm_out"] = norm("conv_norm_out")
         P["t1"], P["t2"] = lin("time_embedding.linear_1"), lin("time_embedding.linear_2")
         half = sd["time_embedding.linear_1.weight"].shape[1] // 2
@@ -259,7 +265,7 @@ class UNet:
         st.sample = torch.zeros((B, cin, h, w), dtype=f32, device=dev)     # static input (concatenated form)
         st.timestep = torch.zeros((1,), dtype=torch.int64, device=dev)     # static timestep
         st.out = torch.empty((B, cfg.out_channels, h, w), dtype=f32, device=dev)
-        st.gn_stats = torch.empty((B * groups * 2,), dtype=torch.float64, device=dev)
+        st.gn_stats = ops.gn_scratch(B, groups, dev)
         temb_dim = P["t1"][0].shape[0]
         st.sinus = torch.empty((2 * P["freqs"].numel(),), dtype=f32, device=dev)
         st.emb1 = torch.empty((temb_dim,), dtype=f32, device=dev)
@@ -309,11 +315,7 @@ class UNet:
             tb = name + ".transformer_blocks.0"
             key = (seq, d)
             if key not in qkv_cache:  # zero-padded head-split buffers, shared by all layers of this level
-                dpad, seq_pad = (d + 63) // 64 * 64, (seq + 7) // 8 * 8
-                qkv_cache[key] = dict(q=torch.zeros((B * heads, seq, dpad), dtype=bf16, device=dev),
-                                      k=torch.zeros((B * heads, seq, dpad), dtype=bf16, device=dev),
-                                      vt=torch.zeros((B * heads, d, seq_pad), dtype=bf16, device=dev),
-                                      heads=heads, head_dim=d, dpad=dpad, seq=seq, seq_pad=seq_pad)
+                qkv_cache[key] = ops.alloc_qkv(B, heads, seq, d, dev)
             qkv = qkv_cache[key]
             t0 = arena.alloc((B, H, W, C))
             add(ops.groupnorm, x, *P[name + ".norm"], t0, st.gn_stats, groups=groups, eps=1e-6, silu=False)
@@ -418,7 +420,8 @@ class UNet:
         # 6. conv_norm_out + SiLU + conv_out (unet.py:428-431) -> fp32 NCHW
         t = arena.alloc((B, H, W, ch[0]))
         add(ops.groupnorm, x, *P["conv_norm_out"], t, st.gn_stats, groups=groups, eps=eps, silu=True)
-        add(ops.conv_out, t, P["conv_out"][0], P["conv_out"][1], st.out)
+        add(ops.gemm, t, P["conv_out"][0], st.out, taps=9, bias=P["conv_out"][1], flags=L.LDM_GEMM_OUT_NCHW_F32,
+            block_n=32, n_store=cfg.out_channels)
         st.plan, st.arena_bytes, st.graph = plan, arena.total, None
         st.launches_per_forward = None
         return st

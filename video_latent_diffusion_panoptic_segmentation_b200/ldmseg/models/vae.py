@@ -112,7 +112,7 @@ class GeneralVAESeg:
                 hh, ww = 2 * hh, 2 * ww
                 bufs["ups"].append(torch.empty((B, hh, ww, cout), dtype=bf16, device=dev))
             bufs["gn"] = torch.empty_like(bufs["ups"][-1])
-            bufs["stats"] = torch.empty((B * self.norm_num_groups * 2,), dtype=torch.float64, device=dev)
+            bufs["stats"] = ops.gn_scratch(B, self.norm_num_groups, dev)
             self._bufs = {key: bufs}  # keep one shape resident
         bufs = self._bufs[key]
         ops.conv3x3_small_cin([z], P["in_w"], P["in_b"], bufs["x0"], scale=float(scale))

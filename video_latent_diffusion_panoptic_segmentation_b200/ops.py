@@ -32,7 +32,7 @@ def _chk(t, dtype, name):
 
 
 def gemm(a1, w, out=None, *, a2=None, taps=1, bias=None, rowbias=None, residual=None, flags=0, block_n=0,
-         qkv=None, ln=None):
+         qkv=None, ln=None, n_store=0):
     """out = epilogue(conv/gemm(a1 ++ a2, w)). a1/a2: [B,H,W,C] or [rows,C] bf16; w: [N, taps*(c1+c2)] bf16.
 
     qkv = dict(q=, k=, vt=, heads=, head_dim=, dpad=, seq=, seq_pad=) for LDM_GEMM_QKV_SPLIT;
@@ -59,9 +59,11 @@ def gemm(a1, w, out=None, *, a2=None, taps=1, bias=None, rowbias=None, residual=
         d.q, d.k, d.vt = _p(qkv["q"]), _p(qkv["k"]), _p(qkv["vt"])
         d.heads, d.head_dim, d.dpad = qkv["heads"], qkv["head_dim"], qkv["dpad"]
         d.seq, d.seq_pad = qkv["seq"], qkv["seq_pad"]
+        d.vt_rows = qkv["vt"].shape[1]
     else:
-        _chk(out, f32 if flags & L.LDM_GEMM_OUT_F32 else bf16, "out")
+        _chk(out, f32 if flags & (L.LDM_GEMM_OUT_F32 | L.LDM_GEMM_OUT_NCHW_F32) else bf16, "out")
         d.out = _p(out)
+        d.n_store = n_store
     if flags & L.LDM_GEMM_CONVT_LN_SILU:
         g, b_, eps = ln
         _chk(g, f32, "ln_gamma"); _chk(b_, f32, "ln_beta")
@@ -70,19 +72,33 @@ def gemm(a1, w, out=None, *, a2=None, taps=1, bias=None, rowbias=None, residual=
     return out
 
 
+def alloc_qkv(B, heads, seq, d, device):
+    """Zero-padded head-split buffers for LDM_GEMM_QKV_SPLIT / flash_attn (see include/ldmseg_b200.h): q, k
+    [B*heads, seq, dpad]; vt [B*heads, vt_rows, seq_pad] with the ones row at index d when d % 16 != 0."""
+    dpad, seq_pad = (d + 63) // 64 * 64, (seq + 7) // 8 * 8
+    rows = (d + 15) // 16 * 16
+    q = torch.zeros((B * heads, seq, dpad), dtype=bf16, device=device)
+    k = torch.zeros((B * heads, seq, dpad), dtype=bf16, device=device)
+    vt = torch.zeros((B * heads, rows, seq_pad), dtype=bf16, device=device)
+    if rows != d:
+        vt[:, d, :seq] = 1.0
+    return dict(q=q, k=k, vt=vt, heads=heads, head_dim=d, dpad=dpad, seq=seq, seq_pad=seq_pad)
+
+
 def flash_attn(q, k, vt, out, *, B, heads, seq, head_dim, dpad, seq_pad, scale):
     for t, n in ((q, "q"), (k, "k"), (vt, "vt"), (out, "out")):
         _chk(t, bf16, n)
     d = L.AttnDesc()
     d.q, d.k, d.vt, d.out = _p(q), _p(k), _p(vt), _p(out)
     d.B, d.heads, d.seq, d.head_dim, d.dpad, d.seq_pad, d.scale = B, heads, seq, head_dim, dpad, seq_pad, scale
+    d.vt_rows = vt.shape[1]
     L.check(L.lib().ldm_flash_attn_fwd(C.byref(d), _stream()), "ldm_flash_attn_fwd")
     return out
 
 
 def groupnorm(x1, gamma, beta, out, stats, *, x2=None, groups=32, eps=1e-5, silu=True):
     _chk(x1, bf16, "x1"); _chk(x2, bf16, "x2"); _chk(gamma, f32, "gamma"); _chk(beta, f32, "beta")
-    _chk(out, bf16, "out"); _chk(stats, torch.float64, "stats")
+    _chk(out, bf16, "out"); _chk(stats, f32, "stats")
     B = x1.shape[0]
     c1 = x1.shape[-1]
     HW = x1.numel() // (B * c1)
@@ -90,10 +106,14 @@ def groupnorm(x1, gamma, beta, out, stats, *, x2=None, groups=32, eps=1e-5, silu
     d.x1, d.x2, d.gamma, d.beta, d.out, d.stats = _p(x1), _p(x2), _p(gamma), _p(beta), _p(out), _p(stats)
     d.B, d.HW, d.c1, d.c2 = B, HW, c1, (0 if x2 is None else x2.shape[-1])
     d.groups, d.eps, d.silu = groups, eps, int(silu)
-    if stats.numel() < B * groups * 2:
-        raise L.LdmError("groupnorm: stats scratch too small")
+    if stats.numel() * 4 < L.lib().ldm_groupnorm_scratch_bytes(B, groups):
+        raise L.LdmError("groupnorm: stats scratch too small (see gn_scratch)")
     L.check(L.lib().ldm_groupnorm_silu(C.byref(d), _stream()), "ldm_groupnorm_silu")
     return out
+
+
+def gn_scratch(B, groups, device):
+    return torch.empty(L.lib().ldm_groupnorm_scratch_bytes(B, groups) // 4, dtype=f32, device=device)
 
 
 def layernorm(x, gamma, beta, out, eps=1e-5):
