@@ -141,9 +141,14 @@ def test_tail_ids_bit_exact_given_identical_logits(models):
     B, h, w, C = 2, 48, 156, 128
     g = torch.Generator().manual_seed(77)
     lo = torch.randn((B, h, w, C), generator=g) * 1.5
-    # a few confident blobs so that segments survive count_th / overlap_th, plus low-confidence background
+    # a few confident blobs so that segments survive count_th / overlap_th, plus low-confidence background; the blob
+    # channels are pushed negative elsewhere so that their sigmoid area (the overlap denominator) is the blob itself
+    lo[..., 10:14] -= 5.0
     for k, (y0, x0, hh, ww) in enumerate([(2, 3, 20, 40), (25, 60, 20, 50), (5, 100, 30, 50), (30, 5, 15, 40)]):
-        lo[:, y0:y0 + hh, x0:x0 + ww, 10 + k] += 9.0
+        lo[:, y0:y0 + hh, x0:x0 + ww, 10 + k] += 14.0
+    # one more blob whose channel is positive over most of the image -> argmax area / sigmoid area < overlap_th
+    lo[..., 20] += 1.0
+    lo[:, 36:46, 100:150, 20] += 9.0
     lo = lo.to(DEV)
     ids = torch.empty((B, 2 * h, 2 * w), dtype=torch.int32, device=DEV)
     counts = torch.empty((B, 2, C), dtype=torch.int32, device=DEV)

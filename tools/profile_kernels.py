@@ -1,0 +1,107 @@
+"""Launch the dominant kernels of the UNet at their configs[1] shapes (B = 8 frames of 384x1248, latent 48x156), one
+after another, for ncu captures and CUDA-event timings.
+
+    python tools/profile_kernels.py [--iters N] [--only substr,substr] [--json out.json]
+
+Each case is launched `iters` times back to back (inputs of the large cases exceed L2 anyway); the event time is
+the mean per launch. Under ncu use --iters 1.
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from video_latent_diffusion_panoptic_segmentation_b200 import _lib as L  # noqa: E402
+from video_latent_diffusion_panoptic_segmentation_b200 import ops  # noqa: E402
+
+DEV, bf16, f32 = "cuda", torch.bfloat16, torch.float32
+B = 8
+LEVELS = {"L0": (48, 156, 320), "L1": (24, 78, 640), "L2": (12, 39, 1280), "L3": (6, 20, 1280)}
+
+
+def rn(shape, dtype=bf16, scale=1.0):
+    return (torch.randn(shape, device=DEV) * scale).to(dtype)
+
+
+def cases():
+    out = {}
+    for lv, (h, w, C) in LEVELS.items():
+        M = B * h * w
+        if lv != "L3":
+            a, wt, bias, res, o = rn((M, C)), rn((C, C), scale=0.05), rn((C,), f32), rn((M, C)), rn((M, C))
+            out[f"gemm1x1_res_{lv}"] = (lambda a=a, wt=wt, bias=bias, res=res, o=o: ops.gemm(a, wt, o, bias=bias, residual=res),
+                                       2 * M * C * C, 2 * (3 * M * C + C * C))
+            w1, b1, g = rn((8 * C, C), scale=0.05), rn((8 * C,), f32), rn((M, 4 * C))
+            out[f"gemm_geglu_{lv}"] = (lambda a=a, w1=w1, b1=b1, g=g: ops.gemm(a, w1, g, bias=b1, flags=L.LDM_GEMM_GEGLU),
+                                      2 * M * 8 * C * C, 2 * (M * C + 8 * C * C + M * 4 * C))
+            w2 = rn((C, 4 * C), scale=0.05)
+            out[f"gemm_ff2_{lv}"] = (lambda g=g, w2=w2, bias=bias, res=res, o=o: ops.gemm(g, w2, o, bias=bias, residual=res),
+                                    2 * M * 4 * C * C, 2 * (M * 4 * C + 4 * C * C + 2 * M * C))
+            d = C // 8
+            qkv = ops.alloc_qkv(B, 8, h * w, d, DEV)
+            wq = rn((3 * C, C), scale=0.05)
+            out[f"gemm_qkv_{lv}"] = (lambda a=a, wq=wq, qkv=qkv: ops.gemm(a, wq, None, flags=L.LDM_GEMM_QKV_SPLIT, qkv=qkv),
+                                    2 * M * 3 * C * C, 2 * (M * C + 3 * C * C + 3 * M * C))
+            ao = rn((M, C))
+            out[f"attn_{lv}"] = (lambda qkv=qkv, ao=ao, h=h, w=w, d=d: ops.flash_attn(
+                qkv["q"], qkv["k"], qkv["vt"], ao, B=B, heads=8, seq=h * w, head_dim=d, dpad=qkv["dpad"],
+                seq_pad=qkv["seq_pad"], scale=d ** -0.5), 4 * B * 8 * (h * w) ** 2 * d, 2 * 4 * M * C)
+            ln_g, ln_b = rn((C,), f32), rn((C,), f32)
+            out[f"layernorm_{lv}"] = (lambda a=a, o=o, ln_g=ln_g, ln_b=ln_b: ops.layernorm(a, ln_g, ln_b, o, 1e-5), 0,
+                                     2 * 2 * M * C)
+        x = rn((B, h, w, C))
+        w3, bias3, o3, res3 = rn((C, 9 * C), scale=0.02), rn((C,), f32), rn((B, h, w, C)), rn((M, C))
+        out[f"conv3x3_{lv}"] = (lambda x=x, w3=w3, bias3=bias3, o3=o3, res3=res3: ops.gemm(x, w3, o3, taps=9, bias=bias3, residual=res3),
+                               2 * M * C * 9 * C, 2 * (3 * M * C + 9 * C * C))
+        gam, bet, stats = rn((C,), f32), rn((C,), f32), ops.gn_scratch(B, 32, DEV)
+        out[f"groupnorm_{lv}"] = (lambda x=x, gam=gam, bet=bet, o3=o3, stats=stats: ops.groupnorm(x, gam, bet, o3, stats, groups=32, eps=1e-5, silu=True),
+                                 0, 2 * 2 * M * C)
+    # concat-input resnet conv1 of the last up block (960 -> 320 at L0) and its GroupNorm
+    h, w, _ = LEVELS["L0"]
+    xa, xb = rn((B, h, w, 640)), rn((B, h, w, 320))
+    t0, wc, bc, oc = rn((B, h, w, 960)), rn((320, 9 * 960), scale=0.02), rn((320,), f32), rn((B, h, w, 320))
+    gam, bet, stats = rn((960,), f32), rn((960,), f32), ops.gn_scratch(B, 32, DEV)
+    out["groupnorm_cat960_L0"] = (lambda: ops.groupnorm(xa, gam, bet, t0, stats, x2=xb, groups=32, eps=1e-5, silu=True), 0,
+                                  2 * 2 * B * h * w * 960)
+    out["conv3x3_960to320_L0"] = (lambda: ops.gemm(t0, wc, oc, taps=9, bias=bc), 2 * B * h * w * 320 * 9 * 960,
+                                  2 * (B * h * w * 1280 + 9 * 960 * 320))
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--only", default="")
+    ap.add_argument("--json", default=None)
+    args = ap.parse_args()
+    torch.manual_seed(0)
+    L.lib()
+    sel = [s for s in args.only.split(",") if s]
+    rows = []
+    for name, (fn, flops, nbytes) in cases().items():
+        if sel and not any(s in name for s in sel):
+            continue
+        fn()  # warm-up (sets the kernel attributes)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / args.iters
+        rows.append({"case": name, "us": round(us, 2), "tflops": round(flops / us / 1e6, 1),
+                     "gbs": round(nbytes / us / 1e3, 1)})
+        print(json.dumps(rows[-1]), flush=True)
+    if args.json:
+        with open(args.json, "w") as f:
+            json.dump(rows, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
