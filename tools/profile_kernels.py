@@ -73,8 +73,38 @@ def cases():
     return out
 
 
+def sweep_block_n(iters):
+    """Time the contraction kernel for every block_n on the UNet's (M, N, K, taps) shapes (plain bf16 epilogue)."""
+    shapes = [(48, 156, 320, 320, 1), (48, 156, 320, 320, 9), (48, 156, 640, 320, 9), (48, 156, 320, 1280, 1),
+              (24, 78, 640, 640, 1), (24, 78, 640, 640, 9), (24, 78, 1280, 640, 9), (24, 78, 640, 2560, 1),
+              (12, 39, 1280, 1280, 1), (12, 39, 1280, 1280, 9), (12, 39, 2560, 1280, 9), (12, 39, 1280, 5120, 1),
+              (6, 20, 1280, 1280, 1), (6, 20, 1280, 1280, 9), (6, 20, 2560, 1280, 9)]
+    rows = []
+    for (h, w, cin, N, taps) in shapes:
+        x = rn((B, h, w, cin))
+        wt, bias, o = rn((N, taps * cin), scale=0.02), rn((N,), f32), rn((B, h, w, N))
+        M = B * h * w
+        best = None
+        for bn in (0, 64, 96, 128, 160, 192, 224, 256):
+            fn = lambda: ops.gemm(x, wt, o, taps=taps, bias=bias, block_n=bn)
+            fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) * 1e3 / iters
+            rows.append({"M": M, "N": N, "K": taps * cin, "taps": taps, "block_n": bn, "us": round(us, 2),
+                         "tflops": round(2 * M * N * taps * cin / us / 1e6, 1)})
+            print(json.dumps(rows[-1]), flush=True)
+    return rows
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--sweep", action="store_true", help="block_n sweep of the contraction kernel")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--only", default="")
     ap.add_argument("--json", default=None)
@@ -82,6 +112,12 @@ def main():
     torch.manual_seed(0)
     L.lib()
     sel = [s for s in args.only.split(",") if s]
+    if args.sweep:
+        rows = sweep_block_n(args.iters)
+        if args.json:
+            with open(args.json, "w") as f:
+                json.dump(rows, f, indent=1)
+        return
     rows = []
     for name, (fn, flops, nbytes) in cases().items():
         if sel and not any(s in name for s in sel):

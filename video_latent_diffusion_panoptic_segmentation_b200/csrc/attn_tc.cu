@@ -3,11 +3,13 @@
 //   grid = (ceil(seq / (128*NQ)), B*heads); one CTA owns NQ tiles of 128 queries of one (image, head).
 //     warp 0              TMA producer : Q tiles once, then a ring of (K block | V^T block) stages
 //     warp 1              MMA issuer   : S = Q K^T and O_part = P V with tcgen05.mma (fp32 in TMEM)
-//     warps 2..2+4*NQ-1   softmax      : one query row per thread. Two passes over S in TMEM (row max, then
-//                                        exp2 / row sum / bf16 P written to swizzled smem as the A operand of the
-//                                        PV MMA); O is accumulated in registers from the per-block O_part so no
-//                                        TMEM read-modify-write rescale is needed.
-//   With NQ = 2 the tensor core computes group B's S / PV while group A is in its softmax.
+//     warps 4..4+4*NQ-1   softmax      : one query row per thread. The whole score row of a KV block is read from TMEM
+//                                        into registers in one pass and the S columns are handed back at once
+//                                        (s_free), so the tensor core computes S of the NEXT block while this block's
+//                                        exp2 / bf16 P (swizzled smem, the A operand of the PV MMA) are produced.
+//                                        O accumulates in TMEM across blocks; it is rescaled (TMEM ld/st) only when a
+//                                        row maximum grew by more than 2^8 since the last rescale, which is rare after
+//                                        the first blocks, so the steady-state loop is max -> exp2 -> pack -> store.
 //   Layouts: q,k [B*heads, seq, dpad] (dpad = 64*ceil(d/64), zero padded), vt [B*heads, vt_rows, seq_pad] (V transposed
 //   so that both MMAs see K-major operands; vt_rows = 16*ceil(d/16); when d % 16 != 0 the caller keeps row d of every
 //   head at 1.0 so the PV MMA also produces the softmax row sums), out [B*seq, heads*d]; all bf16.
@@ -43,7 +45,7 @@ struct AttnCfg {
   static constexpr int kStageBytes = kKBytes + kVBytesPad;
   static constexpr int kPBytes = kVAtoms * 128 * 128;  // per group
   static constexpr int kSmem = NQ * (kQBytes + kPBytes) + STAGES * kStageBytes + 1024 + 256;
-  static constexpr int kThreads = 64 + 128 * NQ;
+  static constexpr int kThreads = 128 + 128 * NQ;  // warpgroup 0: producer, MMA issuer (+2 idle warps); then NQ softmax warpgroups
   static constexpr int kTmemGroupStride = 256;
   static constexpr int kTmemCols = (NQ == 2) ? 512 : ((BKV + kDN <= 256) ? 256 : 512);
   static_assert(NQ == 1 || BKV + kDN <= 256, "TMEM budget");
@@ -67,7 +69,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   uint64_t* s_full = kv_empty + 8;       // [NQ]
   uint64_t* p_full = s_full + 2;         // [NQ]
   uint64_t* o_full = p_full + 2;         // [NQ]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+  uint64_t* s_free = o_full + 2;         // [NQ]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -84,6 +87,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       mbar_init(&s_full[g], 1);
       mbar_init(&p_full[g], 128);
       mbar_init(&o_full[g], 1);
+      mbar_init(&s_free[g], 128);
     }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&kv_full[s], 1);
@@ -100,6 +104,10 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Register rebalancing (NQ = 2 launches 384 threads at 168 registers): the control warpgroup gives registers back,
+  // the softmax warpgroups (a 128-wide score row per thread) take them.
+  if (warp < 4) {
+    if (NQ == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
@@ -143,7 +151,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         }
         umma_commit(&s_full[g]);
       };
-      auto issue_o = [&](int g, int stage) {
+      auto issue_o = [&](int g, int stage, bool accumulate) {
         const uint32_t pa = smem_u32(sP + g * Cfg::kPBytes);
         const uint32_t va = smem_u32(sKV + stage * Cfg::kStageBytes + Cfg::kKBytes);
         const uint32_t d_tmem = tmem_base + g * Cfg::kTmemGroupStride + BKV;
@@ -151,7 +159,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         for (int kk = 0; kk < BKV / 16; ++kk) {
           const uint64_t da = umma_desc_k_sw128(pa + (kk >> 2) * (128 * 128) + (kk & 3) * 32);
           const uint64_t db = umma_desc_k_sw128(va + (kk >> 2) * (Cfg::kDN * 128) + (kk & 3) * 32);
-          umma_bf16(d_tmem, da, db, idesc_o, kk != 0);
+          umma_bf16(d_tmem, da, db, idesc_o, accumulate || kk != 0);
         }
         umma_commit(&o_full[g]);
       };
@@ -168,16 +176,19 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           nstage = 0;
           nphase ^= 1;
         }
-        const bool has_next = (j + 1 < nblk);
-        if (has_next) {
+        if (j + 1 < nblk) {
+          // S of the next block as soon as the softmax threads have pulled this block's scores out of TMEM
           mbar_wait(&kv_full[nstage], nphase);
-          tc_fence_after();
+          for (int g = 0; g < NQ; ++g) {
+            mbar_wait(&s_free[g], j & 1);
+            tc_fence_after();
+            issue_s(g, nstage);
+          }
         }
         for (int g = 0; g < NQ; ++g) {
           mbar_wait(&p_full[g], j & 1);
           tc_fence_after();
-          issue_o(g, stage);
-          if (has_next) issue_s(g, nstage);
+          issue_o(g, stage, j > 0);
         }
         umma_commit(&kv_empty[stage]);
         stage = nstage;
@@ -185,30 +196,20 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       }
     }
     __syncwarp();
+  }
   } else {
     // ------------------------------------------------------------------ softmax / output (one row per thread)
-    const int g = (warp - 2) >> 2;
+    if (NQ == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    const int g = (warp - 4) >> 2;
     const int quad = warp & 3;
     const int r = quad * 32 + lane;
     const int qrow = q_base + g * 128 + r;
     const uint32_t t_s = tmem_base + ((uint32_t)(quad * 32) << 16) + g * Cfg::kTmemGroupStride;
     const uint32_t t_o = t_s + BKV;
     uint8_t* myP = sP + g * Cfg::kPBytes;
-    float o_acc[Cfg::kDN];
-#pragma unroll
-    for (int i = 0; i < Cfg::kDN; ++i) o_acc[i] = 0.f;
-    float m = -INFINITY, l = 0.f;
+    float m = -INFINITY, l = 0.f;      // m: reference maximum the stored P / O are relative to (log2 domain)
     constexpr bool kOnes = Cfg::kOnesRow;  // row sums come out of the PV MMA (ones row of V^T at index D)
-
-    // O_acc = (O_acc + O_part) * alpha; all TMEM loads are issued before the single wait
-    auto add_o_part = [&](float alpha) {
-      uint32_t v[Cfg::kDN];
-#pragma unroll
-      for (int c = 0; c < Cfg::kDN; c += 16) tmem_ld16(t_o + c, v + c);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < Cfg::kDN; ++i) o_acc[i] = (o_acc[i] + __uint_as_float(v[i])) * alpha;
-    };
+    constexpr float kLazy = 8.0f;       // rescale O only when the row maximum grew by more than 2^8
 
     for (int j = 0; j < nblk; ++j) {
       const int nvalid = p.seq - j * BKV;  // keys of this block inside the sequence (>= 1)
@@ -218,6 +219,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 #pragma unroll
       for (int c = 0; c < BKV; c += 32) tmem_ld32(t_s + c, sv + c);
       tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&s_free[g]);  // the S columns may be overwritten by the next block's QK^T now
       if (nvalid < BKV) {  // only the last block of a ragged sequence
 #pragma unroll
         for (int i = 0; i < BKV; ++i)
@@ -231,16 +234,31 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         mx2 = fmaxf(mx2, __uint_as_float(sv[i + 2]));
         mx3 = fmaxf(mx3, __uint_as_float(sv[i + 3]));
       }
-      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-      const float m_new = fmaxf(m, mx * p.scale_log2);
-      const float alpha = ex2(m - m_new);
-      if (j > 0) {
+      const float m_blk = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
+      if (j == 0) {
+        m = m_blk;
+      } else {
+        // PV of the previous block has finished: P smem may be rewritten and O may be touched
         mbar_wait(&o_full[g], (j - 1) & 1);
-        tc_fence_after();
-        add_o_part(alpha);
+        const bool need = m_blk - m > kLazy;
+        if (__any_sync(0xffffffffu, need)) {
+          tc_fence_after();
+          const float m_new = need ? m_blk : m;
+          const float alpha = ex2(m - m_new);  // 1 for the rows that keep their reference
+          m = m_new;
+          if (!kOnes) l *= alpha;
+#pragma unroll
+          for (int c = 0; c < Cfg::kDN; c += 16) {
+            uint32_t v[16];
+            tmem_ld16(t_o + c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st16(t_o + c, v);
+          }
+          tmem_st_wait();
+        }
       }
-      if (!kOnes) l *= alpha;
-      m = m_new;
       float l0 = 0.f, l1 = 0.f;
 #pragma unroll
       for (int c = 0; c < BKV; c += 8) {
@@ -267,7 +285,15 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     }
     mbar_wait(&o_full[g], (nblk - 1) & 1);
     tc_fence_after();
-    add_o_part(1.0f);
+    float o_acc[Cfg::kDN];
+    {
+      uint32_t v[Cfg::kDN];
+#pragma unroll
+      for (int c = 0; c < Cfg::kDN; c += 16) tmem_ld16(t_o + c, v + c);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < Cfg::kDN; ++i) o_acc[i] = __uint_as_float(v[i]);
+    }
     if (kOnes) l = o_acc[D];
     if (qrow < p.seq) {
       const float inv = 1.0f / l;

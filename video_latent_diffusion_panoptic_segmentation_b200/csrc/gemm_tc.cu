@@ -6,9 +6,13 @@
 //                                  the zero padding is TMA out-of-bounds fill. Channel-concat inputs are two maps.
 //     warp 1      MMA issuer     : tcgen05.mma cta_group::1 kind::f16, M=128 x N=block_n x K=16, fp32 accumulators
 //                                  double-buffered in TMEM (2 x 256 columns) so the epilogue overlaps the next tile.
-//     warps 2..5  epilogue       : tcgen05.ld 32x32b -> registers -> fused bias / time-embedding / residual / SiLU /
-//                                  GEGLU / QKV head split / ConvT pixel-shuffle+LayerNorm2d+SiLU -> global.
+//     warps 2..9  epilogue       : tcgen05.ld 32x32b -> registers -> fused bias / time-embedding / residual / SiLU /
+//                                  GEGLU / QKV head split / ConvT pixel-shuffle+LayerNorm2d+SiLU -> global. Two warps
+//                                  per TMEM lane quadrant (even / odd 32-column chunks); the residual rows of a tile
+//                                  are prefetched into registers before the accumulator is waited for.
 //   smem ring of (A 128x64 | B block_n x 64) bf16 stages, SWIZZLE_128B, full/empty mbarriers.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "host_util.h"
 
@@ -20,7 +24,8 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB
 constexpr int kMaxStages = 8;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;  // two warps per TMEM lane quadrant, each takes every other 32-column chunk
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kSmemBudget = 227 * 1024;
 
 struct GemmParams {
@@ -55,11 +60,20 @@ __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* dst, const float* v)
   *reinterpret_cast<uint4*>(dst) = u;
 }
 
+// kPair = false: one CTA per 128 x block_n tile (tcgen05 cta_group::1).
+// kPair = true : a cluster of two CTAs (one TPC) per 256 x block_n tile (cta_group::2, UMMA M = 256). Each CTA loads
+//                its own 128-row A box and HALF of the B tile (block_n/2 weight rows) -- the tensor core reads the other
+//                half from the peer's shared memory -- so the per-SM operand ingest from L2, which bounds the
+//                single-CTA kernel, drops from 16 KiB + block_n*128 B to 16 KiB + block_n*64 B per k-block. The leader
+//                (cluster rank 0) issues every MMA; both CTAs' TMA loads complete on the leader's full barrier; MMA
+//                completion is multicast to both CTAs' empty / accumulator-full barriers; both epilogues release
+//                the accumulator on the leader's barrier.
+template <bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // 1024-byte alignment is required by SWIZZLE_128B tiles.
+  // 1024-byte alignment is required by SWIZZLE_128B tiles (the dynamic smem base is the same in both CTAs of a pair).
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * p.stage_bytes);
   uint64_t* empty_bar = full_bar + kMaxStages;
@@ -69,6 +83,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;   // 0 = leader
+  const int worker = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int num_workers = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA1);
@@ -80,37 +97,47 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 128);
+      mbar_init(&tempty_bar[i], (kPair ? 2 : 1) * 32 * kEpiWarps);
     }
     mbar_fence_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
+    if (kPair) {
+      tmem_alloc_pair(tmem_slot, 512);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, 512);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int num_tiles = p.m_tiles * p.n_tiles;
+  // work items: (m_unit, n_tile) with m_unit = one M tile, or a pair of consecutive M tiles
+  const int m_units = kPair ? (p.m_tiles + 1) / 2 : p.m_tiles;
+  const int num_tiles = m_units * p.n_tiles;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
   const uint32_t a_bytes = (uint32_t)(p.bw * p.bh) * (kBlockK * 2);
-  const uint32_t b_bytes = (uint32_t)p.block_n * (kBlockK * 2);
+  const int b_rows = kPair ? p.block_n / 2 : p.block_n;   // weight rows this CTA loads per k-block
+  const uint32_t b_bytes = (uint32_t)b_rows * (kBlockK * 2);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n_tile = tile / p.m_tiles;
-        const int m_tile = tile - n_tile * p.m_tiles;
+      for (int tile = worker; tile < num_tiles; tile += num_workers) {
+        const int n_tile = tile / m_units;
+        const int m_unit = tile - n_tile * m_units;
+        const int m_tile = kPair ? 2 * m_unit + (int)rank : m_unit;  // == m_tiles for the odd tail: all-OOB box, zeros
         const int b = m_tile / tiles_per_img;
         const int rem = m_tile - b * tiles_per_img;
         const int ty = rem / p.tiles_x;
         const int tx = rem - ty * p.tiles_x;
-        const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = n_tile * p.block_n;
+        const int x0 = tx * p.bw, y0 = ty * p.bh;
+        const int n0 = n_tile * p.block_n + (int)rank * b_rows;
         for (int tap = 0; tap < p.taps; ++tap) {
           const int dy = (p.taps == 9) ? tap / 3 - 1 : 0;
           const int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
@@ -118,12 +145,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * p.stage_bytes;
             uint8_t* sb = sa + kABytes;
-            mbar_arrive_expect_tx(&full_bar[stage], a_bytes + b_bytes);
-            if (kb < p.kblocks1)
-              tma_load_4d(sa, &tmA1, &full_bar[stage], kb * kBlockK, x0 + dx, y0 + dy, b);
-            else
-              tma_load_4d(sa, &tmA2, &full_bar[stage], (kb - p.kblocks1) * kBlockK, x0 + dx, y0 + dy, b);
-            tma_load_2d(sb, &tmB, &full_bar[stage], tap * p.ktap + kb * kBlockK, n0);
+            const CUtensorMap* tmA = (kb < p.kblocks1) ? &tmA1 : &tmA2;
+            const int kc = (kb < p.kblocks1 ? kb : kb - p.kblocks1) * kBlockK;
+            if (kPair) {
+              // the leader's barrier collects the bytes of both CTAs
+              if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (a_bytes + b_bytes));
+              tma_load_4d_pair(sa, tmA, &full_bar[stage], kc, x0 + dx, y0 + dy, b);
+              tma_load_2d_pair(sb, &tmB, &full_bar[stage], tap * p.ktap + kb * kBlockK, n0);
+            } else {
+              mbar_arrive_expect_tx(&full_bar[stage], a_bytes + b_bytes);
+              tma_load_4d(sa, tmA, &full_bar[stage], kc, x0 + dx, y0 + dy, b);
+              tma_load_2d(sb, &tmB, &full_bar[stage], tap * p.ktap + kb * kBlockK, n0);
+            }
             if (++stage == p.stages) {
               stage = 0;
               phase ^= 1;
@@ -134,15 +167,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(kBlockM, (uint32_t)p.block_n);
+    // ------------------------------------------------------------------ MMA issuer (pair: leader CTA only)
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = umma_idesc_bf16(kPair ? 256 : kBlockM, (uint32_t)p.block_n);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
       const int ksteps = p.taps * p.kblocks;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < num_tiles; tile += num_workers) {
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)as * 256u;
@@ -155,15 +188,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             // advance 16 bf16 = 32 bytes inside the 128-byte swizzle atom: +2 in 16-byte units
-            umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (ks | k) != 0);
+            if (kPair)
+              umma_bf16_pair(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (ks | k) != 0);
+            else
+              umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (ks | k) != 0);
           }
-          umma_commit(&empty_bar[stage]);
+          if (kPair) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull_bar[as]);
+        if (kPair) umma_commit_pair(&tfull_bar[as]); else umma_commit(&tfull_bar[as]);
         if (++as == 2) {
           as = 0;
           aphase ^= 1;
@@ -172,29 +208,47 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
+    const int quad = warp & 3;            // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;     // 0: even 32-column chunks, 1: odd chunks
     const int r = quad * 32 + lane;
+    const bool plain = !(p.flags & (LDM_GEMM_CONVT_LN_SILU | LDM_GEMM_GEGLU | LDM_GEMM_QKV_SPLIT));
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int n_tile = tile / p.m_tiles;
-      const int m_tile = tile - n_tile * p.m_tiles;
+    for (int tile = worker; tile < num_tiles; tile += num_workers) {
+      const int n_tile = tile / m_units;
+      const int m_unit = tile - n_tile * m_units;
+      const int m_tile = kPair ? 2 * m_unit + (int)rank : m_unit;
       const int b = m_tile / tiles_per_img;
       const int rem = m_tile - b * tiles_per_img;
       const int ty = rem / p.tiles_x;
       const int tx = rem - ty * p.tiles_x;
       const int ly = r / p.bw, lx = r - ly * p.bw;
       const int y = ty * p.bh + ly, x = tx * p.bw + lx;
-      const bool valid = (r < p.bw * p.bh) && (y < p.H) && (x < p.W);
+      const bool valid = (m_tile < p.m_tiles) && (r < p.bw * p.bh) && (y < p.H) && (x < p.W);
       const long long grow = ((long long)b * p.H + y) * p.W + x;
       const int n0 = n_tile * p.block_n;
+
+      // residual rows of this tile: issue every load now, so that they are in flight while the MMAs finish
+      uint4 rs[4][4];
+      const bool use_res = plain && p.residual != nullptr && valid;
+      if (use_res) {
+        const __nv_bfloat16* rrow = p.residual + grow * p.N + n0;
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+          const int c = (2 * ci + half) * 32;
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            if (c < p.block_n && n0 + c + g * 8 < p.N) rs[ci][g] = ld_nc_v4(rrow + c + g * 8);
+        }
+      }
 
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)as * 256u;
 
       if (p.flags & LDM_GEMM_CONVT_LN_SILU) {
+        if (half == 0) {
         // One N tile == one (dy,dx) sub-pixel of ConvTranspose2d(k=2,s=2); LayerNorm2d over its block_n channels.
         const int cout = p.block_n;
         float mean = 0.f;
@@ -239,8 +293,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             }
           }
         }
+        }
       } else {
-        for (int c = 0; c < p.block_n; c += 32) {
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+          const int c = (2 * ci + half) * 32;
+          if (c >= p.block_n) break;
           uint32_t v[32];
           tmem_ld32(t_addr + c, v);
           tmem_ld_wait();
@@ -250,22 +308,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (p.bias) {
+          if (p.bias) {  // N % 8 == 0 (GEGLU: % 32): 4-wide groups are all-in or all-out
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + nc);
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nc + j < p.N) f[j] += __ldg(&p.bias[nc + j]);
+            for (int g = 0; g < 8; ++g)
+              if (nc + g * 4 < p.N) {
+                const float4 bv = __ldg(bp + g);
+                f[g * 4] += bv.x; f[g * 4 + 1] += bv.y; f[g * 4 + 2] += bv.z; f[g * 4 + 3] += bv.w;
+              }
           }
           if (p.rowbias) {
-            const float* rb = p.rowbias + (long long)b * p.N + nc;
+            const float4* bp = reinterpret_cast<const float4*>(p.rowbias + (long long)b * p.N + nc);
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nc + j < p.N) f[j] += __ldg(&rb[j]);
+            for (int g = 0; g < 8; ++g)
+              if (nc + g * 4 < p.N) {
+                const float4 bv = __ldg(bp + g);
+                f[g * 4] += bv.x; f[g * 4 + 1] += bv.y; f[g * 4 + 2] += bv.z; f[g * 4 + 3] += bv.w;
+              }
           }
           if (p.flags & LDM_GEMM_GEGLU) {
             // columns [0,16) value, [16,32) gate of the same 16 outputs
             float o[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) o[j] = f[j] * gelu_erf_f(f[16 + j]);
+            for (int j = 0; j < 16; ++j) o[j] = f[j] * gelu_erf_fast(f[16 + j]);
             __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + grow * (p.N / 2) + nc / 2;
             store_bf16x8(dst, o);
             store_bf16x8(dst + 8, o + 8);
@@ -296,11 +361,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             continue;
           }
           if (p.residual) {
-            const __nv_bfloat16* rs = p.residual + grow * p.N + nc;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               if (nc + g * 8 >= p.N) break;
-              const uint4 u = *reinterpret_cast<const uint4*>(rs + g * 8);
+              const uint4 u = rs[ci][g];
               const float2 a0 = unpack_bf16(u.x), a1 = unpack_bf16(u.y), a2 = unpack_bf16(u.z), a3 = unpack_bf16(u.w);
               f[g * 8 + 0] += a0.x; f[g * 8 + 1] += a0.y; f[g * 8 + 2] += a1.x; f[g * 8 + 3] += a1.y;
               f[g * 8 + 4] += a2.x; f[g * 8 + 5] += a2.y; f[g * 8 + 6] += a3.x; f[g * 8 + 7] += a3.y;
@@ -337,7 +401,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         }
       }
       tc_fence_before();
-      mbar_arrive(&tempty_bar[as]);
+      if (kPair) mbar_arrive_cluster(&tempty_bar[as], 0); else mbar_arrive(&tempty_bar[as]);
       if (++as == 2) {
         as = 0;
         aphase ^= 1;
@@ -346,10 +410,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all(); else __syncthreads();  // pair: neither CTA may exit while its peer can still signal it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (kPair) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -378,18 +442,47 @@ void pick_box(int H, int W, int taps, int* bw_out, int* bh_out) {
   *bh_out = best_bh;
 }
 
-int pick_block_n(int N) {
-  const int cands[] = {256, 192, 160, 128, 96, 64, 32};
+// Choose block_n with a small cost model of the persistent schedule, calibrated on B200 (tools/profile_kernels.py
+// --sweep, profiles/r01b_sweep_block_n.json): tiles run in waves over the SMs; one 64-wide k-block of a tile costs the
+// slower of the tensor pipe (4 MMAs of block_n/2 cycles at M = 128) and the SM's operand ingest from L2 (A 16 KiB +
+// B block_n*128 B at ~56 B/cycle -- the binding term for every block_n <= 256), plus ~2000 cycles per tile of
+// pipeline fill / epilogue drain. Avoids the two failure modes of "largest tile that divides N": a second, nearly
+// empty wave (150 tiles on 148 SMs) and a handful of huge tiles when M is small (M = 960 at the 6x20 level).
+// pair = true: work items are 256 x block_n tiles on SM pairs and each CTA ingests only half of the B rows.
+int pick_block_n(int N, long m_tiles, long kblocks, int sms, bool pair, double* cost_out) {
+  const int cands[] = {256, 192, 160, 128, 96};
   int best = 256;
-  long best_pad = -1;
+  double best_cost = -1.0;
+  const long m_units = pair ? (m_tiles + 1) / 2 : m_tiles;
+  const long workers = pair ? sms / 2 : sms;
   for (int c : cands) {
-    const long pad = (long)((N + c - 1) / c) * c;
-    if (best_pad < 0 || pad < best_pad) {
-      best_pad = pad;
+    const long n_tiles = (N + c - 1) / c;
+    const int last = N - (int)(n_tiles - 1) * c;  // columns of the ragged last N tile (its B rows beyond N are not fetched)
+    const long waves = (m_units * n_tiles + workers - 1) / workers;
+    auto tile_cycles = [&](int cols) {
+      const double mma = 2.0 * c;
+      const double ingest = (16384.0 + (pair ? 64.0 : 128.0) * cols) / 56.0;
+      return (double)kblocks * ((mma > ingest ? mma : ingest) + 40.0) + 2000.0;
+    };
+    const double avg = (tile_cycles(c) * (double)(n_tiles - 1) + tile_cycles(last)) / (double)n_tiles;
+    const double cost = (double)waves * avg;
+    if (best_cost < 0 || cost < best_cost * 0.999) {
+      best_cost = cost;
       best = c;
     }
   }
+  if (cost_out) *cost_out = best_cost;
   return best;
+}
+
+// LDM_GEMM_PAIR=0 / 1 forces the single-CTA / CTA-pair kernel (A/B timing); default: the cost model decides.
+int pair_override() {
+  static int v = -2;
+  if (v == -2) {
+    const char* e = getenv("LDM_GEMM_PAIR");
+    v = e ? atoi(e) : -1;
+  }
+  return v;
 }
 
 }  // namespace
@@ -407,7 +500,32 @@ extern "C" int ldm_gemm_bf16(const ldm_gemm_desc* d, ldm_stream_t stream) {
     LDM_REQUIRE(d->c1 % 64 == 0 && c2 % 64 == 0, LDM_ERR_BAD_SHAPE,
                 "ldm_gemm_bf16: conv3x3 / concat sources need channels %% 64 == 0 (c1=%d c2=%d)", d->c1, c2);
   const int flags = d->flags;
-  int block_n = d->block_n > 0 ? d->block_n : pick_block_n(d->N);
+  // tile geometry first: the block_n choice depends on the number of M tiles
+  GemmParams p{};
+  p.B = d->B;
+  p.H = d->H;
+  p.W = d->W;
+  // A pointwise GEMM has no spatial structure: flatten to one row of B*H*W pixels so tiles are always full,
+  // except for modes whose epilogue needs (b, y, x).
+  if (d->taps == 1 && !(flags & LDM_GEMM_CONVT_LN_SILU) && !d->rowbias) {
+    p.W = d->B * d->H * d->W;
+    p.H = 1;
+    p.B = 1;
+  }
+  pick_box(p.H, p.W, d->taps, &p.bw, &p.bh);
+  p.tiles_x = (p.W + p.bw - 1) / p.bw;
+  p.tiles_y = (p.H + p.bh - 1) / p.bh;
+  p.m_tiles = p.tiles_x * p.tiles_y * p.B;
+  p.kblocks1 = (d->c1 + kBlockK - 1) / kBlockK;
+  p.kblocks = p.kblocks1 + (c2 + kBlockK - 1) / kBlockK;
+  const long kblocks_total = (long)d->taps * p.kblocks;
+  double cost1 = 0.0, cost2 = 0.0;
+  const int bn1 = pick_block_n(d->N, p.m_tiles, kblocks_total, num_sms(), false, &cost1);
+  const int bn2 = pick_block_n(d->N, p.m_tiles, kblocks_total, num_sms(), true, &cost2);
+  const bool pair_ok = p.m_tiles >= 2 && !(flags & LDM_GEMM_CONVT_LN_SILU) && d->block_n <= 0;  // explicit block_n: single CTA
+  bool pair = pair_ok && cost2 < cost1;
+  if (pair_override() >= 0) pair = pair_ok && pair_override() != 0;
+  int block_n = d->block_n > 0 ? d->block_n : (pair ? bn2 : bn1);
   LDM_REQUIRE(block_n % 32 == 0 && block_n >= 32 && block_n <= 256, LDM_ERR_BAD_ARG, "ldm_gemm_bf16: block_n=%d",
               block_n);
   if (flags & LDM_GEMM_GEGLU) LDM_REQUIRE(d->N % 32 == 0, LDM_ERR_BAD_SHAPE, "GEGLU needs N %% 32 == 0");
@@ -425,29 +543,12 @@ extern "C" int ldm_gemm_bf16(const ldm_gemm_desc* d, ldm_stream_t stream) {
                 "ldm_gemm_bf16: CONVT_LN_SILU needs taps=1, N=4*block_n, bias, ln params");
   }
 
-  GemmParams p{};
-  p.B = d->B;
-  p.H = d->H;
-  p.W = d->W;
-  // A pointwise GEMM has no spatial structure: flatten to one row of B*H*W pixels so tiles are always full,
-  // except for modes whose epilogue needs (b, y, x).
-  if (d->taps == 1 && !(flags & LDM_GEMM_CONVT_LN_SILU) && !d->rowbias) {
-    p.W = d->B * d->H * d->W;
-    p.H = 1;
-    p.B = 1;
-  }
-  pick_box(p.H, p.W, d->taps, &p.bw, &p.bh);
-  p.tiles_x = (p.W + p.bw - 1) / p.bw;
-  p.tiles_y = (p.H + p.bh - 1) / p.bh;
-  p.m_tiles = p.tiles_x * p.tiles_y * p.B;
   p.block_n = block_n;
   p.n_tiles = (d->N + block_n - 1) / block_n;
   p.N = d->N;
   p.taps = d->taps;
-  p.kblocks1 = (d->c1 + kBlockK - 1) / kBlockK;
-  p.kblocks = p.kblocks1 + (c2 + kBlockK - 1) / kBlockK;
   p.ktap = d->c1 + c2;
-  p.stage_bytes = kABytes + block_n * kBlockK * 2;
+  p.stage_bytes = kABytes + (pair ? block_n / 2 : block_n) * kBlockK * 2;
   p.stages = (kSmemBudget - 2048) / p.stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   LDM_REQUIRE(p.stages >= 2, LDM_ERR_BAD_SHAPE, "ldm_gemm_bf16: not enough shared memory for 2 stages");
@@ -492,7 +593,7 @@ extern "C" int ldm_gemm_bf16(const ldm_gemm_desc* d, ldm_stream_t stream) {
     const uint64_t ktot = (uint64_t)d->taps * p.ktap;
     const uint64_t dims[2] = {ktot, (uint64_t)d->N};
     const uint64_t str[1] = {ktot * 2};
-    const uint32_t box[2] = {kBlockK, (uint32_t)block_n};
+    const uint32_t box[2] = {kBlockK, (uint32_t)(pair ? block_n / 2 : block_n)};
     int rc = make_tmap(&tmB, d->w, 2, dims, str, box, 2, true);
     if (rc) return rc;
   }
@@ -500,14 +601,37 @@ extern "C" int ldm_gemm_bf16(const ldm_gemm_desc* d, ldm_stream_t stream) {
   const int smem_bytes = p.stages * p.stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
     if (e != cudaSuccess) return set_error(LDM_ERR_CUDA, "cudaFuncSetAttribute(gemm): %s", cudaGetErrorString(e));
     attr_set = true;
+  }
+  if (pair) {
+    const int units = ((p.m_tiles + 1) / 2) * p.n_tiles;
+    int clusters = num_sms() / 2;
+    if (clusters > units) clusters = units;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = as_stream(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true>, tmA1, tmA2, tmB, p);
+    if (e != cudaSuccess) return set_error(LDM_ERR_CUDA, "gemm_tc_kernel<pair> launch: %s", cudaGetErrorString(e));
+    count_launch();
+    return check_launch("gemm_tc_kernel<pair>");
   }
   const int num_tiles = p.m_tiles * p.n_tiles;
   int grid = num_sms();
   if (grid > num_tiles) grid = num_tiles;
-  gemm_tc_kernel<<<grid, kThreads, smem_bytes, as_stream(stream)>>>(tmA1, tmA2, tmB, p);
+  gemm_tc_kernel<false><<<grid, kThreads, smem_bytes, as_stream(stream)>>>(tmA1, tmA2, tmB, p);
   count_launch();
   return check_launch("gemm_tc_kernel");
 }

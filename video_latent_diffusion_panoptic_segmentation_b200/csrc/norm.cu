@@ -77,7 +77,9 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, const __nv
   }
 }
 
-// GroupNorm pass 2: fold the partials (fixed order, fp64), then normalise + affine (+ SiLU), 16 bytes per thread-iteration.
+// GroupNorm pass 2: fold the partials (fixed order, fp64), then normalise + affine (+ SiLU). Same thread layout as
+// pass 1: a thread owns one 8-channel vector position, so its scale/shift (rstd*gamma, beta - mean*rstd*gamma) are
+// computed once and the pixel loop is load -> 8 FMA (+ SiLU) -> store with 4 independent 16-byte loads in flight.
 __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, const __nv_bfloat16* __restrict__ x2, int c1,
                                 int c2, int HW, int groups, const float* __restrict__ partial, int chunks,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
@@ -86,8 +88,10 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, const __nv
   const int C = c1 + c2;
   const int cpg = C / groups;
   const int b = blockIdx.y;
+  const int ppb = blockDim.y;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
   const double n = (double)cpg * (double)HW;
-  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+  for (int g = tid; g < groups; g += blockDim.x * blockDim.y) {
     double a = 0.0, q = 0.0;
     const float* pp = partial + ((long long)b * chunks * groups + g) * 2;
     for (int k = 0; k < chunks; ++k) {
@@ -101,17 +105,9 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, const __nv
     sh[groups + g] = (float)(1.0 / sqrt(var + (double)eps));
   }
   __syncthreads();
-  const int vpp = C / 8;
-  const long long total = (long long)HW * vpp;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int pix = (int)(i / vpp);
-    const int c0 = (int)(i - (long long)pix * vpp) * 8;
-    const __nv_bfloat16* src = (c0 < c1) ? x1 + ((long long)b * HW + pix) * c1 + c0
-                                         : x2 + ((long long)b * HW + pix) * c2 + (c0 - c1);
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(src));
-    const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
-    float f[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
+  const int c0 = threadIdx.x * 8;
+  float sc[8], sf[8];
+  {
     const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c0));
     const float4 gb = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
     const float4 ba = __ldg(reinterpret_cast<const float4*>(beta + c0));
@@ -121,7 +117,24 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, const __nv
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int g = (c0 + j) / cpg;
-      float y = (f[j] - sh[g]) * sh[groups + g] * gm[j] + bt[j];
+      sc[j] = sh[groups + g] * gm[j];
+      sf[j] = fmaf(-sh[g], sc[j], bt[j]);
+    }
+  }
+  const __nv_bfloat16* src;
+  int cs;
+  if (c0 < c1) {
+    src = x1 + (long long)b * HW * c1 + c0; cs = c1;
+  } else {
+    src = x2 + (long long)b * HW * c2 + (c0 - c1); cs = c2;
+  }
+  __nv_bfloat16* dst = out + (long long)b * HW * C + c0;
+  auto apply8 = [&](const uint4& u, int pix) {
+    const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
+    float f[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float y = fmaf(f[j], sc[j], sf[j]);
       f[j] = silu ? silu_f(y) : y;
     }
     uint4 o;
@@ -129,8 +142,18 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, const __nv
     o.y = pack_bf16(f[2], f[3]);
     o.z = pack_bf16(f[4], f[5]);
     o.w = pack_bf16(f[6], f[7]);
-    *reinterpret_cast<uint4*>(out + ((long long)b * HW + pix) * C + c0) = o;
+    *reinterpret_cast<uint4*>(dst + (long long)pix * C) = o;
+  };
+  const int stride = gridDim.x * ppb;
+  int pix = blockIdx.x * ppb + threadIdx.y;
+  for (; pix + 3 * stride < HW; pix += 4 * stride) {
+    const uint4 u0 = ld_nc_v4(src + (long long)pix * cs);
+    const uint4 u1 = ld_nc_v4(src + (long long)(pix + stride) * cs);
+    const uint4 u2 = ld_nc_v4(src + (long long)(pix + 2 * stride) * cs);
+    const uint4 u3 = ld_nc_v4(src + (long long)(pix + 3 * stride) * cs);
+    apply8(u0, pix); apply8(u1, pix + stride); apply8(u2, pix + 2 * stride); apply8(u3, pix + 3 * stride);
   }
+  for (; pix < HW; pix += stride) apply8(ld_nc_v4(src + (long long)pix * cs), pix);
 }
 
 // LayerNorm: one warp per row, row cached in registers (C <= 32*8*kMaxVec).
@@ -240,10 +263,7 @@ extern "C" int ldm_groupnorm_silu(const ldm_groupnorm_desc* d, ldm_stream_t stre
   count_launch();
   int rc = check_launch("gn_stats_kernel");
   if (rc) return rc;
-  const long long total = (long long)d->HW * vpp;
-  int gx = (int)((total + 256 * 4 - 1) / (256 * 4));
-  if (gx < 1) gx = 1;
-  gn_apply_kernel<<<dim3(gx, d->B), 256, sizeof(float) * 2 * d->groups, s>>>(
+  gn_apply_kernel<<<dim3(chunks, d->B), dim3(vpp, ppb), sizeof(float) * 2 * d->groups, s>>>(
       reinterpret_cast<const __nv_bfloat16*>(d->x1), reinterpret_cast<const __nv_bfloat16*>(d->x2), d->c1, c2, d->HW,
       d->groups, partial, chunks, d->gamma, d->beta, d->eps, d->silu, reinterpret_cast<__nv_bfloat16*>(d->out));
   count_launch();
