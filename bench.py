@@ -254,6 +254,24 @@ def run_ours(args):
     ms_e2e, _, _, _ = timed(False, 1, max(1, min(args.steps, 3)))
     fps_e2e = world * B * max(1, min(args.steps, 3)) / (ms_e2e / 1e3)
 
+    # where one step spends its time (one extra, untimed-for-the-metric step with CUDA events between the phases)
+    def phases():
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        evaluator.reset()
+        ev[0].record()
+        lat = tr.sample([""] * B, T, seed=None, rgb_latents=rgb_dev, scheduler=sched, noise=noise_host)
+        ev[1].record()
+        _, cleaned, _ = tr.panoptic_ids(lat)
+        ev[2].record()
+        for b in range(B):
+            evaluator.add_image(cleaned[b], gt_dev[b])
+        evaluator.evaluate()
+        ev[3].record()
+        torch.cuda.synchronize()
+        return {"sampler_50xunet_ddim": ev[0].elapsed_time(ev[1]), "ae_decode_ids_merge": ev[1].elapsed_time(ev[2]),
+                "pq_evaluator": ev[2].elapsed_time(ev[3])}
+
+    phase_ms = phases()
     hbm, tf_burst, tf_sus, which = peaks()
     line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -267,7 +285,8 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(rgb_host.numel() * 4 + noise_host.numel() * 4 + gt_host.numel() * 4),
                     "d2h_bytes_per_step": int(ids_host.numel() * 4)},
             "gpu_launches": int(graph_launches + eager_launches),
-            "clocks": clocks, "pq": {k: res[k] for k in ("pq", "tp", "fp", "fn")}}
+            "clocks": clocks, "pq": {k: res[k] for k in ("pq", "tp", "fp", "fn")},
+            "phases_ms_per_step": {k: round(v, 2) for k, v in phase_ms.items()}}
 
     if rank == 0:
         # roofline of the dominant kernel (gemm_tc_kernel: linear / conv1x1 / implicit conv3x3), measured live with

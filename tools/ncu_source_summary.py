@@ -1,50 +1,54 @@
-"""Summarise `ncu --page source --print-source cuda,sass --csv` output: samples per CUDA source line and per stall reason.
+"""Samples per CUDA source line from `ncu --page source --print-source cuda,sass --csv` (first launch of the kernel).
 
-    ncu -i X.ncu-rep --page source --print-source cuda,sass --csv --kernel-name regex:NAME | python tools/ncu_source_summary.py [N]
+    ncu -i X.ncu-rep --page source --print-source cuda,sass --csv --kernel-name regex:NAME > /tmp/src.csv
+    python tools/ncu_source_summary.py /tmp/src.csv [topN] [kernel-substring]
 """
 import csv
 import sys
+from collections import defaultdict
 
 
 def main():
-    topn = int(sys.argv[1]) if len(sys.argv) > 1 else 30
-    rows = list(csv.reader(sys.stdin))
-    his = [i for i, r in enumerate(rows) if r and r[0] in ("Address", "#", "Line") or (r and "# Samples" in r)]
-    if not his:
-        print("no table found")
-        return
-    # only the first kernel instance
-    blocks = []
-    for k, hi in enumerate(his):
-        end = his[k + 1] - 1 if k + 1 < len(his) else len(rows)
-        blocks.append((rows[hi], rows[hi + 1:end]))
-    for hdr, data in blocks[:2]:
-        col = {h: i for i, h in enumerate(hdr)}
-        if "# Samples" not in col:
+    path = sys.argv[1]
+    topn = int(sys.argv[2]) if len(sys.argv) > 2 else 30
+    want = sys.argv[3] if len(sys.argv) > 3 else None
+    rows = list(csv.reader(open(path)))
+    secs = [i for i, r in enumerate(rows) if r and r[0] == "File Path"]
+    agg, srcs, stall = defaultdict(int), {}, defaultdict(lambda: defaultdict(int))
+    done = set()
+    for si, s in enumerate(secs):
+        fp, fn = rows[s][1], rows[s + 1][1]
+        if want and want not in fn:
             continue
-        stall_cols = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
-        tot = {h: 0 for h in stall_cols}
-        recs = []
-        for r in data:
-            if len(r) < len(hdr):
+        if (fp, fn) in done:
+            continue  # later launches of the same kernel
+        done.add((fp, fn))
+        hdr = rows[s + 2]
+        end = secs[si + 1] if si + 1 < len(secs) else len(rows)
+        col = {}
+        for i, h in enumerate(hdr):
+            col.setdefault(h, i)
+        scols = [h for h in col if h.startswith("stall_") and "Not Issued" not in h]
+        for r in rows[s + 3:end]:
+            if len(r) < len(hdr) or r[0] == "":
                 continue
             try:
                 ns = int(r[col["# Samples"]])
             except ValueError:
                 continue
-            recs.append((ns, r))
-            for h in stall_cols:
+            k = (fp.split("/")[-1], int(r[0]))
+            srcs[k] = r[1].strip()
+            agg[k] += ns
+            for h in scols:
                 try:
-                    tot[h] += int(r[col[h]])
+                    stall[k][h[6:]] += int(r[col[h]])
                 except ValueError:
                     pass
-        total = sum(ns for ns, _ in recs)
-        print(f"== view with first column '{hdr[0]}': {len(recs)} rows, {total} samples")
-        print("   stalls:", ", ".join(f"{h[6:]}={v}" for h, v in sorted(tot.items(), key=lambda kv: -kv[1])[:8]))
-        for ns, r in sorted(recs, key=lambda t: -t[0])[:topn]:
-            st = sorted(((h[6:], int(r[col[h]])) for h in stall_cols if r[col[h]] not in ("", "0")), key=lambda kv: -kv[1])[:3]
-            src = r[col["Source"]].strip()[:100]
-            print(f"{ns:8d} {100.0 * ns / max(1, total):5.1f}% ex={r[col['Instructions Executed']]:>10s} {r[0][-6:]:>6s} {src}  {st}")
+    tot = sum(agg.values())
+    print(f"total samples {tot}")
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1])[:topn]:
+        st = sorted(stall[k].items(), key=lambda kv: -kv[1])[:3]
+        print(f"{v:7d} {100 * v / max(1, tot):5.1f}%  {k[0]}:{k[1]:<4d} {srcs[k][:95]:95s} {st}")
 
 
 if __name__ == "__main__":

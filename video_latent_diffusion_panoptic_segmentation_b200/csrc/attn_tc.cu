@@ -13,6 +13,8 @@
 //   Layouts: q,k [B*heads, seq, dpad] (dpad = 64*ceil(d/64), zero padded), vt [B*heads, vt_rows, seq_pad] (V transposed
 //   so that both MMAs see K-major operands; vt_rows = 16*ceil(d/16); when d % 16 != 0 the caller keeps row d of every
 //   head at 1.0 so the PV MMA also produces the softmax row sums), out [B*seq, heads*d]; all bf16.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "host_util.h"
 
@@ -29,6 +31,19 @@ __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// exp2 on the FMA pipe (Cody-Waite split + degree-3 minimax of 2^f on [-0.5, 0.5], max rel. error 1.0e-4 -- 40x below
+// the bf16 rounding of P): the softmax of the 40-wide heads is bound by the 16/clk/SM MUFU unit, so kPoly of every 8
+// exponentials are computed here instead. x <= 8 (lazy rescale) and x may be -inf (masked tail keys).
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;         // 1.5 * 2^23: round(x) lands in the low mantissa bits
+  const float f = x - (t - 12582912.0f);  // [-0.5, 0.5]
+  float p = fmaf(f, 0.05500891f, 0.24221097f);
+  p = fmaf(p, f, 0.69328293f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 
 template <int D, int NQ, int BKV, int STAGES>
@@ -52,7 +67,7 @@ struct AttnCfg {
   static_assert(kSmem <= 227 * 1024, "smem budget");
 };
 
-template <int D, int NQ, int BKV, int STAGES>
+template <int D, int NQ, int BKV, int STAGES, int kPoly>
 __global__ void __launch_bounds__(AttnCfg<D, NQ, BKV, STAGES>::kThreads, 1)
 flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -72,7 +87,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   uint64_t* s_free = o_full + 2;         // [NQ]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
 
-  const int warp = threadIdx.x >> 5;
+  // warp-uniform by construction, so that the control warps' loops run with uniform control flow (see gemm_tc.cu)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int bh = blockIdx.y;
   const int q_base = blockIdx.x * 128 * NQ;
@@ -110,11 +126,13 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     if (NQ == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      for (int g = 0; g < NQ; ++g) {
-        mbar_arrive_expect_tx(&q_full[g], Cfg::kQBytes);
-        for (int a = 0; a < Cfg::kAtoms; ++a)
-          tma_load_3d(sQ + g * Cfg::kQBytes + a * 128 * 128, &tmQ, &q_full[g], a * 64, q_base + g * 128, bh);
+    {
+      if (elect_one()) {
+        for (int g = 0; g < NQ; ++g) {
+          mbar_arrive_expect_tx(&q_full[g], Cfg::kQBytes);
+          for (int a = 0; a < Cfg::kAtoms; ++a)
+            tma_load_3d(sQ + g * Cfg::kQBytes + a * 128 * 128, &tmQ, &q_full[g], a * 64, q_base + g * 128, bh);
+        }
       }
       int stage = 0;
       uint32_t phase = 0;
@@ -122,11 +140,14 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         mbar_wait(&kv_empty[stage], phase ^ 1);
         uint8_t* sk = sKV + stage * Cfg::kStageBytes;
         uint8_t* sv = sk + Cfg::kKBytes;
-        mbar_arrive_expect_tx(&kv_full[stage], Cfg::kKBytes + Cfg::kVBytes);
-        for (int a = 0; a < Cfg::kAtoms; ++a)
-          tma_load_3d(sk + a * BKV * 128, &tmK, &kv_full[stage], a * 64, j * BKV, bh);
-        for (int a = 0; a < Cfg::kVAtoms; ++a)
-          tma_load_3d(sv + a * Cfg::kDN * 128, &tmV, &kv_full[stage], j * BKV + a * 64, 0, bh);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&kv_full[stage], Cfg::kKBytes + Cfg::kVBytes);
+          for (int a = 0; a < Cfg::kAtoms; ++a)
+            tma_load_3d(sk + a * BKV * 128, &tmK, &kv_full[stage], a * 64, j * BKV, bh);
+          for (int a = 0; a < Cfg::kVAtoms; ++a)
+            tma_load_3d(sv + a * Cfg::kDN * 128, &tmV, &kv_full[stage], j * BKV + a * 64, 0, bh);
+        }
+        __syncwarp();
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
@@ -135,33 +156,39 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (all lanes wait, one lane issues)
+    {
       const uint32_t idesc_s = umma_idesc_bf16(128, BKV);
       const uint32_t idesc_o = umma_idesc_bf16(128, Cfg::kDN);
       auto issue_s = [&](int g, int stage) {
         const uint32_t qa = smem_u32(sQ + g * Cfg::kQBytes);
         const uint32_t ka = smem_u32(sKV + stage * Cfg::kStageBytes);
         const uint32_t d_tmem = tmem_base + g * Cfg::kTmemGroupStride;
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < Cfg::kSteps; ++kk) {
-          const uint64_t da = umma_desc_k_sw128(qa + (kk >> 2) * (128 * 128) + (kk & 3) * 32);
-          const uint64_t db = umma_desc_k_sw128(ka + (kk >> 2) * (BKV * 128) + (kk & 3) * 32);
-          umma_bf16(d_tmem, da, db, idesc_s, kk != 0);
+          for (int kk = 0; kk < Cfg::kSteps; ++kk) {
+            const uint64_t da = umma_desc_k_sw128(qa + (kk >> 2) * (128 * 128) + (kk & 3) * 32);
+            const uint64_t db = umma_desc_k_sw128(ka + (kk >> 2) * (BKV * 128) + (kk & 3) * 32);
+            umma_bf16(d_tmem, da, db, idesc_s, kk != 0);
+          }
+          umma_commit(&s_full[g]);
         }
-        umma_commit(&s_full[g]);
+        __syncwarp();
       };
       auto issue_o = [&](int g, int stage, bool accumulate) {
         const uint32_t pa = smem_u32(sP + g * Cfg::kPBytes);
         const uint32_t va = smem_u32(sKV + stage * Cfg::kStageBytes + Cfg::kKBytes);
         const uint32_t d_tmem = tmem_base + g * Cfg::kTmemGroupStride + BKV;
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < BKV / 16; ++kk) {
-          const uint64_t da = umma_desc_k_sw128(pa + (kk >> 2) * (128 * 128) + (kk & 3) * 32);
-          const uint64_t db = umma_desc_k_sw128(va + (kk >> 2) * (Cfg::kDN * 128) + (kk & 3) * 32);
-          umma_bf16(d_tmem, da, db, idesc_o, accumulate || kk != 0);
+          for (int kk = 0; kk < BKV / 16; ++kk) {
+            const uint64_t da = umma_desc_k_sw128(pa + (kk >> 2) * (128 * 128) + (kk & 3) * 32);
+            const uint64_t db = umma_desc_k_sw128(va + (kk >> 2) * (Cfg::kDN * 128) + (kk & 3) * 32);
+            umma_bf16(d_tmem, da, db, idesc_o, accumulate || kk != 0);
+          }
+          umma_commit(&o_full[g]);
         }
-        umma_commit(&o_full[g]);
+        __syncwarp();
       };
       for (int g = 0; g < NQ; ++g) mbar_wait(&q_full[g], 0);
       int stage = 0;
@@ -190,7 +217,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           tc_fence_after();
           issue_o(g, stage, j > 0);
         }
-        umma_commit(&kv_empty[stage]);
+        if (elect_one()) umma_commit(&kv_empty[stage]);
+        __syncwarp();
         stage = nstage;
         phase = nphase;
       }
@@ -208,8 +236,10 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const uint32_t t_o = t_s + BKV;
     uint8_t* myP = sP + g * Cfg::kPBytes;
     float m = -INFINITY, l = 0.f;      // m: reference maximum the stored P / O are relative to (log2 domain)
+    float m_seen = -INFINITY;          // running row maximum including the previous block (m lags behind it)
     constexpr bool kOnes = Cfg::kOnesRow;  // row sums come out of the PV MMA (ones row of V^T at index D)
-    constexpr float kLazy = 8.0f;       // rescale O only when the row maximum grew by more than 2^8
+    constexpr float kLazy = 8.0f;       // rescale O only when the row maximum grew by more than 2^8 ...
+    constexpr float kRedo = 64.0f;      // ... and redo a block's exponentials if it alone jumps by more than 2^64
 
     for (int j = 0; j < nblk; ++j) {
       const int nvalid = p.seq - j * BKV;  // keys of this block inside the sequence (>= 1)
@@ -226,59 +256,85 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         for (int i = 0; i < BKV; ++i)
           if (i >= nvalid) sv[i] = 0xff800000u;  // -inf
       }
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+
+      // O (TMEM) and l move to the new reference max(m, target) for the rows that need it
+      auto rescale = [&](bool need, float target) {
+        tc_fence_after();
+        const float m_new = need ? target : m;
+        const float alpha = ex2(m - m_new);  // 1 for the rows that keep their reference
+        m = m_new;
+        if (!kOnes) l *= alpha;
 #pragma unroll
-      for (int i = 0; i < BKV; i += 4) {
-        mx0 = fmaxf(mx0, __uint_as_float(sv[i]));
-        mx1 = fmaxf(mx1, __uint_as_float(sv[i + 1]));
-        mx2 = fmaxf(mx2, __uint_as_float(sv[i + 2]));
-        mx3 = fmaxf(mx3, __uint_as_float(sv[i + 3]));
-      }
-      const float m_blk = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
+        for (int c = 0; c < Cfg::kDN; c += 16) {
+          uint32_t v[16];
+          tmem_ld16(t_o + c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+          tmem_st16(t_o + c, v);
+        }
+        tmem_st_wait();
+      };
+      // P = exp2(s*scale - m) as bf16 into the swizzled A-operand tile; the block maximum is tracked in the same
+      // pass (the FMNMX issue between the MUFUs instead of in a MUFU-idle phase of their own)
+      auto exp_pass = [&](float& bmax, float& bsum) {
+        float mx0 = -INFINITY, mx1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < BKV; c += 8) {
+          float e[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float sraw = __uint_as_float(sv[c + i]);
+            const float x = fmaf(sraw, p.scale_log2, -m);
+            e[i] = (i < 8 - kPoly) ? ex2(x) : ex2_poly(x);
+            if (i & 1) mx1 = fmaxf(mx1, sraw); else mx0 = fmaxf(mx0, sraw);
+          }
+          if (!kOnes) {
+            l0 += (e[0] + e[1]) + (e[2] + e[3]);
+            l1 += (e[4] + e[5]) + (e[6] + e[7]);
+          }
+          uint4 u;
+          u.x = pack_bf16(e[0], e[1]);
+          u.y = pack_bf16(e[2], e[3]);
+          u.z = pack_bf16(e[4], e[5]);
+          u.w = pack_bf16(e[6], e[7]);
+          // row r of the K-major SWIZZLE_128B tile: 16-byte chunk index XOR (r & 7)
+          uint8_t* rowp = myP + (c >> 6) * (128 * 128) + r * 128;
+          *reinterpret_cast<uint4*>(rowp + ((((c & 63) >> 3) ^ (r & 7)) << 4)) = u;
+        }
+        bmax = fmaxf(mx0, mx1) * p.scale_log2;  // scale > 0
+        bsum = l0 + l1;
+      };
+
       if (j == 0) {
-        m = m_blk;
+        // the first block needs its true maximum up front (nothing to be relative to yet)
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < BKV; i += 4) {
+          mx0 = fmaxf(mx0, __uint_as_float(sv[i]));
+          mx1 = fmaxf(mx1, __uint_as_float(sv[i + 1]));
+          mx2 = fmaxf(mx2, __uint_as_float(sv[i + 2]));
+          mx3 = fmaxf(mx3, __uint_as_float(sv[i + 3]));
+        }
+        m = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
+        m_seen = m;
       } else {
         // PV of the previous block has finished: P smem may be rewritten and O may be touched
         mbar_wait(&o_full[g], (j - 1) & 1);
-        const bool need = m_blk - m > kLazy;
-        if (__any_sync(0xffffffffu, need)) {
-          tc_fence_after();
-          const float m_new = need ? m_blk : m;
-          const float alpha = ex2(m - m_new);  // 1 for the rows that keep their reference
-          m = m_new;
-          if (!kOnes) l *= alpha;
-#pragma unroll
-          for (int c = 0; c < Cfg::kDN; c += 16) {
-            uint32_t v[16];
-            tmem_ld16(t_o + c, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-            tmem_st16(t_o + c, v);
-          }
-          tmem_st_wait();
+        const bool need = m_seen - m > kLazy;
+        if (__any_sync(0xffffffffu, need)) rescale(need, m_seen);
+      }
+      float bmax, bsum;
+      exp_pass(bmax, bsum);
+      if (j > 0) {
+        const bool redo = bmax - m > kRedo;  // would leave the comfortable fp32 / bf16 range: never on sane inputs
+        if (__any_sync(0xffffffffu, redo)) {
+          rescale(redo, bmax);
+          exp_pass(bmax, bsum);
         }
       }
-      float l0 = 0.f, l1 = 0.f;
-#pragma unroll
-      for (int c = 0; c < BKV; c += 8) {
-        float e[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) e[i] = ex2(fmaf(__uint_as_float(sv[c + i]), p.scale_log2, -m));
-        if (!kOnes) {
-          l0 += (e[0] + e[1]) + (e[2] + e[3]);
-          l1 += (e[4] + e[5]) + (e[6] + e[7]);
-        }
-        uint4 u;
-        u.x = pack_bf16(e[0], e[1]);
-        u.y = pack_bf16(e[2], e[3]);
-        u.z = pack_bf16(e[4], e[5]);
-        u.w = pack_bf16(e[6], e[7]);
-        // row r of the K-major SWIZZLE_128B tile: 16-byte chunk index XOR (r & 7)
-        uint8_t* rowp = myP + (c >> 6) * (128 * 128) + r * 128;
-        *reinterpret_cast<uint4*>(rowp + ((((c & 63) >> 3) ^ (r & 7)) << 4)) = u;
-      }
-      if (!kOnes) l += l0 + l1;
+      m_seen = fmaxf(m_seen, bmax);
+      if (!kOnes) l += bsum;
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&p_full[g]);
@@ -319,7 +375,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   }
 }
 
-template <int D, int NQ, int BKV, int STAGES>
+template <int D, int NQ, int BKV, int STAGES, int kPoly>
 int launch_attn(const ldm_attn_desc* d, cudaStream_t s) {
   using namespace ldm_host;
   using Cfg = AttnCfg<D, NQ, BKV, STAGES>;
@@ -348,7 +404,7 @@ int launch_attn(const ldm_attn_desc* d, cudaStream_t s) {
   p.head_dim = d->head_dim;
   p.scale_log2 = d->scale * 1.4426950408889634f;
   p.out = reinterpret_cast<__nv_bfloat16*>(d->out);
-  auto kern = flash_attn_kernel<D, NQ, BKV, STAGES>;
+  auto kern = flash_attn_kernel<D, NQ, BKV, STAGES, kPoly>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
@@ -377,12 +433,20 @@ extern "C" int ldm_flash_attn_fwd(const ldm_attn_desc* d, ldm_stream_t stream) {
               d->seq_pad, d->head_dim, d->seq);
   cudaStream_t s = as_stream(stream);
   switch (d->head_dim) {
-    case 40:
-      return launch_attn<40, 2, 128, 4>(d, s);
+    case 40: {
+      static int poly = -1;  // LDM_ATTN_POLY=0/2/3: A/B timing of the FMA-pipe exp2 share (default 2 of 8)
+      if (poly < 0) {
+        const char* e = getenv("LDM_ATTN_POLY");
+        poly = e ? atoi(e) : 2;
+      }
+      if (poly == 0) return launch_attn<40, 2, 128, 4, 0>(d, s);
+      if (poly == 3) return launch_attn<40, 2, 128, 4, 3>(d, s);
+      return launch_attn<40, 2, 128, 4, 2>(d, s);
+    }
     case 80:
-      return launch_attn<80, 1, 128, 3>(d, s);
+      return launch_attn<80, 1, 128, 3, 0>(d, s);
     case 160:
-      return launch_attn<160, 1, 64, 3>(d, s);
+      return launch_attn<160, 1, 64, 3, 0>(d, s);
     default:
       return set_error(LDM_ERR_BAD_SHAPE, "ldm_flash_attn_fwd: head_dim %d not built (40, 80, 160)", d->head_dim);
   }

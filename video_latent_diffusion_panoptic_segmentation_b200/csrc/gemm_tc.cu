@@ -12,6 +12,7 @@
 //                                  are prefetched into registers before the accumulator is waited for.
 //   smem ring of (A 128x64 | B block_n x 64) bf16 stages, SWIZZLE_128B, full/empty mbarriers.
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "host_util.h"
@@ -27,6 +28,14 @@ constexpr int kMaxStages = 8;
 constexpr int kEpiWarps = 8;  // two warps per TMEM lane quadrant, each takes every other 32-column chunk
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kSmemBudget = 227 * 1024;
+constexpr int kEpiStageBytes = 2 * 16384;  // epilogue output staging for the TMA-store path
+// Diagnostic switches (env LDM_GEMM_DEBUG, never set by the product): isolate the two halves of the main loop.
+constexpr int kStagedStore = 1 << 20; // internal: epilogue writes the output through shared memory + TMA store
+constexpr int kDbgNoTma = 1 << 29;  // producer signals the stages without loading them
+constexpr int kDbgNoMma = 1 << 30;
+constexpr int kDbgNoFence = 1 << 27; // skip tcgen05.fence::after_thread_sync after the full-barrier wait
+constexpr int kDbgKeepCommit = 1 << 26; // (with nowait) keep the per-k-block tcgen05.commit
+constexpr int kDbgNoWait = 1 << 28; // (with notma) MMA thread neither waits for nor releases stages: a pure MMA stream  // MMA thread releases the stages without issuing MMAs
 
 struct GemmParams {
   // tile geometry
@@ -71,17 +80,22 @@ __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* dst, const float* v)
 template <bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
-               const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by SWIZZLE_128B tiles (the dynamic smem base is the same in both CTAs of a pair).
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * p.stage_bytes);
+  uint8_t* epi_smem = smem + p.stages * p.stage_bytes;  // 2 x 16 KiB output staging (one 128 x 64 bf16 block per half)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + kEpiStageBytes);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tfull_bar = empty_bar + kMaxStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle so that the compiler knows it is warp-uniform: the producer / MMA warps then run
+  // their loops on all 32 lanes with uniform control flow (descriptors and barrier addresses live in uniform
+  // registers) and only the TMA / MMA / commit instructions themselves are issued by one elected lane. Running the
+  // loops on a single lane inside a divergent branch made ptxas wrap every UTCHMMA in an ELECT / R2UR.BROADCAST loop.
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const uint32_t rank = kPair ? cluster_ctarank() : 0u;   // 0 = leader
   const int worker = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -91,6 +105,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     tma_prefetch_desc(&tmA1);
     tma_prefetch_desc(&tmA2);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmO);
     for (int i = 0; i < p.stages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -125,7 +140,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = worker; tile < num_tiles; tile += num_workers) {
@@ -142,12 +157,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           const int dy = (p.taps == 9) ? tap / 3 - 1 : 0;
           const int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
           for (int kb = 0; kb < p.kblocks; ++kb) {
+            if (p.flags & kDbgNoWait) continue;
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * p.stage_bytes;
             uint8_t* sb = sa + kABytes;
             const CUtensorMap* tmA = (kb < p.kblocks1) ? &tmA1 : &tmA2;
             const int kc = (kb < p.kblocks1 ? kb : kb - p.kblocks1) * kBlockK;
-            if (kPair) {
+            if (!elect_one()) {
+            } else if (p.flags & kDbgNoTma) {
+              if (rank == 0) mbar_arrive(&full_bar[stage]);
+            } else if (kPair) {
               // the leader's barrier collects the bytes of both CTAs
               if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (a_bytes + b_bytes));
               tma_load_4d_pair(sa, tmA, &full_bar[stage], kc, x0 + dx, y0 + dy, b);
@@ -168,7 +187,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (pair: leader CTA only)
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {
       const uint32_t idesc = umma_idesc_bf16(kPair ? 256 : kBlockM, (uint32_t)p.block_n);
       int stage = 0;
       uint32_t phase = 0;
@@ -180,26 +199,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)as * 256u;
         for (int ks = 0; ks < ksteps; ++ks) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
+          if (!(p.flags & kDbgNoWait)) {
+            mbar_wait(&full_bar[stage], phase);
+            if (!(p.flags & kDbgNoFence)) tc_fence_after();
+          }
           const uint32_t sa = smem_u32(smem + stage * p.stage_bytes);
           const uint64_t da = umma_desc_k_sw128(sa);
           const uint64_t db = umma_desc_k_sw128(sa + kABytes);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            // advance 16 bf16 = 32 bytes inside the 128-byte swizzle atom: +2 in 16-byte units
-            if (kPair)
-              umma_bf16_pair(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (ks | k) != 0);
-            else
-              umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (ks | k) != 0);
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              if (p.flags & kDbgNoMma) break;
+              // advance 16 bf16 = 32 bytes inside the 128-byte swizzle atom: +2 in 16-byte units
+              if (kPair)
+                umma_bf16_pair(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (ks | k) != 0);
+              else
+                umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (ks | k) != 0);
+            }
+            if ((p.flags & kDbgNoWait) && !(p.flags & kDbgKeepCommit)) {
+            } else if (kPair) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           }
-          if (kPair) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        if (kPair) umma_commit_pair(&tfull_bar[as]); else umma_commit(&tfull_bar[as]);
+        if (elect_one()) {
+          if (kPair) umma_commit_pair(&tfull_bar[as]); else umma_commit(&tfull_bar[as]);
+        }
+        __syncwarp();
         if (++as == 2) {
           as = 0;
           aphase ^= 1;
@@ -213,6 +242,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     const int half = (warp - 2) >> 2;     // 0: even 32-column chunks, 1: odd chunks
     const int r = quad * 32 + lane;
     const bool plain = !(p.flags & (LDM_GEMM_CONVT_LN_SILU | LDM_GEMM_GEGLU | LDM_GEMM_QKV_SPLIT));
+    const bool geglu = (p.flags & LDM_GEMM_GEGLU) != 0;
+    const bool staged = (p.flags & kStagedStore) != 0;  // bf16 [rows, N] (or GEGLU [rows, N/2]) through smem + TMA store
+    const bool epi_leader = (warp == 2 + 4 * half) && lane == 0;  // issues this half's TMA stores
+    uint8_t* sbuf = epi_smem + half * 16384;
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = worker; tile < num_tiles; tile += num_workers) {
@@ -230,13 +263,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       const int n0 = n_tile * p.block_n;
 
       // residual rows of this tile: issue every load now, so that they are in flight while the MMAs finish
+      // staged path: a half owns 64-column output blocks (ob = half, half + 2), i.e. chunk ci covers columns
+      // (2*(ci>>1) + half)*64 + (ci&1)*32; direct path: a half owns every other 32-column chunk.
       uint4 rs[4][4];
       const bool use_res = plain && p.residual != nullptr && valid;
       if (use_res) {
         const __nv_bfloat16* rrow = p.residual + grow * p.N + n0;
 #pragma unroll
         for (int ci = 0; ci < 4; ++ci) {
-          const int c = (2 * ci + half) * 32;
+          // (the last 64-column block of a block_n that is not a multiple of 64 is shifted left to end at block_n)
+          const int cb = (2 * (ci >> 1) + half) * 64;
+          const int c = staged ? (cb < p.block_n ? min(cb, p.block_n - 64) + (ci & 1) * 32 : p.block_n)
+                               : (2 * ci + half) * 32;
 #pragma unroll
           for (int g = 0; g < 4; ++g)
             if (c < p.block_n && n0 + c + g * 8 < p.N) rs[ci][g] = ld_nc_v4(rrow + c + g * 8);
@@ -293,6 +331,92 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             }
           }
         }
+        }
+      } else if (staged) {
+        // 64 output columns (= one 128-byte swizzle atom per row) at a time: registers -> swizzled smem -> TMA store.
+        // The TMA store clips pixels / columns outside the tensor, so ragged tiles need no predication here.
+        const int acc_w = geglu ? 128 : 64;  // accumulator columns behind 64 output columns
+#pragma unroll
+        for (int oi = 0; oi < 2; ++oi) {
+          // a ragged last block is shifted left so that it ends at block_n: the overlap is rewritten with the same values
+          if ((2 * oi + half) * acc_w >= p.block_n) break;
+          const int c0 = min((2 * oi + half) * acc_w, p.block_n - acc_w);
+          if (epi_leader) bulk_wait_read0();     // the previous store out of this buffer has been read
+          named_bar_sync(1 + half, 128);
+#pragma unroll
+          for (int cq = 0; cq < 4; ++cq) {
+            const int cc = cq * 32;
+            if (cc >= acc_w) break;
+            const int c = c0 + cc;
+            uint32_t v[32];
+            tmem_ld32(t_addr + c, v);
+            tmem_ld_wait();
+            const int nc = n0 + c;
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            if (p.bias) {
+              const float4* bp = reinterpret_cast<const float4*>(p.bias + nc);
+#pragma unroll
+              for (int g = 0; g < 8; ++g)
+                if (nc + g * 4 < p.N) {
+                  const float4 bv = __ldg(bp + g);
+                  f[g * 4] += bv.x; f[g * 4 + 1] += bv.y; f[g * 4 + 2] += bv.z; f[g * 4 + 3] += bv.w;
+                }
+            }
+            if (p.rowbias) {
+              const float4* bp = reinterpret_cast<const float4*>(p.rowbias + (long long)b * p.N + nc);
+#pragma unroll
+              for (int g = 0; g < 8; ++g)
+                if (nc + g * 4 < p.N) {
+                  const float4 bv = __ldg(bp + g);
+                  f[g * 4] += bv.x; f[g * 4 + 1] += bv.y; f[g * 4 + 2] += bv.z; f[g * 4 + 3] += bv.w;
+                }
+            }
+            uint8_t* rowp = sbuf + r * 128;
+            if (geglu) {
+              // columns [0,16) value, [16,32) gate of the same 16 outputs -> output chunk pair cq*2, cq*2+1
+              float o[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) o[j] = f[j] * gelu_erf_fast(f[16 + j]);
+#pragma unroll
+              for (int g = 0; g < 2; ++g) {
+                uint4 u;
+                u.x = pack_bf16(o[g * 8 + 0], o[g * 8 + 1]); u.y = pack_bf16(o[g * 8 + 2], o[g * 8 + 3]);
+                u.z = pack_bf16(o[g * 8 + 4], o[g * 8 + 5]); u.w = pack_bf16(o[g * 8 + 6], o[g * 8 + 7]);
+                *reinterpret_cast<uint4*>(rowp + (((cq * 2 + g) ^ (r & 7)) << 4)) = u;
+              }
+            } else {
+              if (use_res) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                  if (nc + g * 8 >= p.N) break;
+                  const uint4 u = rs[oi * 2 + cq][g];
+                  const float2 a0 = unpack_bf16(u.x), a1 = unpack_bf16(u.y), a2 = unpack_bf16(u.z), a3 = unpack_bf16(u.w);
+                  f[g * 8 + 0] += a0.x; f[g * 8 + 1] += a0.y; f[g * 8 + 2] += a1.x; f[g * 8 + 3] += a1.y;
+                  f[g * 8 + 4] += a2.x; f[g * 8 + 5] += a2.y; f[g * 8 + 6] += a3.x; f[g * 8 + 7] += a3.y;
+                }
+              }
+              if (p.flags & LDM_GEMM_SILU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = silu_f(f[j]);
+              }
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                uint4 u;
+                u.x = pack_bf16(f[g * 8 + 0], f[g * 8 + 1]); u.y = pack_bf16(f[g * 8 + 2], f[g * 8 + 3]);
+                u.z = pack_bf16(f[g * 8 + 4], f[g * 8 + 5]); u.w = pack_bf16(f[g * 8 + 6], f[g * 8 + 7]);
+                *reinterpret_cast<uint4*>(rowp + (((cq * 4 + g) ^ (r & 7)) << 4)) = u;
+              }
+            }
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1 + half, 128);
+          if (epi_leader) {
+            const int ncol = geglu ? (n0 + c0) / 2 : n0 + c0;
+            tma_store_4d(&tmO, sbuf, ncol, tx * p.bw, ty * p.bh, b);
+            bulk_commit();
+          }
         }
       } else {
 #pragma unroll
@@ -409,6 +533,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     }
   }
 
+  if (warp >= 2 && lane == 0 && ((warp - 2) & 3) == 0) bulk_wait_all();  // outstanding TMA stores of this half
   tc_fence_before();
   if (kPair) cluster_sync_all(); else __syncthreads();  // pair: neither CTA may exit while its peer can still signal it
   if (warp == 1) {
@@ -475,6 +600,30 @@ int pick_block_n(int N, long m_tiles, long kblocks, int sms, bool pair, double* 
   return best;
 }
 
+int debug_flags() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LDM_GEMM_DEBUG");
+    v = 0;
+    if (e && strstr(e, "notma")) v |= kDbgNoTma;
+    if (e && strstr(e, "nomma")) v |= kDbgNoMma;
+    if (e && strstr(e, "nowait")) v |= kDbgNoWait | kDbgNoTma;
+    if (e && strstr(e, "nofence")) v |= kDbgNoFence;
+    if (e && strstr(e, "keepcommit")) v |= kDbgKeepCommit;
+  }
+  return v;
+}
+
+// LDM_GEMM_STAGED=0 keeps the direct (row-per-thread) global stores (A/B timing)
+bool staged_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LDM_GEMM_STAGED");
+    v = e ? atoi(e) : 1;
+  }
+  return v != 0;
+}
+
 // LDM_GEMM_PAIR=0 / 1 forces the single-CTA / CTA-pair kernel (A/B timing); default: the cost model decides.
 int pair_override() {
   static int v = -2;
@@ -522,10 +671,13 @@ extern "C" int ldm_gemm_bf16(const ldm_gemm_desc* d, ldm_stream_t stream) {
   double cost1 = 0.0, cost2 = 0.0;
   const int bn1 = pick_block_n(d->N, p.m_tiles, kblocks_total, num_sms(), false, &cost1);
   const int bn2 = pick_block_n(d->N, p.m_tiles, kblocks_total, num_sms(), true, &cost2);
-  const bool pair_ok = p.m_tiles >= 2 && !(flags & LDM_GEMM_CONVT_LN_SILU) && d->block_n <= 0;  // explicit block_n: single CTA
+  // an explicit block_n keeps the single-CTA kernel (unless the A/B override forces pairs on a pairable block_n)
+  const bool pair_ok = p.m_tiles >= 2 && !(flags & LDM_GEMM_CONVT_LN_SILU) &&
+                       (d->block_n <= 0 || (pair_override() == 1 && d->block_n >= 64 && d->block_n % 32 == 0));
   bool pair = pair_ok && cost2 < cost1;
   if (pair_override() >= 0) pair = pair_ok && pair_override() != 0;
   int block_n = d->block_n > 0 ? d->block_n : (pair ? bn2 : bn1);
+  if ((flags & LDM_GEMM_GEGLU) && d->block_n <= 0 && block_n < 128) block_n = 128;  // staged GEGLU blocks span 128 columns
   LDM_REQUIRE(block_n % 32 == 0 && block_n >= 32 && block_n <= 256, LDM_ERR_BAD_ARG, "ldm_gemm_bf16: block_n=%d",
               block_n);
   if (flags & LDM_GEMM_GEGLU) LDM_REQUIRE(d->N % 32 == 0, LDM_ERR_BAD_SHAPE, "GEGLU needs N %% 32 == 0");
@@ -549,10 +701,14 @@ extern "C" int ldm_gemm_bf16(const ldm_gemm_desc* d, ldm_stream_t stream) {
   p.taps = d->taps;
   p.ktap = d->c1 + c2;
   p.stage_bytes = kABytes + (pair ? block_n / 2 : block_n) * kBlockK * 2;
-  p.stages = (kSmemBudget - 2048) / p.stage_bytes;
+  p.stages = (kSmemBudget - 2048 - kEpiStageBytes) / p.stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   LDM_REQUIRE(p.stages >= 2, LDM_ERR_BAD_SHAPE, "ldm_gemm_bf16: not enough shared memory for 2 stages");
-  p.flags = flags;
+  // bf16 [rows, N] outputs (and GEGLU's [rows, N/2]) leave through shared memory + TMA store
+  const int n_out = (flags & LDM_GEMM_GEGLU) ? d->N / 2 : d->N;
+  const bool staged = !(flags & (LDM_GEMM_OUT_F32 | LDM_GEMM_OUT_NCHW_F32 | LDM_GEMM_QKV_SPLIT | LDM_GEMM_CONVT_LN_SILU)) &&
+                      n_out >= 64 && n_out % 8 == 0 && block_n >= ((flags & LDM_GEMM_GEGLU) ? 128 : 64) && staged_enabled();
+  p.flags = flags | debug_flags() | (staged ? kStagedStore : 0);
   p.bias = d->bias;
   p.rowbias = d->rowbias;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(d->residual);
@@ -598,7 +754,16 @@ extern "C" int ldm_gemm_bf16(const ldm_gemm_desc* d, ldm_stream_t stream) {
     if (rc) return rc;
   }
 
-  const int smem_bytes = p.stages * p.stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  CUtensorMap tmO = tmB;
+  if (staged) {
+    const uint64_t dims[4] = {(uint64_t)n_out, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.B};
+    const uint64_t str[3] = {(uint64_t)n_out * 2, (uint64_t)n_out * 2 * p.W, (uint64_t)n_out * 2 * p.W * p.H};
+    const uint32_t box[4] = {64, (uint32_t)p.bw, (uint32_t)p.bh, 1};
+    int rc = make_tmap(&tmO, d->out, 4, dims, str, box, 2, true);
+    if (rc) return rc;
+  }
+
+  const int smem_bytes = p.stages * p.stage_bytes + kEpiStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
@@ -623,7 +788,7 @@ extern "C" int ldm_gemm_bf16(const ldm_gemm_desc* d, ldm_stream_t stream) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true>, tmA1, tmA2, tmB, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true>, tmA1, tmA2, tmB, tmO, p);
     if (e != cudaSuccess) return set_error(LDM_ERR_CUDA, "gemm_tc_kernel<pair> launch: %s", cudaGetErrorString(e));
     count_launch();
     return check_launch("gemm_tc_kernel<pair>");
@@ -631,7 +796,7 @@ extern "C" int ldm_gemm_bf16(const ldm_gemm_desc* d, ldm_stream_t stream) {
   const int num_tiles = p.m_tiles * p.n_tiles;
   int grid = num_sms();
   if (grid > num_tiles) grid = num_tiles;
-  gemm_tc_kernel<false><<<grid, kThreads, smem_bytes, as_stream(stream)>>>(tmA1, tmA2, tmB, p);
+  gemm_tc_kernel<false><<<grid, kThreads, smem_bytes, as_stream(stream)>>>(tmA1, tmA2, tmB, tmO, p);
   count_launch();
   return check_launch("gemm_tc_kernel");
 }

@@ -220,6 +220,81 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, const floa
   }
 }
 
+// LayerNorm for C = LPR * 40 (320 / 640 / 1280): LPR lanes share a row, five 16-byte vectors per lane, 32/LPR rows per
+// warp -- every lane busy, five independent loads in flight per lane, sub-warp xor-shuffle reductions.
+template <int LPR>
+__global__ void layernorm_rows_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, __nv_bfloat16* __restrict__ out, int rows, float eps) {
+  constexpr int C = LPR * 40;
+  constexpr int RPW = 32 / LPR;  // rows per warp
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, sl = lane % LPR;
+  const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long row = warp_global * RPW + sub;
+  if (row >= rows) return;  // whole sub-groups leave together; the shuffles below stay inside a sub-group
+  const __nv_bfloat16* src = x + row * C;
+  uint4 u[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) u[k] = ld_nc_v4(src + (sl + k * LPR) * 8);
+  float f[5][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const float2 a = unpack_bf16(u[k].x), b2 = unpack_bf16(u[k].y), c = unpack_bf16(u[k].z), d = unpack_bf16(u[k].w);
+    f[k][0] = a.x; f[k][1] = a.y; f[k][2] = b2.x; f[k][3] = b2.y;
+    f[k][4] = c.x; f[k][5] = c.y; f[k][6] = d.x; f[k][7] = d.y;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sum += f[k][j];
+  }
+  const unsigned mask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(mask, sum, o);
+  const float mean = sum / (float)C;
+  float sq = 0.f;
+#pragma unroll
+  for (int k = 0; k < 5; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float d = f[k][j] - mean;
+      sq += d * d;
+    }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(mask, sq, o);
+  const float rstd = rsqrtf(sq / (float)C + eps);
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const int c0 = (sl + k * LPR) * 8;
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c0));
+    const float4 gb = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
+    const float4 ba = __ldg(reinterpret_cast<const float4*>(beta + c0));
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
+    const float gm[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+    const float bt[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = (f[k][j] - mean) * rstd * gm[j] + bt[j];
+    uint4 w;
+    w.x = pack_bf16(o[0], o[1]);
+    w.y = pack_bf16(o[2], o[3]);
+    w.z = pack_bf16(o[4], o[5]);
+    w.w = pack_bf16(o[6], o[7]);
+    *reinterpret_cast<uint4*>(out + row * C + c0) = w;
+  }
+}
+
+template <int LPR>
+static int launch_layernorm_rows(const void* x, const float* gamma, const float* beta, void* out, int rows, float eps,
+                                 cudaStream_t s) {
+  constexpr int RPW = 32 / LPR;
+  const int wpb = 8;
+  const long long warps = ((long long)rows + RPW - 1) / RPW;
+  const int grid = (int)((warps + wpb - 1) / wpb);
+  layernorm_rows_kernel<LPR><<<grid, wpb * 32, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta,
+                                                      reinterpret_cast<__nv_bfloat16*>(out), rows, eps);
+  ldm_host::count_launch();
+  return ldm_host::check_launch("layernorm_rows_kernel");
+}
+
 }  // namespace
 
 static int gn_chunks(int B, int HW, int ppb) {
@@ -276,6 +351,9 @@ extern "C" int ldm_layernorm(const void* x, const float* gamma, const float* bet
   LDM_REQUIRE(x && gamma && beta && out, LDM_ERR_BAD_ARG, "ldm_layernorm: null arg");
   LDM_REQUIRE(rows > 0 && C > 0 && C % 8 == 0 && C <= 32 * 8 * kMaxVec, LDM_ERR_BAD_SHAPE,
               "ldm_layernorm: rows=%d C=%d unsupported (C %% 8 == 0, C <= %d)", rows, C, 32 * 8 * kMaxVec);
+  if (C == 320) return launch_layernorm_rows<8>(x, gamma, beta, out, rows, eps, as_stream(stream));
+  if (C == 640) return launch_layernorm_rows<16>(x, gamma, beta, out, rows, eps, as_stream(stream));
+  if (C == 1280) return launch_layernorm_rows<32>(x, gamma, beta, out, rows, eps, as_stream(stream));
   const int wpb = 8;
   int grid = (rows + wpb - 1) / wpb;
   const int cap = num_sms() * 16;
