@@ -137,7 +137,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int j = 0; j < nblk; ++j) {
-        mbar_wait(&kv_empty[stage], phase ^ 1);
+        mbar_wait_sleep(&kv_empty[stage], phase ^ 1, 128);
         uint8_t* sk = sKV + stage * Cfg::kStageBytes;
         uint8_t* sv = sk + Cfg::kKBytes;
         if (elect_one()) {
@@ -434,14 +434,14 @@ extern "C" int ldm_flash_attn_fwd(const ldm_attn_desc* d, ldm_stream_t stream) {
   cudaStream_t s = as_stream(stream);
   switch (d->head_dim) {
     case 40: {
-      static int poly = -1;  // LDM_ATTN_POLY=0/2/3: A/B timing of the FMA-pipe exp2 share (default 2 of 8)
+      static int poly = -1;  // LDM_ATTN_POLY=0/1/2: A/B timing of the FMA-pipe exp2 share (default 1 of 8)
       if (poly < 0) {
         const char* e = getenv("LDM_ATTN_POLY");
-        poly = e ? atoi(e) : 2;
+        poly = e ? atoi(e) : 1;
       }
       if (poly == 0) return launch_attn<40, 2, 128, 4, 0>(d, s);
-      if (poly == 3) return launch_attn<40, 2, 128, 4, 3>(d, s);
-      return launch_attn<40, 2, 128, 4, 2>(d, s);
+      if (poly == 2) return launch_attn<40, 2, 128, 4, 2>(d, s);
+      return launch_attn<40, 2, 128, 4, 1>(d, s);
     }
     case 80:
       return launch_attn<80, 1, 128, 3, 0>(d, s);

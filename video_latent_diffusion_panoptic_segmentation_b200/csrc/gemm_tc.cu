@@ -35,6 +35,7 @@ constexpr int kDbgNoTma = 1 << 29;  // producer signals the stages without loadi
 constexpr int kDbgNoMma = 1 << 30;
 constexpr int kDbgNoFence = 1 << 27; // skip tcgen05.fence::after_thread_sync after the full-barrier wait
 constexpr int kDbgKeepCommit = 1 << 26; // (with nowait) keep the per-k-block tcgen05.commit
+constexpr int kDbgAltAcc = 1 << 25;  // (timing only, wrong results) alternate two accumulators between consecutive MMAs
 constexpr int kDbgNoWait = 1 << 28; // (with notma) MMA thread neither waits for nor releases stages: a pure MMA stream  // MMA thread releases the stages without issuing MMAs
 
 struct GemmParams {
@@ -158,7 +159,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           const int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
           for (int kb = 0; kb < p.kblocks; ++kb) {
             if (p.flags & kDbgNoWait) continue;
-            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_wait_sleep(&empty_bar[stage], phase ^ 1, 32);
             uint8_t* sa = smem + stage * p.stage_bytes;
             uint8_t* sb = sa + kABytes;
             const CUtensorMap* tmA = (kb < p.kblocks1) ? &tmA1 : &tmA2;
@@ -211,10 +212,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             for (int k = 0; k < kBlockK / 16; ++k) {
               if (p.flags & kDbgNoMma) break;
               // advance 16 bf16 = 32 bytes inside the 128-byte swizzle atom: +2 in 16-byte units
+              const uint32_t dt = (p.flags & kDbgAltAcc) ? d_tmem + (uint32_t)(k & 1) * 128u : d_tmem;
               if (kPair)
-                umma_bf16_pair(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (ks | k) != 0);
+                umma_bf16_pair(dt, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (ks | k) != 0);
               else
-                umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (ks | k) != 0);
+                umma_bf16(dt, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (ks | k) != 0);
             }
             if ((p.flags & kDbgNoWait) && !(p.flags & kDbgKeepCommit)) {
             } else if (kPair) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
@@ -281,7 +283,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         }
       }
 
-      mbar_wait(&tfull_bar[as], aphase);
+      mbar_wait_sleep(&tfull_bar[as], aphase, 64);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)as * 256u;
 
@@ -567,30 +569,31 @@ void pick_box(int H, int W, int taps, int* bw_out, int* bh_out) {
   *bh_out = best_bh;
 }
 
-// Choose block_n with a small cost model of the persistent schedule, calibrated on B200 (tools/profile_kernels.py
-// --sweep, profiles/r01b_sweep_block_n.json): tiles run in waves over the SMs; one 64-wide k-block of a tile costs the
-// slower of the tensor pipe (4 MMAs of block_n/2 cycles at M = 128) and the SM's operand ingest from L2 (A 16 KiB +
-// B block_n*128 B at ~56 B/cycle -- the binding term for every block_n <= 256), plus ~2000 cycles per tile of
-// pipeline fill / epilogue drain. Avoids the two failure modes of "largest tile that divides N": a second, nearly
-// empty wave (150 tiles on 148 SMs) and a handful of huge tiles when M is small (M = 960 at the 6x20 level).
-// pair = true: work items are 256 x block_n tiles on SM pairs and each CTA ingests only half of the B rows.
-int pick_block_n(int N, long m_tiles, long kblocks, int sms, bool pair, double* cost_out) {
-  const int cands[] = {256, 192, 160, 128, 96};
+// Choose block_n (and single CTA vs CTA pair) with a cost model of the persistent schedule, fitted to block_n sweeps on
+// B200 (tools/profile_kernels.py --sweep; profiles/r01d_sweep_block_n*.json): work items run in waves over the SMs (or
+// SM pairs); an item costs kblocks * 4 MMAs of a measured per-MMA time plus a per-item epilogue / pipeline term.
+// Measured per-MMA cycles (M = 128 per SM, K = 16): roughly a 100-cycle floor for N <= 128 and ~60 + operand bytes /
+// 114 B/clk above it -- the tensor pipe's shared-memory operand read, not its math, is what binds, which is why the
+// CTA pair (each SM reads only half of B) wins on the long-K convolutions, and why N = 160 beats N = 256 for 320-wide
+// layers. The pair's cross-CTA accumulator hand-off costs more per item, so short-K GEMMs stay on single CTAs.
+// Avoids the two failure modes of "largest tile that divides N": a second, nearly empty wave (150 tiles on 148 SMs) and a
+// handful of huge tiles when M is small (M = 960 at the 6x20 level).
+int pick_block_n(int N, long m_tiles, long kblocks, int sms, bool pair, int taps, double* cost_out) {
+  static const int cands[] = {256, 224, 192, 160, 128, 96};
+  static const double mma_single[] = {167, 158, 151, 141, 111, 106};
+  static const double mma_pair[] = {160, 149, 136, 124, 99, 92};
   int best = 256;
   double best_cost = -1.0;
   const long m_units = pair ? (m_tiles + 1) / 2 : m_tiles;
   const long workers = pair ? sms / 2 : sms;
-  for (int c : cands) {
+  for (int i = 0; i < 6; ++i) {
+    const int c = cands[i];
+    if (c == 224 && taps != 9) continue;  // 224 only pays on the long-K convolutions (and is erratic on short K)
     const long n_tiles = (N + c - 1) / c;
-    const int last = N - (int)(n_tiles - 1) * c;  // columns of the ragged last N tile (its B rows beyond N are not fetched)
     const long waves = (m_units * n_tiles + workers - 1) / workers;
-    auto tile_cycles = [&](int cols) {
-      const double mma = 2.0 * c;
-      const double ingest = (16384.0 + (pair ? 64.0 : 128.0) * cols) / 56.0;
-      return (double)kblocks * ((mma > ingest ? mma : ingest) + 40.0) + 2000.0;
-    };
-    const double avg = (tile_cycles(c) * (double)(n_tiles - 1) + tile_cycles(last)) / (double)n_tiles;
-    const double cost = (double)waves * avg;
+    const double item = (double)kblocks * 4.0 * (pair ? mma_pair[i] : mma_single[i]) +
+                        (pair ? 3300.0 + 11.0 * c : 1000.0 + 17.0 * c);
+    const double cost = (double)waves * item;
     if (best_cost < 0 || cost < best_cost * 0.999) {
       best_cost = cost;
       best = c;
@@ -609,6 +612,7 @@ int debug_flags() {
     if (e && strstr(e, "nomma")) v |= kDbgNoMma;
     if (e && strstr(e, "nowait")) v |= kDbgNoWait | kDbgNoTma;
     if (e && strstr(e, "nofence")) v |= kDbgNoFence;
+    if (e && strstr(e, "altacc")) v |= kDbgAltAcc;
     if (e && strstr(e, "keepcommit")) v |= kDbgKeepCommit;
   }
   return v;
@@ -669,8 +673,8 @@ extern "C" int ldm_gemm_bf16(const ldm_gemm_desc* d, ldm_stream_t stream) {
   p.kblocks = p.kblocks1 + (c2 + kBlockK - 1) / kBlockK;
   const long kblocks_total = (long)d->taps * p.kblocks;
   double cost1 = 0.0, cost2 = 0.0;
-  const int bn1 = pick_block_n(d->N, p.m_tiles, kblocks_total, num_sms(), false, &cost1);
-  const int bn2 = pick_block_n(d->N, p.m_tiles, kblocks_total, num_sms(), true, &cost2);
+  const int bn1 = pick_block_n(d->N, p.m_tiles, kblocks_total, num_sms(), false, d->taps, &cost1);
+  const int bn2 = pick_block_n(d->N, p.m_tiles, kblocks_total, num_sms(), true, d->taps, &cost2);
   // an explicit block_n keeps the single-CTA kernel (unless the A/B override forces pairs on a pairable block_n)
   const bool pair_ok = p.m_tiles >= 2 && !(flags & LDM_GEMM_CONVT_LN_SILU) &&
                        (d->block_n <= 0 || (pair_override() == 1 && d->block_n >= 64 && d->block_n % 32 == 0));
