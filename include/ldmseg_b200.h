@@ -86,6 +86,10 @@ typedef struct ldm_gemm_desc {
   int32_t heads, head_dim, dpad, seq, seq_pad; /* QKV_SPLIT geometry (seq = tokens per image)    */
   int32_t vt_rows;      /* rows per head of vt (ldm_attn_vt_rows(head_dim)); 0 = head_dim         */
   int32_t n_store;      /* OUT_NCHW_F32: channels stored (0 = N)                                 */
+  const void* identity; /* optional bf16 [256,256] identity matrix (caller-owned, may be shared by all calls). When
+                           given, a short-K pointwise GEMM adds `residual` on the tensor core: the residual rows
+                           are streamed by TMA as extra K blocks against identity weights instead of being read
+                           row by row in the epilogue. NULL: always the epilogue path.                    */
 } ldm_gemm_desc;
 
 int ldm_gemm_bf16(const ldm_gemm_desc* d, ldm_stream_t stream);

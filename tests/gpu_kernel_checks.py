@@ -18,6 +18,19 @@ DEV = "cuda"
 bf16 = torch.bfloat16
 
 
+def _poison(t):
+    """Outputs start poisoned (NaN / a sentinel), so that an element a kernel fails to write cannot pass by luck."""
+    return t.fill_(float("nan")) if t.is_floating_point() else t.fill_(-12345)
+
+
+def _empty(*a, **k):
+    return _poison(torch.empty(*a, **k))
+
+
+def _empty_like(*a, **k):
+    return _poison(torch.empty_like(*a, **k))
+
+
 def _gen(seed):
     g = torch.Generator(device="cpu")
     g.manual_seed(seed)
@@ -57,7 +70,7 @@ def check_ddim():
     a_t, a_p = torch.tensor(0.0047), torch.tensor(0.0060)
     coef = torch.stack([(1 - a_t) ** 0.5, a_t ** 0.5, a_p ** 0.5, (1 - a_p) ** 0.5]).float().view(1, 4).to(DEV)
     ti = torch.zeros(1, dtype=torch.int32, device=DEV)
-    prev, x0 = torch.empty_like(x), torch.empty_like(x)
+    prev, x0 = _empty_like(x), _empty_like(x)
     ops.ddim_step(eps, x, coef, ti, prev, x0)
     c = coef[0].cpu()
     xc, ec = x.cpu(), eps.cpu()
@@ -72,7 +85,7 @@ def check_ddim():
 def check_layernorm(C=640, rows=1000):
     x = _randn((rows, C), 3, dtype=bf16)
     g, b = _randn((C,), 4) * 0.2 + 1, _randn((C,), 5) * 0.1
-    out = torch.empty_like(x)
+    out = _empty_like(x)
     ops.layernorm(x, g, b, out, 1e-5)
     ref = F.layer_norm(x.float(), (C,), g, b, 1e-5)
     return _stats(out, ref, f"layernorm C={C}", 2e-2, 1e-2)
@@ -83,7 +96,7 @@ def check_groupnorm(c1=320, c2=0, HW=468, B=2, silu=True, eps=1e-5):
     x2 = (_randn((B, HW, c2), 7, dtype=bf16) * 0.7 - 0.2) if c2 else None
     C = c1 + c2
     g, b = _randn((C,), 8) * 0.2 + 1, _randn((C,), 9) * 0.1
-    out = torch.empty((B, HW, C), dtype=bf16, device=DEV)
+    out = _empty((B, HW, C), dtype=bf16, device=DEV)
     stats = ops.gn_scratch(B, 32, DEV)
     ops.groupnorm(x1, g, b, out, stats, x2=x2, groups=32, eps=eps, silu=silu)
     xin = x1 if x2 is None else torch.cat([x1, x2], dim=-1)
@@ -100,7 +113,7 @@ def check_gemv():
     w = _randn((N, K), 10, 0.05, bf16)
     x = _randn((K,), 11)
     b1, b2 = _randn((N,), 12), _randn((N,), 13)
-    out = torch.empty(N, device=DEV)
+    out = _empty(N, device=DEV)
     ops.gemv(w, x, out, b1, b2, silu=True)
     ref = F.silu(w.float() @ x + b1 + b2)
     return _stats(out, ref, "gemv", 1e-3, 1e-3)
@@ -114,7 +127,7 @@ def check_timestep_sinusoid():
     res = None
     for i in range(3):
         ti = torch.tensor([i], dtype=torch.int32, device=DEV)
-        out = torch.empty(2 * half, device=DEV)
+        out = _empty(2 * half, device=DEV)
         ops.timestep_sinusoid(ts, ti, freqs.to(DEV), out)
         emb = ts[i].float().cpu() * freqs
         ref = torch.cat([torch.cos(emb), torch.sin(emb)])
@@ -126,13 +139,13 @@ def check_conv_small_cin():
     B, h, w, cout = 2, 12, 39, 320
     xt, rgb = _randn((B, 4, h, w), 14), _randn((B, 4, h, w), 15)
     wt, bias = _randn((cout, 8, 3, 3), 16, 0.1), _randn((cout,), 17)
-    out = torch.empty((B, h, w, cout), dtype=bf16, device=DEV)
+    out = _empty((B, h, w, cout), dtype=bf16, device=DEV)
     ops.conv3x3_small_cin([xt, rgb], wt, bias, out, scale=1.0)
     ref = F.conv2d(torch.cat([xt, rgb], 1), wt, bias, padding=1).permute(0, 2, 3, 1)
     r = _stats(out, ref, "conv3x3_small_cin(8->320)", 2e-2, 1e-2)
     z = _randn((B, 4, h, w), 18)
     w2, b2 = _randn((256, 4, 3, 3), 19, 0.1), _randn((256,), 20)
-    out2 = torch.empty((B, h, w, 256), dtype=bf16, device=DEV)
+    out2 = _empty((B, h, w, 256), dtype=bf16, device=DEV)
     ops.conv3x3_small_cin([z], w2, b2, out2, scale=5.0)
     ref2 = F.conv2d(z * 5.0, w2, b2, padding=1).permute(0, 2, 3, 1)
     _stats(out2, ref2, "conv3x3_small_cin(4->256, scale)", 4e-2, 1e-2)
@@ -143,7 +156,7 @@ def check_conv_out():
     B, h, w, cin = 2, 12, 39, 320
     x = _randn((B, h, w, cin), 21, dtype=bf16)
     wt, bias = _randn((4, cin, 3, 3), 22, 0.05), _randn((4,), 23)
-    out = torch.empty((B, 4, h, w), device=DEV)
+    out = _empty((B, 4, h, w), device=DEV)
     ops.conv_out(x, wt, bias, out)
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt, bias, padding=1)
     return _stats(out, ref, "conv_out", 2e-3, 1e-3)
@@ -167,17 +180,17 @@ def check_gemm_conv_out_nchw():
 def check_upsample_im2col():
     B, h, w, C = 2, 6, 20, 64
     x = _randn((B, h, w, C), 24, dtype=bf16)
-    out = torch.empty((B, 12, 39, C), dtype=bf16, device=DEV)
+    out = _empty((B, 12, 39, C), dtype=bf16, device=DEV)
     ops.upsample_nearest(x, out)
     ref = F.interpolate(x.float().permute(0, 3, 1, 2), size=(12, 39), mode="nearest").permute(0, 2, 3, 1)
     assert torch.equal(out.float(), ref), "upsample_nearest (size) mismatch"
-    out2 = torch.empty((B, 12, 40, C), dtype=bf16, device=DEV)
+    out2 = _empty((B, 12, 40, C), dtype=bf16, device=DEV)
     ops.upsample_nearest(x, out2)
     ref2 = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1)
     assert torch.equal(out2.float(), ref2), "upsample_nearest (x2) mismatch"
     x3 = _randn((B, 12, 39, C), 25, dtype=bf16)
     oh, ow = 6, 20
-    col = torch.empty((B * oh * ow, 9 * C), dtype=bf16, device=DEV)
+    col = _empty((B * oh * ow, 9 * C), dtype=bf16, device=DEV)
     ops.im2col3x3_s2(x3, col)
     unf = F.unfold(x3.float().permute(0, 3, 1, 2), 3, padding=1, stride=2)  # [B, C*9, L] (c-major, tap-minor)
     unf = unf.view(B, C, 9, oh * ow).permute(0, 3, 2, 1).reshape(B * oh * ow, 9 * C)
@@ -200,7 +213,7 @@ def check_gemm_tiny():
     M, N, K = 128, 32, 64
     a = _randn((M, K), 30, 1.0, bf16)
     w = _randn((N, K), 31, 1.0, bf16)
-    out = torch.empty((M, N), dtype=torch.float32, device=DEV)
+    out = _empty((M, N), dtype=torch.float32, device=DEV)
     ops.gemm(a, w, out, flags=L.LDM_GEMM_OUT_F32, block_n=32)
     torch.cuda.synchronize()
     ref = _gemm_ref(a, w)
@@ -226,7 +239,7 @@ def check_gemm_plain(M=1000, N=320, K=320, block_n=0, bias=True, residual=True, 
     w = _randn((N, K), 33, 0.05, bf16)
     b = _randn((N,), 34) if bias else None
     r = _randn((M, N), 35, 1.0, bf16) if residual else None
-    out = torch.empty((M, N), dtype=torch.float32 if f32out else bf16, device=DEV)
+    out = _empty((M, N), dtype=torch.float32 if f32out else bf16, device=DEV)
     ops.gemm(a, w, out, bias=b, residual=r, flags=L.LDM_GEMM_OUT_F32 if f32out else 0, block_n=block_n)
     ref = _gemm_ref(a, w, b, r)
     return _stats(out, ref, f"gemm M={M} N={N} K={K} bn={block_n}", 3e-2 if not f32out else 2e-3, 1e-2)
@@ -240,7 +253,7 @@ def check_gemm_conv3x3(B=2, H=12, W=39, c1=128, c2=0, N=192, block_n=0):
     wp = wt.permute(0, 2, 3, 1).reshape(N, 9 * C).contiguous().to(bf16)
     bias = _randn((N,), 39)
     res = _randn((B * H * W, N), 40, 1.0, bf16)
-    out = torch.empty((B, H, W, N), dtype=bf16, device=DEV)
+    out = _empty((B, H, W, N), dtype=bf16, device=DEV)
     ops.gemm(x1, wp, out, a2=x2, taps=9, bias=bias, residual=res, block_n=block_n)
     xin = x1 if x2 is None else torch.cat([x1, x2], -1)
     ref = F.conv2d(xin.float().permute(0, 3, 1, 2), wp.float().view(N, 3, 3, C).permute(0, 3, 1, 2), bias, padding=1)
@@ -253,7 +266,7 @@ def check_gemm_concat_1x1():
     x1, x2 = _randn((B, H, W, c1), 41, 1.0, bf16), _randn((B, H, W, c2), 42, 1.0, bf16)
     w = _randn((N, c1 + c2), 43, 0.05, bf16)
     bias = _randn((N,), 44)
-    out = torch.empty((B, H, W, N), dtype=bf16, device=DEV)
+    out = _empty((B, H, W, N), dtype=bf16, device=DEV)
     ops.gemm(x1, w, out, a2=x2, taps=1, bias=bias)
     ref = torch.cat([x1, x2], -1).float() @ w.float().t() + bias
     return _stats(out, ref, "conv1x1 concat", 3e-2, 1e-2)
@@ -269,7 +282,7 @@ def check_gemm_geglu():
     idx = torch.arange(inner).view(-1, 16)
     perm = torch.cat([idx, idx + inner], dim=1).reshape(-1).to(DEV)
     wp, bp = w[perm].contiguous().to(bf16), b[perm].contiguous()
-    out = torch.empty((M, inner), dtype=bf16, device=DEV)
+    out = _empty((M, inner), dtype=bf16, device=DEV)
     ops.gemm(a, wp, out, bias=bp, flags=L.LDM_GEMM_GEGLU)
     h = a.float() @ w.to(bf16).float().t() + b
     val, gate = h.chunk(2, dim=-1)
@@ -309,7 +322,7 @@ def check_gemm_convt():
     g, be = _randn((cout,), 53) * 0.2 + 1, _randn((cout,), 54) * 0.1
     wp = wt.permute(2, 3, 1, 0).reshape(4 * cout, cin).contiguous().to(bf16)  # [(dy,dx,co), ci]
     bp = bias.repeat(4).contiguous()
-    out = torch.empty((B, 2 * H, 2 * W, cout), dtype=bf16, device=DEV)
+    out = _empty((B, 2 * H, 2 * W, cout), dtype=bf16, device=DEV)
     ops.gemm(x, wp, out, bias=bp, flags=L.LDM_GEMM_CONVT_LN_SILU, block_n=cout, ln=(g, be, 1e-6))
     wq = wp.float().view(2, 2, cout, cin).permute(3, 2, 0, 1)
     y = F.conv_transpose2d(x.float().permute(0, 3, 1, 2), wq, bias, stride=2)
@@ -329,7 +342,7 @@ def check_attention(B=1, heads=2, d=40, seq=300):
     q[:, :, :d] = qf
     k[:, :, :d] = kf
     vt[:, :d, :seq] = vf.transpose(1, 2)
-    out = torch.empty((B * seq, heads * d), dtype=bf16, device=DEV)
+    out = _empty((B * seq, heads * d), dtype=bf16, device=DEV)
     ops.flash_attn(q, k, vt, out, B=B, heads=heads, seq=seq, head_dim=d, dpad=dpad, seq_pad=seq_pad, scale=d ** -0.5)
     ref = F.scaled_dot_product_attention(qf.float(), kf.float(), vf.float())  # [BH, seq, d]
     ref = ref.view(B, heads, seq, d).permute(0, 2, 1, 3).reshape(B * seq, heads * d)
@@ -343,13 +356,13 @@ def check_logits_to_ids(up=2):
     lg[:, :, :, 5] += 3.0  # a dominant class so that the threshold keeps some pixels
     lg[0, 3, 4, 7] = lg[0, 3, 4, 9] = 50.0  # exact tie -> first index
     H, W = h * up, w * up
-    ids = torch.empty((B, H, W), dtype=torch.int32, device=DEV)
-    counts = torch.empty((B, 2, C), dtype=torch.int32, device=DEV)
+    ids = _empty((B, H, W), dtype=torch.int32, device=DEV)
+    counts = _empty((B, 2, C), dtype=torch.int32, device=DEV)
     ops.logits_to_ids(lg, ids, counts, up=up, mask_th=0.5, ignore_label=127)
     x = lg.permute(0, 3, 1, 2).cpu()
     if up != 1:
         x = F.interpolate(x, scale_factor=up, mode="bilinear", align_corners=False)
-    full = torch.empty((B, C, H, W), device=DEV)
+    full = _empty((B, C, H, W), device=DEV)
     ops.bilinear_up_nchw(lg, full, up)
     interp_exact = bool(torch.equal(full.cpu(), x))
     pred = torch.argmax(x, dim=1)
@@ -364,7 +377,7 @@ def check_logits_to_ids(up=2):
             "count_mismatch": int((c[:, 0] != cnt_ref).sum()), "over_mismatch": int((c[:, 1] != over_ref).sum())}
     assert mism == 0 and info["count_mismatch"] == 0 and info["over_mismatch"] == 0, str(info)
     # merge filter
-    cleaned = torch.empty_like(ids)
+    cleaned = _empty_like(ids)
     ops.segment_filter(ids, counts, cleaned, count_th=512, overlap_th=0.5, ignore_label=127)
     cl_ref = pred.clone().numpy()
     pn, sg = pred.numpy(), sig.numpy()
@@ -389,14 +402,14 @@ def check_bitmap():
     ids_np[0, :2] = 31
     ids_np[1, 5:7] = 255
     ids = torch.from_numpy(ids_np).to(DEV)
-    x = torch.empty((B, n, H, W), device=DEV)
+    x = _empty((B, n, H, W), device=DEV)
     ops.encode_bitmap(ids, x, ignore_label=255, fill=0.5)
     t = torch.from_numpy(ids_np[0]).long()
     ign = t == 255
     ref = torch.remainder(torch.bitwise_right_shift(t, torch.arange(n)[:, None, None]), 2).float()
     ref[:, ign] = 0.5
     assert torch.equal(x[0].cpu(), ref), "encode_bitmap mismatch"
-    dec = torch.empty((B, H, W), dtype=torch.int32, device=DEV)
+    dec = _empty((B, H, W), dtype=torch.int32, device=DEV)
     ops.decode_bitmap(x, dec, quirk31=True)
     exp = ids_np.copy()
     exp[exp == 31] = 0

@@ -30,6 +30,7 @@ class GemmDesc(C.Structure):
         ("block_n", c_i32), ("flags", c_i32),
         ("heads", c_i32), ("head_dim", c_i32), ("dpad", c_i32), ("seq", c_i32), ("seq_pad", c_i32),
         ("vt_rows", c_i32), ("n_store", c_i32),
+        ("identity", c_vp),
     ]
 
 

@@ -137,7 +137,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int j = 0; j < nblk; ++j) {
-        mbar_wait_sleep(&kv_empty[stage], phase ^ 1, 128);
+        mbar_wait(&kv_empty[stage], phase ^ 1);
         uint8_t* sk = sKV + stage * Cfg::kStageBytes;
         uint8_t* sv = sk + Cfg::kKBytes;
         if (elect_one()) {

@@ -28,8 +28,9 @@ constexpr int kMaxStages = 8;
 constexpr int kEpiWarps = 8;  // two warps per TMEM lane quadrant, each takes every other 32-column chunk
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kSmemBudget = 227 * 1024;
-constexpr int kEpiStageBytes = 2 * 16384;  // epilogue output staging for the TMA-store path
+constexpr int kEpiStageBytes = 2 * 16384 + 1024;  // epilogue output staging for the TMA-store path + per-half bias slice
 // Diagnostic switches (env LDM_GEMM_DEBUG, never set by the product): isolate the two halves of the main loop.
+constexpr int kPrefetchNext = 1 << 21; // internal: producer prefetches the next tile's A boxes / residual rows into L2
 constexpr int kStagedStore = 1 << 20; // internal: epilogue writes the output through shared memory + TMA store
 constexpr int kDbgNoTma = 1 << 29;  // producer signals the stages without loading them
 constexpr int kDbgNoMma = 1 << 30;
@@ -44,6 +45,7 @@ struct GemmParams {
   int m_tiles, n_tiles, block_n;
   int N, taps, kblocks1, kblocks, ktap;
   int stages, stage_bytes;
+  int res_kblocks;  // > 0: the residual is accumulated by res_kblocks extra K blocks (residual box x identity band)
   int flags;
   // epilogue
   const float* bias;
@@ -81,7 +83,8 @@ __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* dst, const float* v)
 template <bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
-               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
+               const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmE, const GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by SWIZZLE_128B tiles (the dynamic smem base is the same in both CTAs of a pair).
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -113,7 +116,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], (kPair ? 2 : 1) * 32 * kEpiWarps);
+      mbar_init(&tempty_bar[i], (kPair ? 2 : 1) * kEpiWarps);  // one arrival per epilogue warp
     }
     mbar_fence_init();
   }
@@ -154,12 +157,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         const int tx = rem - ty * p.tiles_x;
         const int x0 = tx * p.bw, y0 = ty * p.bh;
         const int n0 = n_tile * p.block_n + (int)rank * b_rows;
+        if ((p.flags & kPrefetchNext) && elect_one()) {
+          // Short main loops: the smem ring holds barely one tile, so the next tile's loads can only be issued once
+          // this tile's MMAs have drained it and would pay the full DRAM latency. Pull the next tile's A boxes and
+          // the residual rows (this tile's on the first pass, then always one tile ahead) into L2 now.
+          for (int pass = (tile == worker ? 0 : 1); pass < 2; ++pass) {
+            const int t2 = tile + pass * num_workers;
+            if (t2 >= num_tiles) break;
+            const int nt2 = t2 / m_units;
+            const int mu2 = t2 - nt2 * m_units;
+            const int mt2 = kPair ? 2 * mu2 + (int)rank : mu2;
+            const int b2 = mt2 / tiles_per_img;
+            const int rem2 = mt2 - b2 * tiles_per_img;
+            const int ty2 = rem2 / p.tiles_x;
+            const int tx2 = rem2 - ty2 * p.tiles_x;
+            if (pass == 1)
+              for (int kb = 0; kb < p.kblocks; ++kb)
+                tma_prefetch_l2_4d(kb < p.kblocks1 ? &tmA1 : &tmA2, (kb < p.kblocks1 ? kb : kb - p.kblocks1) * kBlockK,
+                                   tx2 * p.bw, ty2 * p.bh, b2);
+            if (p.residual)
+              for (int c = 0; c < p.block_n && nt2 * p.block_n + c < p.N; c += 64)
+                tma_prefetch_l2_4d(&tmR, nt2 * p.block_n + c, tx2 * p.bw, ty2 * p.bh, b2);
+          }
+        }
         for (int tap = 0; tap < p.taps; ++tap) {
           const int dy = (p.taps == 9) ? tap / 3 - 1 : 0;
           const int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
           for (int kb = 0; kb < p.kblocks; ++kb) {
             if (p.flags & kDbgNoWait) continue;
-            mbar_wait_sleep(&empty_bar[stage], phase ^ 1, 32);
+            mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * p.stage_bytes;
             uint8_t* sb = sa + kABytes;
             const CUtensorMap* tmA = (kb < p.kblocks1) ? &tmA1 : &tmA2;
@@ -183,6 +209,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             }
           }
         }
+        // residual as extra K blocks: A = residual[rows of this tile, 64 output columns], B = the matching band of the
+        // identity matrix (row n of the tile x column n), so that D += R on the tensor core
+        for (int j = 0; j < p.res_kblocks; ++j) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * p.stage_bytes;
+          uint8_t* sb = sa + kABytes;
+          if (elect_one()) {
+            if (kPair) {
+              if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (a_bytes + b_bytes));
+              tma_load_4d_pair(sa, &tmR, &full_bar[stage], n_tile * p.block_n + j * kBlockK, x0, y0, b);
+              tma_load_2d_pair(sb, &tmE, &full_bar[stage], j * kBlockK, (int)rank * b_rows);
+            } else {
+              mbar_arrive_expect_tx(&full_bar[stage], a_bytes + b_bytes);
+              tma_load_4d(sa, &tmR, &full_bar[stage], n_tile * p.block_n + j * kBlockK, x0, y0, b);
+              tma_load_2d(sb, &tmE, &full_bar[stage], j * kBlockK, 0);
+            }
+          }
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
       }
     }
     __syncwarp();
@@ -194,7 +242,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      const int ksteps = p.taps * p.kblocks;
+      const int ksteps = p.taps * p.kblocks + p.res_kblocks;
       for (int tile = worker; tile < num_tiles; tile += num_workers) {
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
@@ -246,8 +294,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     const bool plain = !(p.flags & (LDM_GEMM_CONVT_LN_SILU | LDM_GEMM_GEGLU | LDM_GEMM_QKV_SPLIT));
     const bool geglu = (p.flags & LDM_GEMM_GEGLU) != 0;
     const bool staged = (p.flags & kStagedStore) != 0;  // bf16 [rows, N] (or GEGLU [rows, N/2]) through smem + TMA store
-    const bool epi_leader = (warp == 2 + 4 * half) && lane == 0;  // issues this half's TMA stores
-    uint8_t* sbuf = epi_smem + half * 16384;
+    const bool epi_leader = threadIdx.x == 64;  // issues the TMA stores of the staged path
+    int sb = 0;                                  // staging buffer of the next output block (alternates)
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = worker; tile < num_tiles; tile += num_workers) {
@@ -265,17 +313,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       const int n0 = n_tile * p.block_n;
 
       // residual rows of this tile: issue every load now, so that they are in flight while the MMAs finish
-      // staged path: a half owns 64-column output blocks (ob = half, half + 2), i.e. chunk ci covers columns
-      // (2*(ci>>1) + half)*64 + (ci&1)*32; direct path: a half owns every other 32-column chunk.
+      // staged path: both halves work on the same 64-column output block, half h on its 32-column chunk h, so chunk
+      // ci of a thread covers columns min(ci*64, block_n-64) + h*32; direct path: a half owns every other chunk.
       uint4 rs[4][4];
-      const bool use_res = plain && p.residual != nullptr && valid;
+      const bool use_res = plain && p.residual != nullptr && valid && p.res_kblocks == 0;
       if (use_res) {
         const __nv_bfloat16* rrow = p.residual + grow * p.N + n0;
 #pragma unroll
         for (int ci = 0; ci < 4; ++ci) {
           // (the last 64-column block of a block_n that is not a multiple of 64 is shifted left to end at block_n)
-          const int cb = (2 * (ci >> 1) + half) * 64;
-          const int c = staged ? (cb < p.block_n ? min(cb, p.block_n - 64) + (ci & 1) * 32 : p.block_n)
+          const int c = staged ? (ci * 64 < p.block_n ? min(ci * 64, p.block_n - 64) + half * 32 : p.block_n)
                                : (2 * ci + half) * 32;
 #pragma unroll
           for (int g = 0; g < 4; ++g)
@@ -283,7 +330,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         }
       }
 
-      mbar_wait_sleep(&tfull_bar[as], aphase, 64);
+      mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)as * 256u;
 
@@ -336,48 +383,56 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         }
       } else if (staged) {
         // 64 output columns (= one 128-byte swizzle atom per row) at a time: registers -> swizzled smem -> TMA store.
-        // The TMA store clips pixels / columns outside the tensor, so ragged tiles need no predication here.
+        // All eight warps work on the same block (half h converts accumulator chunk(s) h), the two staging buffers
+        // alternate, and one thread issues the store. The TMA store clips pixels / columns outside the tensor, so
+        // ragged tiles need no predication here.
         const int acc_w = geglu ? 128 : 64;  // accumulator columns behind 64 output columns
 #pragma unroll
-        for (int oi = 0; oi < 2; ++oi) {
+        for (int ob = 0; ob < 4; ++ob) {
+          if (ob * acc_w >= p.block_n) break;
           // a ragged last block is shifted left so that it ends at block_n: the overlap is rewritten with the same values
-          if ((2 * oi + half) * acc_w >= p.block_n) break;
-          const int c0 = min((2 * oi + half) * acc_w, p.block_n - acc_w);
-          if (epi_leader) bulk_wait_read0();     // the previous store out of this buffer has been read
-          named_bar_sync(1 + half, 128);
+          const int c0 = min(ob * acc_w, p.block_n - acc_w);
+          uint8_t* sbuf = epi_smem + sb * 16384;
+          float* sbias = reinterpret_cast<float*>(epi_smem + 2 * 16384) + sb * 128;
+          if (epi_leader) bulk_wait_read1();  // the store that last used this buffer (two blocks ago) has been read
+          {
+            // this block's bias values (bias + per-image bias) once, through shared memory
+            const int t = threadIdx.x - 64;
+            if (t < acc_w) {
+              const int n = n0 + c0 + t;
+              float bv = 0.f;
+              if (n < p.N) {
+                if (p.bias) bv = __ldg(p.bias + n);
+                if (p.rowbias) bv += __ldg(p.rowbias + (long long)b * p.N + n);
+              }
+              sbias[t] = bv;
+            }
+          }
+          named_bar_sync(1, 32 * kEpiWarps);
+          uint8_t* rowp = sbuf + r * 128;
 #pragma unroll
-          for (int cq = 0; cq < 4; ++cq) {
-            const int cc = cq * 32;
-            if (cc >= acc_w) break;
+          for (int cq = 0; cq < 2; ++cq) {
+            if (!geglu && cq == 1) break;            // plain: one 32-column chunk per thread and block
+            const int cc = geglu ? half * 64 + cq * 32 : half * 32;
             const int c = c0 + cc;
             uint32_t v[32];
             tmem_ld32(t_addr + c, v);
             tmem_ld_wait();
             const int nc = n0 + c;
             float f[32];
+            {
+              const float4* bp = reinterpret_cast<const float4*>(sbias + cc);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-            if (p.bias) {
-              const float4* bp = reinterpret_cast<const float4*>(p.bias + nc);
-#pragma unroll
-              for (int g = 0; g < 8; ++g)
-                if (nc + g * 4 < p.N) {
-                  const float4 bv = __ldg(bp + g);
-                  f[g * 4] += bv.x; f[g * 4 + 1] += bv.y; f[g * 4 + 2] += bv.z; f[g * 4 + 3] += bv.w;
-                }
+              for (int g = 0; g < 8; ++g) {
+                const float4 bv = bp[g];
+                f[g * 4] = __uint_as_float(v[g * 4]) + bv.x;
+                f[g * 4 + 1] = __uint_as_float(v[g * 4 + 1]) + bv.y;
+                f[g * 4 + 2] = __uint_as_float(v[g * 4 + 2]) + bv.z;
+                f[g * 4 + 3] = __uint_as_float(v[g * 4 + 3]) + bv.w;
+              }
             }
-            if (p.rowbias) {
-              const float4* bp = reinterpret_cast<const float4*>(p.rowbias + (long long)b * p.N + nc);
-#pragma unroll
-              for (int g = 0; g < 8; ++g)
-                if (nc + g * 4 < p.N) {
-                  const float4 bv = __ldg(bp + g);
-                  f[g * 4] += bv.x; f[g * 4 + 1] += bv.y; f[g * 4 + 2] += bv.z; f[g * 4 + 3] += bv.w;
-                }
-            }
-            uint8_t* rowp = sbuf + r * 128;
             if (geglu) {
-              // columns [0,16) value, [16,32) gate of the same 16 outputs -> output chunk pair cq*2, cq*2+1
+              // columns [0,16) value, [16,32) gate of the same 16 outputs -> output 16-byte chunks (cc/32)*2, +1
               float o[16];
 #pragma unroll
               for (int j = 0; j < 16; ++j) o[j] = f[j] * gelu_erf_fast(f[16 + j]);
@@ -386,14 +441,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                 uint4 u;
                 u.x = pack_bf16(o[g * 8 + 0], o[g * 8 + 1]); u.y = pack_bf16(o[g * 8 + 2], o[g * 8 + 3]);
                 u.z = pack_bf16(o[g * 8 + 4], o[g * 8 + 5]); u.w = pack_bf16(o[g * 8 + 6], o[g * 8 + 7]);
-                *reinterpret_cast<uint4*>(rowp + (((cq * 2 + g) ^ (r & 7)) << 4)) = u;
+                *reinterpret_cast<uint4*>(rowp + ((((cc >> 5) * 2 + g) ^ (r & 7)) << 4)) = u;
               }
             } else {
               if (use_res) {
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                   if (nc + g * 8 >= p.N) break;
-                  const uint4 u = rs[oi * 2 + cq][g];
+                  const uint4 u = rs[ob][g];
                   const float2 a0 = unpack_bf16(u.x), a1 = unpack_bf16(u.y), a2 = unpack_bf16(u.z), a3 = unpack_bf16(u.w);
                   f[g * 8 + 0] += a0.x; f[g * 8 + 1] += a0.y; f[g * 8 + 2] += a1.x; f[g * 8 + 3] += a1.y;
                   f[g * 8 + 4] += a2.x; f[g * 8 + 5] += a2.y; f[g * 8 + 6] += a3.x; f[g * 8 + 7] += a3.y;
@@ -408,17 +463,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                 uint4 u;
                 u.x = pack_bf16(f[g * 8 + 0], f[g * 8 + 1]); u.y = pack_bf16(f[g * 8 + 2], f[g * 8 + 3]);
                 u.z = pack_bf16(f[g * 8 + 4], f[g * 8 + 5]); u.w = pack_bf16(f[g * 8 + 6], f[g * 8 + 7]);
-                *reinterpret_cast<uint4*>(rowp + (((cq * 4 + g) ^ (r & 7)) << 4)) = u;
+                *reinterpret_cast<uint4*>(rowp + (((half * 4 + g) ^ (r & 7)) << 4)) = u;
               }
             }
           }
           fence_proxy_async_smem();
-          named_bar_sync(1 + half, 128);
+          named_bar_sync(1, 32 * kEpiWarps);
           if (epi_leader) {
             const int ncol = geglu ? (n0 + c0) / 2 : n0 + c0;
             tma_store_4d(&tmO, sbuf, ncol, tx * p.bw, ty * p.bh, b);
             bulk_commit();
           }
+          sb ^= 1;
         }
       } else {
 #pragma unroll
@@ -486,7 +542,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             }
             continue;
           }
-          if (p.residual) {
+          if (use_res) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               if (nc + g * 8 >= p.N) break;
@@ -526,8 +582,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           }
         }
       }
+      // the accumulator buffer is free again: every lane's TMEM loads are complete (tcgen05.wait::ld), one lane per
+      // warp tells the MMA warp (of the leader CTA)
       tc_fence_before();
-      if (kPair) mbar_arrive_cluster(&tempty_bar[as], 0); else mbar_arrive(&tempty_bar[as]);
+      __syncwarp();
+      if (lane == 0) {
+        if (kPair) mbar_arrive_cluster(&tempty_bar[as], 0); else mbar_arrive(&tempty_bar[as]);
+      }
       if (++as == 2) {
         as = 0;
         aphase ^= 1;
@@ -535,7 +596,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     }
   }
 
-  if (warp >= 2 && lane == 0 && ((warp - 2) & 3) == 0) bulk_wait_all();  // outstanding TMA stores of this half
+  if (threadIdx.x == 64) bulk_wait_all();  // outstanding TMA stores
   tc_fence_before();
   if (kPair) cluster_sync_all(); else __syncthreads();  // pair: neither CTA may exit while its peer can still signal it
   if (warp == 1) {
@@ -618,6 +679,26 @@ int debug_flags() {
   return v;
 }
 
+// LDM_GEMM_PREFETCH=0 disables the one-tile-ahead L2 prefetch (A/B timing)
+bool prefetch_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LDM_GEMM_PREFETCH");
+    v = e ? atoi(e) : 0;
+  }
+  return v != 0;
+}
+
+// Residual on the tensor core for main loops of up to this many K blocks (LDM_GEMM_RESMMA overrides, 0 = never)
+int resmma_max_kblocks() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LDM_GEMM_RESMMA");
+    v = e ? atoi(e) : 1 << 30;
+  }
+  return v;
+}
+
 // LDM_GEMM_STAGED=0 keeps the direct (row-per-thread) global stores (A/B timing)
 bool staged_enabled() {
   static int v = -1;
@@ -678,8 +759,8 @@ extern "C" int ldm_gemm_bf16(const ldm_gemm_desc* d, ldm_stream_t stream) {
   // an explicit block_n keeps the single-CTA kernel (unless the A/B override forces pairs on a pairable block_n)
   const bool pair_ok = p.m_tiles >= 2 && !(flags & LDM_GEMM_CONVT_LN_SILU) &&
                        (d->block_n <= 0 || (pair_override() == 1 && d->block_n >= 64 && d->block_n % 32 == 0));
-  bool pair = pair_ok && cost2 < cost1;
-  if (pair_override() >= 0) pair = pair_ok && pair_override() != 0;
+  bool pair = pair_ok && cost2 < cost1 && kblocks_total >= 32;  // the pair's hand-offs only pay on long main loops
+  if (pair_override() >= 0) pair = pair_ok && pair_override() != 0;  // LDM_GEMM_PAIR=-1: model decides
   int block_n = d->block_n > 0 ? d->block_n : (pair ? bn2 : bn1);
   if ((flags & LDM_GEMM_GEGLU) && d->block_n <= 0 && block_n < 128) block_n = 128;  // staged GEGLU blocks span 128 columns
   LDM_REQUIRE(block_n % 32 == 0 && block_n >= 32 && block_n <= 256, LDM_ERR_BAD_ARG, "ldm_gemm_bf16: block_n=%d",
@@ -712,7 +793,9 @@ extern "C" int ldm_gemm_bf16(const ldm_gemm_desc* d, ldm_stream_t stream) {
   const int n_out = (flags & LDM_GEMM_GEGLU) ? d->N / 2 : d->N;
   const bool staged = !(flags & (LDM_GEMM_OUT_F32 | LDM_GEMM_OUT_NCHW_F32 | LDM_GEMM_QKV_SPLIT | LDM_GEMM_CONVT_LN_SILU)) &&
                       n_out >= 64 && n_out % 8 == 0 && block_n >= ((flags & LDM_GEMM_GEGLU) ? 128 : 64) && staged_enabled();
-  p.flags = flags | debug_flags() | (staged ? kStagedStore : 0);
+  // pointwise GEMMs with a short K loop are latency-bound on the next tile's first loads: prefetch one tile ahead
+  const bool prefetch_next = d->taps == 1 && kblocks_total <= 32 && prefetch_enabled();  // measured: no gain, off by default
+  p.flags = flags | debug_flags() | (staged ? kStagedStore : 0) | (prefetch_next ? kPrefetchNext : 0);
   p.bias = d->bias;
   p.rowbias = d->rowbias;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(d->residual);
@@ -767,6 +850,27 @@ extern "C" int ldm_gemm_bf16(const ldm_gemm_desc* d, ldm_stream_t stream) {
     if (rc) return rc;
   }
 
+  // short-K pointwise GEMMs: the residual goes through the tensor core (see ldm_gemm_desc.identity)
+  const bool plain_mode = !(flags & (LDM_GEMM_CONVT_LN_SILU | LDM_GEMM_GEGLU | LDM_GEMM_QKV_SPLIT));
+  const bool res_mma = d->residual && d->identity && plain_mode && kblocks_total <= resmma_max_kblocks() && d->N % 8 == 0;
+  p.res_kblocks = res_mma ? (block_n + kBlockK - 1) / kBlockK : 0;
+  CUtensorMap tmE = tmB;
+  if (res_mma) {
+    const uint64_t dims[2] = {256, 256};
+    const uint64_t str[1] = {512};
+    const uint32_t box[2] = {kBlockK, (uint32_t)(pair ? block_n / 2 : block_n)};
+    int rc = make_tmap(&tmE, d->identity, 2, dims, str, box, 2, true);
+    if (rc) return rc;
+  }
+  CUtensorMap tmR = tmB;
+  if ((prefetch_next || res_mma) && d->residual) {
+    const uint64_t dims[4] = {(uint64_t)d->N, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.B};
+    const uint64_t str[3] = {(uint64_t)d->N * 2, (uint64_t)d->N * 2 * p.W, (uint64_t)d->N * 2 * p.W * p.H};
+    const uint32_t box[4] = {64, (uint32_t)p.bw, (uint32_t)p.bh, 1};
+    int rc = make_tmap(&tmR, d->residual, 4, dims, str, box, 2, true);
+    if (rc) return rc;
+  }
+
   const int smem_bytes = p.stages * p.stage_bytes + kEpiStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static bool attr_set = false;
   if (!attr_set) {
@@ -792,7 +896,7 @@ extern "C" int ldm_gemm_bf16(const ldm_gemm_desc* d, ldm_stream_t stream) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true>, tmA1, tmA2, tmB, tmO, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true>, tmA1, tmA2, tmB, tmO, tmR, tmE, p);
     if (e != cudaSuccess) return set_error(LDM_ERR_CUDA, "gemm_tc_kernel<pair> launch: %s", cudaGetErrorString(e));
     count_launch();
     return check_launch("gemm_tc_kernel<pair>");
@@ -800,7 +904,7 @@ extern "C" int ldm_gemm_bf16(const ldm_gemm_desc* d, ldm_stream_t stream) {
   const int num_tiles = p.m_tiles * p.n_tiles;
   int grid = num_sms();
   if (grid > num_tiles) grid = num_tiles;
-  gemm_tc_kernel<false><<<grid, kThreads, smem_bytes, as_stream(stream)>>>(tmA1, tmA2, tmB, tmO, p);
+  gemm_tc_kernel<false><<<grid, kThreads, smem_bytes, as_stream(stream)>>>(tmA1, tmA2, tmB, tmO, tmR, tmE, p);
   count_launch();
   return check_launch("gemm_tc_kernel");
 }

@@ -31,6 +31,17 @@ def _chk(t, dtype, name):
         raise L.LdmError(f"{name}: expected a contiguous tensor")
 
 
+_EYE = {}
+
+
+def _identity(device):
+    """bf16 [256,256] identity shared by every GEMM on `device` (ldm_gemm_desc.identity)."""
+    key = torch.device(device).index
+    if key not in _EYE:
+        _EYE[key] = torch.eye(256, dtype=bf16, device=device)
+    return _EYE[key]
+
+
 def gemm(a1, w, out=None, *, a2=None, taps=1, bias=None, rowbias=None, residual=None, flags=0, block_n=0,
          qkv=None, ln=None, n_store=0):
     """out = epilogue(conv/gemm(a1 ++ a2, w)). a1/a2: [B,H,W,C] or [rows,C] bf16; w: [N, taps*(c1+c2)] bf16.
@@ -47,6 +58,8 @@ def gemm(a1, w, out=None, *, a2=None, taps=1, bias=None, rowbias=None, residual=
     d = L.GemmDesc()
     d.a1, d.a2, d.w = _p(a1), _p(a2), _p(w)
     d.bias, d.rowbias, d.residual = _p(bias), _p(rowbias), _p(residual)
+    if residual is not None:
+        d.identity = _p(_identity(a1.device))
     d.B, d.H, d.W, d.c1 = B, H, W, c1
     d.c2 = 0 if a2 is None else a2.shape[-1]
     d.N = w.shape[0]
