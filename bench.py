@@ -29,6 +29,16 @@ FLOP_AE_PER_FRAME = 90.4e9
 METRIC = "panoptic frames/sec (DDIM-50, 384x1248 KITTI)"
 
 
+def config_dict(frames_per_gpu, ddim_steps, world):
+    """`config` of the JSON line -- shared by both arms (the reference arm times a bounded sample of this workload)."""
+    return {"workload": f"LDMSeg sampler, batch {frames_per_gpu} frames 384x1248 per GPU, DDIM {ddim_steps} steps, "
+                        "random-init UNet (815M, SD-1.4 topology, self-attn only) + seg-AE, bf16 storage / fp32 "
+                        "accumulate, incl. AE decode, ids, merge, PQ stats",
+            "frames_per_gpu": frames_per_gpu, "ddim_steps": ddim_steps,
+            "parallelism": f"frames sharded over {world} GPU(s)",
+            "l2": "per-step working set (weights 1.6 GB + activations) exceeds the 126 MB L2"}
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -125,7 +135,8 @@ class CpuReference:
     def describe(self, t_unet, t_tail, n):
         return (f"1 frame 384x1248 on {self.threads} host threads: {n} of {self.T} DDIM iterations timed (UNet fp32 + "
                 f"scheduler, {t_unet:.2f} s each) + seg-AE decode + ids/merge + PQ ({t_tail:.2f} s), "
-                f"extrapolated to {self.T} iterations per frame")
+                f"extrapolated to {self.T} iterations per frame; fp32 CPU port of the reference path (the reference's "
+                f"diffusers UNet is not installable here, the oracle restatement stands in)")
 
 
 def cpu_reference_sample(ddim_steps, unet_iters=1):
@@ -154,9 +165,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": len(times), "warmup": args.warmup, "ms_per_step": 1e3 * t_unet, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"LDMSeg sampler, 384x1248 frames, DDIM {args.ddim_steps}, random-init UNet + seg-AE, "
-                                   "CPU reference path (oracle port: diffusers is not installable here); one step = "
-                                   "one DDIM iteration of one frame"},
+            "config": config_dict(args.frames_per_gpu, args.ddim_steps, args.gpus),
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": ref.threads, "kind": "port",
                              "sample": ref.describe(t_unet, t_tail, len(times))},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -276,11 +285,7 @@ def run_ours(args):
     line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"LDMSeg sampler, batch {B} frames 384x1248 per GPU, DDIM {T} steps, random-init UNet "
-                                   "(815M, SD-1.4 topology, self-attn only) + seg-AE, bf16 storage / fp32 accumulate, "
-                                   "incl. AE decode, ids, merge, PQ stats",
-                       "frames_per_gpu": B, "ddim_steps": T, "parallelism": f"frames sharded over {world} GPU(s)",
-                       "l2": "per-step working set (weights 1.6 GB + activations) exceeds the 126 MB L2"},
+            "config": config_dict(B, T, world),
             "e2e": {"value": fps_e2e, "unit": "frames/s",
                     "h2d_bytes_per_step": int(rgb_host.numel() * 4 + noise_host.numel() * 4 + gt_host.numel() * 4),
                     "d2h_bytes_per_step": int(ids_host.numel() * 4)},

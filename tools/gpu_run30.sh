@@ -1,0 +1,4 @@
+#!/bin/bash
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 2 --warmup 3 > gpurun_out/bench_2gpu.log 2> gpurun_out/bench_2gpu.err; echo "2gpu rc=$?"; tail -c 1200 gpurun_out/bench_2gpu.log; tail -5 gpurun_out/bench_2gpu.err
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.log 2> gpurun_out/bench_ref.err; echo "ref rc=$?"; tail -c 1500 gpurun_out/bench_ref.log; tail -3 gpurun_out/bench_ref.err

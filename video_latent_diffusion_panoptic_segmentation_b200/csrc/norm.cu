@@ -60,16 +60,23 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, const __nv
     shq[j] = ss[j];
   }
   __syncthreads();
+  // fold in two steps, both in a fixed order: every channel over the ppb pixel lanes, then every group over its channels
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int nthr = blockDim.x * blockDim.y;
+  for (int c = tid; c < 2 * C; c += nthr) {  // c < C: sums, c >= C: sums of squares
+    const float* col = sh + (c < C ? c : ppb * C + (c - C));
+    float a = 0.f;
+    for (int y = 0; y < ppb; ++y) a += col[y * C];
+    sh[(c < C ? c : ppb * C + (c - C))] = a;  // row 0 of each half now holds the per-channel totals
+  }
+  __syncthreads();
   if (tid < groups) {
     float a = 0.f, q = 0.f;
-    for (int y = 0; y < ppb; ++y) {
-      const float* rs = sh + y * C + tid * cpg;
-      const float* rq = sh + ppb * C + y * C + tid * cpg;
-      for (int c = 0; c < cpg; ++c) {
-        a += rs[c];
-        q += rq[c];
-      }
+    const float* rs = sh + tid * cpg;
+    const float* rq = sh + ppb * C + tid * cpg;
+    for (int c = 0; c < cpg; ++c) {
+      a += rs[c];
+      q += rq[c];
     }
     float* dst = partial + (((long long)b * gridDim.x + blockIdx.x) * groups + tid) * 2;
     dst[0] = a;
@@ -91,12 +98,28 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, const __nv
   const int ppb = blockDim.y;
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
   const double n = (double)cpg * (double)HW;
-  for (int g = tid; g < groups; g += blockDim.x * blockDim.y) {
+  // fold the per-chunk partials in fp64: kFoldSlices threads per group take every kFoldSlices-th chunk, then one
+  // thread per group adds the slices in order (fixed order -> bit-reproducible)
+  constexpr int kFoldSlices = 8;
+  double* shd = reinterpret_cast<double*>(sh + 2 * groups);  // [kFoldSlices][groups][2]
+  const int nthr = blockDim.x * blockDim.y;
+  for (int t = tid; t < kFoldSlices * groups; t += nthr) {
+    const int g = t % groups, sl = t / groups;
     double a = 0.0, q = 0.0;
     const float* pp = partial + ((long long)b * chunks * groups + g) * 2;
-    for (int k = 0; k < chunks; ++k) {
+    for (int k = sl; k < chunks; k += kFoldSlices) {
       a += (double)pp[(long long)k * groups * 2];
       q += (double)pp[(long long)k * groups * 2 + 1];
+    }
+    shd[(sl * groups + g) * 2] = a;
+    shd[(sl * groups + g) * 2 + 1] = q;
+  }
+  __syncthreads();
+  for (int g = tid; g < groups; g += nthr) {
+    double a = 0.0, q = 0.0;
+    for (int sl = 0; sl < kFoldSlices; ++sl) {
+      a += shd[(sl * groups + g) * 2];
+      q += shd[(sl * groups + g) * 2 + 1];
     }
     const double m = a / n;
     double var = q / n - m * m;
@@ -338,7 +361,7 @@ extern "C" int ldm_groupnorm_silu(const ldm_groupnorm_desc* d, ldm_stream_t stre
   count_launch();
   int rc = check_launch("gn_stats_kernel");
   if (rc) return rc;
-  gn_apply_kernel<<<dim3(chunks, d->B), dim3(vpp, ppb), sizeof(float) * 2 * d->groups, s>>>(
+  gn_apply_kernel<<<dim3(chunks, d->B), dim3(vpp, ppb), sizeof(float) * 2 * d->groups + sizeof(double) * 2 * 8 * d->groups, s>>>(
       reinterpret_cast<const __nv_bfloat16*>(d->x1), reinterpret_cast<const __nv_bfloat16*>(d->x2), d->c1, c2, d->HW,
       d->groups, partial, chunks, d->gamma, d->beta, d->eps, d->silu, reinterpret_cast<__nv_bfloat16*>(d->out));
   count_launch();
