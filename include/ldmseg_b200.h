@@ -195,6 +195,11 @@ int ldm_logits_to_ids(const float* logits, int32_t* ids, int32_t* counts, int32_
 /* Materialising variant of the bilinear x`up` resize: NHWC f32 [B,h,w,C] -> NCHW f32 [B,C,up*h,up*w]. */
 int ldm_bilinear_up_nchw(const float* logits, float* out, int32_t B, int32_t h, int32_t w, int32_t C, int32_t up,
                          ldm_stream_t stream);
+/* General bilinear resize, F.interpolate(size=(oh,ow), mode="bilinear", align_corners=False), of the crop window
+ * [y0, y0+ch) x [x0, x0+cw) of NHWC f32 [B,h,w,C] (C % 4 == 0) into NHWC f32 [B,oh,ow,C]: the resize to the RGB size
+ * (trainers_ldm_cond.py:1264-1269), crop_padding (:1175-1181,1276) and the resize to meta.im_size (:1279-1284). */
+int ldm_resize_bilinear_nhwc(const float* in, float* out, int32_t B, int32_t h, int32_t w, int32_t C, int32_t y0,
+                             int32_t x0, int32_t ch, int32_t cw, int32_t oh, int32_t ow, ldm_stream_t stream);
 /* Panoptic merge (trainers_ldm_cond.py:1303-1325): for every class c, keep[c] = count[c] >= count_th and
  * c != ignore_label and not (count[c] / over[c] < overlap_th) (float64 ratio as numpy computes it); then
  * cleaned[i] = keep[ids[i]] ? ids[i] : -1.  counts is the [B,2,C] array written by ldm_logits_to_ids. */

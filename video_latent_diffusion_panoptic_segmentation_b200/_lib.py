@@ -71,6 +71,8 @@ SIGNATURES = {
     "ldm_im2col3x3_s2": (C.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "ldm_logits_to_ids": (C.c_int, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_i32, c_vp]),
     "ldm_bilinear_up_nchw": (C.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    "ldm_resize_bilinear_nhwc": (C.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32,
+                                           c_i32, c_vp]),
     "ldm_segment_filter": (C.c_int, [c_vp, c_vp, c_vp, c_i32, c_i64, c_i32, c_i32, c_f64, c_i32, c_vp]),
     "ldm_decode_bitmap": (C.c_int, [c_vp, c_vp, c_i32, c_i32, c_i64, c_i32, c_vp]),
     "ldm_encode_bitmap": (C.c_int, [c_vp, c_vp, c_i32, c_i32, c_i64, c_i32, c_f32, c_vp]),

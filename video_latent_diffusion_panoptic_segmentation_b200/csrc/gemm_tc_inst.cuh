@@ -1,0 +1,47 @@
+// One translation unit per epilogue mode instantiates the kernel (single CTA and CTA pair) and exports its launcher.
+#pragma once
+#include "gemm_tc_kernel.cuh"
+
+namespace ldm_gemm {
+
+template <int kEpi>
+cudaError_t launch_epi(bool pair, int grid, int smem_bytes, cudaStream_t stream, const CUtensorMap& tmA1,
+                       const CUtensorMap& tmA2, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmR,
+                       const CUtensorMap& tmE, const GemmParams& p) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<false, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gemm_tc_kernel<true, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  if (pair) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true, kEpi>, tmA1, tmA2, tmB, tmO, tmR, tmE, p);
+  }
+  gemm_tc_kernel<false, kEpi><<<grid, kThreads, smem_bytes, stream>>>(tmA1, tmA2, tmB, tmO, tmR, tmE, p);
+  return cudaGetLastError();
+}
+
+}  // namespace ldm_gemm
+
+#define LDM_GEMM_DEFINE_LAUNCHER(NAME, EPI)                                                                          \
+  namespace ldm_gemm {                                                                                               \
+  cudaError_t NAME(bool pair, int grid, int smem_bytes, cudaStream_t stream, const CUtensorMap& tmA1,                \
+                   const CUtensorMap& tmA2, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmR,  \
+                   const CUtensorMap& tmE, const GemmParams& p) {                                                    \
+    return launch_epi<EPI>(pair, grid, smem_bytes, stream, tmA1, tmA2, tmB, tmO, tmR, tmE, p);                       \
+  }                                                                                                                  \
+  }

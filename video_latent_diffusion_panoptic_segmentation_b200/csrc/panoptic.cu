@@ -168,6 +168,50 @@ __global__ void bilinear_up_nchw_kernel(const float* __restrict__ logits, float*
   }
 }
 
+// General bilinear resize (F.interpolate(size=..., mode="bilinear", align_corners=False): scale = in/out) of a crop
+// window of NHWC f32 logits, NHWC out. One thread per (output pixel, 4 channels). Used for the resizes that are the
+// identity on the benchmark shapes: to the RGB size, crop_padding + resize to meta.im_size
+// (trainers_ldm_cond.py:1264-1284).
+__device__ __forceinline__ Axis axis_scaled(int dst, int in_size, float scale) {
+  Axis a;
+  float src = __fsub_rn(__fmul_rn(scale, __fadd_rn((float)dst, 0.5f)), 0.5f);
+  if (src < 0.f) src = 0.f;
+  a.i0 = (int)src;
+  if (a.i0 > in_size - 1) a.i0 = in_size - 1;
+  a.i1 = a.i0 < in_size - 1 ? a.i0 + 1 : a.i0;
+  a.w1 = __fsub_rn(src, (float)a.i0);
+  a.w0 = __fsub_rn(1.f, a.w1);
+  return a;
+}
+
+__global__ void resize_bilinear_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int h, int w,
+                                            int C, int y0, int x0, int ch, int cw, int oh, int ow) {
+  const int vec = C / 4;
+  const float sy = (float)ch / (float)oh, sx = (float)cw / (float)ow;
+  const long long total = (long long)B * oh * ow * vec;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vec);
+    long long t = i / vec;
+    const int ox = (int)(t % ow);
+    t /= ow;
+    const int oy = (int)(t % oh);
+    const int b = (int)(t / oh);
+    const Axis ay = axis_scaled(oy, ch, sy), ax = axis_scaled(ox, cw, sx);
+    const float* img = in + ((long long)b * h * w) * C + 4 * v;
+    auto px = [&](int yy, int xx) {
+      return __ldg(reinterpret_cast<const float4*>(img + ((long long)(y0 + yy) * w + (x0 + xx)) * C));
+    };
+    const float4 a = px(ay.i0, ax.i0), bq = px(ay.i0, ax.i1), c = px(ay.i1, ax.i0), d = px(ay.i1, ax.i1);
+    float4 o;
+    o.x = lerp2(lerp2(a.x, ax.w0, bq.x, ax.w1), ay.w0, lerp2(c.x, ax.w0, d.x, ax.w1), ay.w1);
+    o.y = lerp2(lerp2(a.y, ax.w0, bq.y, ax.w1), ay.w0, lerp2(c.y, ax.w0, d.y, ax.w1), ay.w1);
+    o.z = lerp2(lerp2(a.z, ax.w0, bq.z, ax.w1), ay.w0, lerp2(c.z, ax.w0, d.z, ax.w1), ay.w1);
+    o.w = lerp2(lerp2(a.w, ax.w0, bq.w, ax.w1), ay.w0, lerp2(c.w, ax.w0, d.w, ax.w1), ay.w1);
+    *reinterpret_cast<float4*>(out + (((long long)b * oh + oy) * ow + ox) * C + 4 * v) = o;
+  }
+}
+
 // Merge filter (trainers_ldm_cond.py:1307-1325). counts = [B][2][C] (argmax area, sigmoid>=th area).
 __global__ void segment_filter_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ counts,
                                       int32_t* __restrict__ cleaned, long long hw, int C, int count_th,
@@ -407,6 +451,21 @@ extern "C" int ldm_bilinear_up_nchw(const float* logits, float* out, int32_t B, 
   bilinear_up_nchw_kernel<<<grid1d(total, 256), 256, 0, as_stream(stream)>>>(logits, out, B, h, w, C, up);
   count_launch();
   return check_launch("bilinear_up_nchw_kernel");
+}
+
+extern "C" int ldm_resize_bilinear_nhwc(const float* in, float* out, int32_t B, int32_t h, int32_t w, int32_t C,
+                                        int32_t y0, int32_t x0, int32_t ch, int32_t cw, int32_t oh, int32_t ow,
+                                        ldm_stream_t stream) {
+  using namespace ldm_host;
+  LDM_REQUIRE(in && out && B > 0 && h > 0 && w > 0 && C > 0 && C % 4 == 0 && oh > 0 && ow > 0, LDM_ERR_BAD_ARG,
+              "ldm_resize_bilinear_nhwc: bad arg");
+  LDM_REQUIRE(y0 >= 0 && x0 >= 0 && ch > 0 && cw > 0 && y0 + ch <= h && x0 + cw <= w, LDM_ERR_BAD_SHAPE,
+              "ldm_resize_bilinear_nhwc: crop window (%d,%d,%d,%d) outside %dx%d", y0, x0, ch, cw, h, w);
+  const long long total = (long long)B * oh * ow * (C / 4);
+  resize_bilinear_nhwc_kernel<<<grid1d(total, 256), 256, 0, as_stream(stream)>>>(in, out, B, h, w, C, y0, x0, ch, cw, oh,
+                                                                                ow);
+  count_launch();
+  return check_launch("resize_bilinear_nhwc_kernel");
 }
 
 extern "C" int ldm_segment_filter(const int32_t* ids, const int32_t* counts, int32_t* cleaned, int32_t B, int64_t hw,

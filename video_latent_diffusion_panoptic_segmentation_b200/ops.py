@@ -211,6 +211,16 @@ def bilinear_up_nchw(logits, out, up):
     return out
 
 
+def resize_bilinear_nhwc(logits, out, crop=None):
+    """logits f32 NHWC [B,h,w,C] -> out f32 NHWC [B,oh,ow,C]; crop = (y0, x0, ch, cw) source window (default: all)."""
+    _chk(logits, f32, "logits"); _chk(out, f32, "out")
+    B, h, w, Cc = logits.shape
+    y0, x0, ch, cw = crop if crop is not None else (0, 0, h, w)
+    L.check(L.lib().ldm_resize_bilinear_nhwc(_p(logits), _p(out), B, h, w, Cc, y0, x0, ch, cw, out.shape[1],
+                                             out.shape[2], _stream()), "ldm_resize_bilinear_nhwc")
+    return out
+
+
 def segment_filter(ids, counts, cleaned, *, count_th, overlap_th, ignore_label):
     _chk(ids, i32, "ids"); _chk(counts, i32, "counts"); _chk(cleaned, i32, "cleaned")
     B = ids.shape[0]
