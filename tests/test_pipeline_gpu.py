@@ -246,3 +246,40 @@ def test_compute_pq_end_to_end(models):
     for k in ("pq", "sq", "rq", "tp", "fp", "fn", "iou_sum"):
         assert res[k] == want[k], k
     assert res["tp"] + res["fn"] > 0
+
+
+def test_resized_cropped_tail_vs_reference_chain(models):
+    """H5: when the resizes are not the identity (RGB size != decoder size, padding mask, meta.im_size), the CUDA tail
+    (bilinear x2 -> bilinear to RGB size -> crop_padding -> bilinear to im_size -> argmax/threshold/merge) follows the
+    reference chain of F.interpolate calls (trainers_ldm_cond.py:1264-1325) run by torch on the SAME decoder logits.
+    Float resampling differs in the last bits between implementations, so ids may flip on a vanishing share of pixels."""
+    from oracle import ldmseg_oracle as LO
+    from video_latent_diffusion_panoptic_segmentation_b200.ldmseg.schedulers import DDIMNoiseScheduler
+    from video_latent_diffusion_panoptic_segmentation_b200.ldmseg.trainers import TrainerDiffusion
+    B, h, w = 2, 8, 16
+    p = {"eval_kwargs": {"mask_th": 0.3, "count_th": 64, "overlap_th": 0.2}, "ignore_label": 127}
+    tr = TrainerDiffusion(p=p, vae_semseg=models["vae"], unet_model=models["unet"],
+                          noise_scheduler=DDIMNoiseScheduler(**SCHED_KW), args={"gpu": 0})
+    lat = (0.2 * 3.0 * torch.randn((B, 4, h, w), generator=torch.Generator().manual_seed(5))).to(DEV)
+    rgb_size = (72, 136)                       # != decoder size 64 x 128
+    masks = torch.zeros((B,) + rgb_size, dtype=torch.bool)
+    masks[0, :60, :120] = True                 # padded bottom / right
+    masks[1, 4:70, 10:130] = True
+    im_sizes = [(90, 180), (66, 120)]
+    got = tr.panoptic_ids_resized(lat, rgb_size, masks.to(DEV), im_sizes)
+    # reference chain on the CUDA decoder's own logits
+    logits = models["vae"].decode_nhwc(lat, scale=1.0 / models["vae"].scaling_factor).permute(0, 3, 1, 2).cpu()
+    full = F.interpolate(logits, scale_factor=2, mode="bilinear", align_corners=False)
+    full = F.interpolate(full, size=rgb_size, mode="bilinear", align_corners=False)
+    for b in range(B):
+        co = masks[b].nonzero()
+        y0, y1, x0, x1 = co[:, 0].min(), co[:, 0].max(), co[:, 1].min(), co[:, 1].max()
+        crop = full[b][:, y0:y1 + 1, x0:x1 + 1]
+        img = F.interpolate(crop[None].float(), size=im_sizes[b], mode="bilinear", align_corners=False)[0]
+        pred, cl, _ = LO.logits_to_panoptic(img, 0.3, 64, 0.2, 127)
+        ids, cleaned, _ = got[b]
+        assert tuple(ids.shape[-2:]) == im_sizes[b]
+        mism = float((ids[0].cpu().numpy() != pred).mean())
+        assert mism < 2e-3, f"image {b}: {mism:.4%} of the ids differ from the reference chain"
+        mism_c = float((cleaned[0].cpu().numpy() != cl).mean())
+        assert mism_c < 1e-2, f"image {b}: {mism_c:.4%} of the merged ids differ"

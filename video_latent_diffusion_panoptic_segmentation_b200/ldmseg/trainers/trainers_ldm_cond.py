@@ -161,6 +161,49 @@ class TrainerDiffusion:
                            ignore_label=self.ignore_label)
         return ids, cleaned, counts
 
+    @torch.no_grad()
+    def panoptic_ids_resized(self, latents, rgb_size, padding_masks=None, im_sizes=None):
+        """General tail (:1255-1325) for the cases where the resizes are not the identity: decoder logits ->
+        bilinear x interpolation_factor (vae.py:271) -> bilinear to the RGB size (:1264-1269) -> per image
+        crop_padding (:1175-1181) -> bilinear to meta.im_size (:1279-1284) -> argmax / threshold / merge.
+        Returns a list of (ids, cleaned, counts) int32 device tensors, one entry per image ([1, h_i, w_i])."""
+        logits = self.vae_semseg.decode_nhwc(latents, scale=1.0 / self.vae_semseg.scaling_factor)
+        up = self.vae_semseg.interpolation_factor
+        B, H, W, C = logits.shape
+        dev = logits.device
+        full = torch.empty((B, H * up, W * up, C), dtype=f32, device=dev)
+        ops.resize_bilinear_nhwc(logits, full)
+        rh, rw = int(rgb_size[0]), int(rgb_size[1])
+        if (rh, rw) != (H * up, W * up):
+            full2 = torch.empty((B, rh, rw, C), dtype=f32, device=dev)
+            ops.resize_bilinear_nhwc(full, full2)
+            full = full2
+        out = []
+        for b in range(B):
+            if padding_masks is not None:
+                y0, y1, x0, x1 = self.crop_padding_box(padding_masks[b])
+            else:
+                y0, y1, x0, x1 = 0, rh - 1, 0, rw - 1
+            oh, ow = (int(im_sizes[b][0]), int(im_sizes[b][1])) if im_sizes is not None else (y1 - y0 + 1, x1 - x0 + 1)
+            img = torch.empty((1, oh, ow, C), dtype=f32, device=dev)
+            ops.resize_bilinear_nhwc(full[b:b + 1], img, crop=(y0, x0, y1 - y0 + 1, x1 - x0 + 1))
+            ids = torch.empty((1, oh, ow), dtype=i32, device=dev)
+            counts = torch.empty((1, 2, C), dtype=i32, device=dev)
+            ops.logits_to_ids(img, ids, counts, up=1, mask_th=self.mask_th, ignore_label=self.ignore_label)
+            cleaned = torch.empty_like(ids)
+            ops.segment_filter(ids, counts, cleaned, count_th=self.count_th, overlap_th=self.overlap_th,
+                               ignore_label=self.ignore_label)
+            out.append((ids, cleaned, counts))
+        return out
+
+    @staticmethod
+    def crop_padding_box(padding_mask):
+        """Bounding box (y0, y1, x0, x1, inclusive) of the non-zero padding mask, as crop_padding (:1175-1181)."""
+        rows = padding_mask.to(torch.bool).any(dim=1).nonzero()
+        cols = padding_mask.to(torch.bool).any(dim=0).nonzero()
+        box = torch.stack([rows.min(), rows.max(), cols.min(), cols.max()]).cpu().tolist()
+        return int(box[0]), int(box[1]), int(box[2]), int(box[3])
+
     def crop_padding(self, prediction, padding_mask):
         co = padding_mask.nonzero()
         y0, y1 = co[:, 0].min(), co[:, 0].max()
@@ -172,7 +215,10 @@ class TrainerDiffusion:
     def compute_pq(self, num_inference_steps=50, guidance_scale=7.5, seed=None, threshold_output=True,
                    save_images=False, max_iter=None, dataloader=None, threshold_mode="max", save_model=False):
         """`dataloader` yields dicts with 'rgb_latents' [B,4,h,w] (the RGB-VAE encode is the step before this path,
-        SURVEY section 8(f) rank 1), 'semseg' [B,H,W] ground-truth labels, optional 'mask' [B,H,W] and 'meta'."""
+        SURVEY section 8(f) rank 1), 'semseg' ground-truth labels ([B,H,W], or a list of per-image [h_i,w_i] maps at
+        meta.im_size), optional 'mask' [B,Hrgb,Wrgb] padding masks (their size is the RGB input size) and 'meta'
+        (per image {'im_size': (h_i, w_i)}). When every resize / crop of :1264-1284 is the identity the fused tail runs;
+        otherwise the logits are resized, cropped and resized again as the reference does."""
         if threshold_mode != "max" or not threshold_output:
             raise NotImplementedError("only threshold_mode='max' with threshold_output=True is built")
         if is_main_process():
@@ -187,19 +233,33 @@ class TrainerDiffusion:
         all_cleaned = []
         for batch_idx, data in enumerate(dataloader):
             rgb_latents = data["rgb_latents"].to(self.device)
-            gt_semseg = data["semseg"].to(self.device)
+            gt_semseg = data["semseg"]  # [B,H,W] tensor, or a list of [h_i,w_i] tensors (original image sizes)
+            gt_semseg = ([g.to(self.device) for g in gt_semseg] if isinstance(gt_semseg, (list, tuple))
+                         else gt_semseg.to(self.device))
             B = rgb_latents.shape[0]
             latents = self.sample([""] * B, num_inference_steps, guidance_scale, seed, rgb_latents=rgb_latents,
                                   scheduler=scheduler, disable_progress_bar=True)
-            ids, cleaned, _ = self.panoptic_ids(latents)
-            H, W = cleaned.shape[-2:]
-            if tuple(gt_semseg.shape[-2:]) != (H, W):
-                raise NotImplementedError("non-identity resize to meta.im_size / padding crop (:1264-1284) is not built")
-            if "mask" in data and not bool(data["mask"].to(torch.bool).all()):
-                raise NotImplementedError("padding-mask crop (:1175-1181,1276) is not built (synthetic masks are all ones)")
-            for b in range(B):
-                evaluator.add_image(cleaned[b], gt_semseg[b])
-            all_cleaned.append(cleaned)
+            f = self.vae_semseg.downsample_factor
+            dec_size = (rgb_latents.shape[-2] * f, rgb_latents.shape[-1] * f)
+            masks = data["mask"].to(self.device) if "mask" in data else None
+            rgb_size = tuple(masks.shape[-2:]) if masks is not None else dec_size
+            im_sizes = [tuple(m["im_size"]) for m in data["meta"]] if "meta" in data else [rgb_size] * B
+            identity = (rgb_size == dec_size and all(tuple(sz) == rgb_size for sz in im_sizes)
+                        and (masks is None or bool(masks.to(torch.bool).all())))
+            if identity:  # every resize / crop of :1264-1284 is the identity: fused tail
+                ids, cleaned, _ = self.panoptic_ids(latents)
+                for b in range(B):
+                    evaluator.add_image(cleaned[b], gt_semseg[b])
+                all_cleaned.append(cleaned)
+            else:
+                per_image = self.panoptic_ids_resized(latents, rgb_size, masks, im_sizes)
+                for b, (_, cleaned, _) in enumerate(per_image):
+                    gt_b = gt_semseg[b]
+                    if tuple(gt_b.shape[-2:]) != tuple(cleaned.shape[-2:]):
+                        raise ValueError(f"ground truth {tuple(gt_b.shape[-2:])} does not match meta.im_size "
+                                         f"{tuple(cleaned.shape[-2:])} of image {b}")
+                    evaluator.add_image(cleaned[0], gt_b.contiguous())
+                    all_cleaned.append(cleaned)
             if max_iter is not None and batch_idx > max_iter:
                 break
         self.last_cleaned = all_cleaned
