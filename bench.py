@@ -307,9 +307,15 @@ def run_ours(args):
         tot_ms = sum(d["ms"] for d in by.values())
         gm = by.get("gemm", {"ms": 1e-9, "flops": 0, "n": 1})
         ach = gm["flops"] / (gm["ms"] / 1e3) / 1e12
+        traffic = None  # DRAM bytes per launch of the contraction kernel, from the committed ncu capture of one forward
+        tpath = os.path.join(ROOT, "profiles", "r01f_unet_forward_traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            if "gemm_tc_kernel" in tj:
+                traffic = tj["gemm_tc_kernel"]["dram_bytes_per_launch"]
         line["roofline"] = {"bound": "tensor", "kernel": "gemm_tc_kernel", "achieved": ach, "peak": tf_sus,
                             "unit": "TFLOP/s", "frac": ach / tf_sus, "peak_source": f"{which} (sustained bf16)",
-                            "traffic": None, "launches": gm["n"],
+                            "traffic": traffic, "launches": gm["n"],
                             "avg_launch_us": gm["ms"] * 1e3 / max(1, gm["n"]),
                             "share_of_unet_step": gm["ms"] / tot_ms,
                             "whole_job_frac": fps / world * (T * FLOP_PER_FRAME_STEP + FLOP_AE_PER_FRAME) / (tf_sus * 1e12)}
@@ -317,6 +323,16 @@ def run_ours(args):
         at = by.get("flash_attn")
         if at:
             line["attention_tflops"] = at["flops"] / (at["ms"] / 1e3) / 1e12
+        # the HBM-bound kernels of the UNet step (GroupNorm+SiLU, LayerNorm): algorithmic bytes / event time
+        hb = {"bytes": 0, "ms": 0.0}
+        for r in prof:
+            if r["op"] in ("groupnorm", "layernorm"):
+                hb["bytes"] += r["bytes"] * 2 // 3 if r["op"] == "groupnorm" else r["bytes"]  # 1R + 1W
+                hb["ms"] += r["ms"]
+        if hb["ms"] > 0:
+            gbs = hb["bytes"] / (hb["ms"] / 1e3) / 1e9
+            line["hbm_kernels"] = {"kernels": "gn_stats+gn_apply, layernorm", "achieved": gbs, "peak": hbm, "unit": "GB/s",
+                                   "frac": gbs / hbm, "note": "eager per-launch events; small launches are host-bound"}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 cb = cpu_reference_sample(T, unet_iters=1)

@@ -70,6 +70,33 @@ def cases():
                                   2 * 2 * B * h * w * 960)
     out["conv3x3_960to320_L0"] = (lambda: ops.gemm(t0, wc, oc, taps=9, bias=bc), 2 * B * h * w * 320 * 9 * 960,
                                   2 * (B * h * w * 1280 + 9 * 960 * 320))
+    # HBM-bound tail / scheduler kernels at full size (8 frames of 384x1248)
+    H, W, Cc = 192, 624, 128
+    lo = torch.randn((B, H, W, Cc), device=DEV)
+    ids = torch.empty((B, 2 * H, 2 * W), dtype=torch.int32, device=DEV)
+    counts = torch.empty((B, 2, Cc), dtype=torch.int32, device=DEV)
+    cleaned = torch.empty_like(ids)
+    out["logits_to_ids_up2"] = (lambda: ops.logits_to_ids(lo, ids, counts, up=2, mask_th=0.5, ignore_label=127), 0,
+                                lo.numel() * 4 + ids.numel() * 4)
+    out["segment_filter"] = (lambda: ops.segment_filter(ids, counts, cleaned, count_th=512, overlap_th=0.5, ignore_label=127),
+                             0, 2 * ids.numel() * 4)
+    bits = torch.randn((B, 16, 2 * H, 2 * W), device=DEV)
+    out["decode_bitmap16"] = (lambda: ops.decode_bitmap(bits, ids), 0, bits.numel() * 4 + ids.numel() * 4)
+    gt = torch.randint(0, 19, (B * 2 * H * 2 * W,), dtype=torch.int32, device=DEV)
+    pr = torch.randint(0, 40, (B * 2 * H * 2 * W,), dtype=torch.int32, device=DEV)
+    hk = torch.empty(1 << 14, dtype=torch.int64, device=DEV)
+    hc = torch.empty(1 << 14, dtype=torch.int32, device=DEV)
+    ho = torch.empty(1, dtype=torch.int32, device=DEV)
+    import ctypes as Cx
+    out["joint_hist"] = (lambda: L.check(L.lib().ldm_joint_hist(Cx.c_void_p(gt.data_ptr()), Cx.c_void_p(pr.data_ptr()), gt.numel(),
+                                                               Cx.c_void_p(hk.data_ptr()), Cx.c_void_p(hc.data_ptr()), 1 << 14,
+                                                               Cx.c_void_p(ho.data_ptr()),
+                                                               Cx.c_void_p(torch.cuda.current_stream().cuda_stream)), "joint_hist"),
+                         0, 2 * gt.numel() * 4)
+    eps, xs = torch.randn((B, 4, 48, 156), device=DEV), torch.randn((B, 4, 48, 156), device=DEV)
+    coef = torch.rand((50, 4), device=DEV) + 0.1
+    ti = torch.zeros(1, dtype=torch.int32, device=DEV)
+    out["ddim_step"] = (lambda: ops.ddim_step(eps, xs, coef, ti, prev_sample=xs), 0, 3 * eps.numel() * 4)
     return out
 
 

@@ -13,7 +13,8 @@ def main(path, out):
     rows = [r for r in csv.reader(open(path)) if len(r) >= 15 and r[0].isdigit()]
     per = defaultdict(dict)
     for r in rows:
-        per[int(r[0])]["name"] = re.sub(r"\(.*", "", r[4]).replace("void ", "").replace("<unnamed>::", "")
+        name = re.sub(r"\(.*", "", r[4]).replace("void ", "").replace("<unnamed>::", "")
+        per[int(r[0])]["name"] = re.sub(r"^(ldm_gemm::)?(\w+)<.*", r"\2", name)  # template arguments folded together
         val = float(r[14].replace(",", ""))
         unit = r[13]
         if unit in ("Mbyte", "MB"):

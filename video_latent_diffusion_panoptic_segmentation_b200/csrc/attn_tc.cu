@@ -443,8 +443,15 @@ extern "C" int ldm_flash_attn_fwd(const ldm_attn_desc* d, ldm_stream_t stream) {
       if (poly == 2) return launch_attn<40, 2, 128, 4, 2>(d, s);
       return launch_attn<40, 2, 128, 4, 1>(d, s);
     }
-    case 80:
-      return launch_attn<80, 1, 128, 3, 0>(d, s);
+    case 80: {
+      static int v = -1;  // LDM_ATTN_D80=0: one query group, 128-key blocks; 1 (default): two groups, 64-key blocks
+      if (v < 0) {
+        const char* e = getenv("LDM_ATTN_D80");
+        v = e ? atoi(e) : 1;
+      }
+      if (v == 0) return launch_attn<80, 1, 128, 3, 0>(d, s);
+      return launch_attn<80, 2, 64, 4, 0>(d, s);
+    }
     case 160:
       return launch_attn<160, 1, 64, 3, 0>(d, s);
     default:
