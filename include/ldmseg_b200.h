@@ -158,8 +158,8 @@ int ldm_gemv_bf16(const void* w, const float* bias, const float* bias2, const fl
 /* 3x3 conv (pad 1) with few input channels, fused with the latent concat + cast + scale:
  *   conv_in of the UNet: cat([x_t, rgb_latents(, condition)], 1) (trainers_ldm_cond.py:1131-1141) -> unet.py:357
  *   seg-AE decoder[0]  : z * (1/scaling_factor) (trainers_ldm_cond.py:423) -> vae.py:134
- * s0..s2: f32 NCHW [B,cps,h,w] sources (nsrc of them), scaled by `scale`; w f32 [cout, nsrc*cps, 3, 3]
- * (reference layout); out bf16 NHWC [B,h,w,cout]. */
+ * s0..s2: f32 NCHW [B,cps,h,w] sources (nsrc of them), scaled by `scale`; w f32 [nsrc*cps, 3, 3, cout] (the reference's
+ * [cout, cin, 3, 3] permuted so that the output channel is innermost: coalesced weight reads); out bf16 NHWC [B,h,w,cout]. */
 int ldm_conv3x3_small_cin(const float* s0, const float* s1, const float* s2, int32_t nsrc, int32_t cps, float scale,
                           const float* w, const float* bias, void* out, int32_t B, int32_t h, int32_t wd,
                           int32_t cout, ldm_stream_t stream);

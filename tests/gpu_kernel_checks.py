@@ -140,13 +140,13 @@ def check_conv_small_cin():
     xt, rgb = _randn((B, 4, h, w), 14), _randn((B, 4, h, w), 15)
     wt, bias = _randn((cout, 8, 3, 3), 16, 0.1), _randn((cout,), 17)
     out = _empty((B, h, w, cout), dtype=bf16, device=DEV)
-    ops.conv3x3_small_cin([xt, rgb], wt, bias, out, scale=1.0)
+    ops.conv3x3_small_cin([xt, rgb], ops.pack_small_cin_weight(wt), bias, out, scale=1.0)
     ref = F.conv2d(torch.cat([xt, rgb], 1), wt, bias, padding=1).permute(0, 2, 3, 1)
     r = _stats(out, ref, "conv3x3_small_cin(8->320)", 2e-2, 1e-2)
     z = _randn((B, 4, h, w), 18)
     w2, b2 = _randn((256, 4, 3, 3), 19, 0.1), _randn((256,), 20)
     out2 = _empty((B, h, w, 256), dtype=bf16, device=DEV)
-    ops.conv3x3_small_cin([z], w2, b2, out2, scale=5.0)
+    ops.conv3x3_small_cin([z], ops.pack_small_cin_weight(w2), b2, out2, scale=5.0)
     ref2 = F.conv2d(z * 5.0, w2, b2, padding=1).permute(0, 2, 3, 1)
     _stats(out2, ref2, "conv3x3_small_cin(4->256, scale)", 4e-2, 1e-2)
     return r

@@ -83,7 +83,7 @@ __global__ void gemv_bf16_kernel(const __nv_bfloat16* __restrict__ w, const floa
 
 // ---------------------------------------------------------------- few-input-channel conv3x3 (conv_in / AE conv_in)
 // Input: up to 3 NCHW fp32 sources of `cps` channels each (the latent concat, trainers_ldm_cond.py:1134-1141),
-// scaled by `scale`; weights fp32 [cout, cin, 3, 3]; output bf16 NHWC. One thread per output channel, a CTA per
+// scaled by `scale`; weights fp32 [cin, 3, 3, cout] (output channel innermost); output bf16 NHWC. One thread per output channel, a CTA per
 // strip of pixels in one image row; the input patch is staged in shared memory (broadcast reads).
 constexpr int kStrip = 32;
 __global__ void conv3x3_small_cin_kernel(const float* __restrict__ s0, const float* __restrict__ s1,
@@ -122,7 +122,7 @@ __global__ void conv3x3_small_cin_kernel(const float* __restrict__ s0, const flo
   for (int c = 0; c < cin; ++c) {
     float wk[9];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) wk[t] = __ldg(&w[((long long)co * cin + c) * 9 + t]);
+    for (int t = 0; t < 9; ++t) wk[t] = __ldg(&w[((long long)c * 9 + t) * cout + co]);  // [cin,3,3,cout]: coalesced over co
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
       const float* prow = patch + (c * 3 + r) * pw;

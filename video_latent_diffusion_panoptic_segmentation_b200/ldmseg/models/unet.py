@@ -199,7 +199,7 @@ class UNet:
         def norm(name):
             return dv(sd[name + ".weight"]), dv(sd[name + ".bias"])
 
-        P["conv_in"] = (dv(sd["conv_in.weight"]), dv(sd["conv_in.bias"]))
+        P["conv_in"] = (dv(ops.pack_small_cin_weight(sd["conv_in.weight"])), dv(sd["conv_in.bias"]))
         wo, bo = sd["conv_out.weight"], sd["conv_out.bias"]  # [4, C, 3, 3] -> tap-major rows, zero-padded to 8 outputs
         npad = (wo.shape[0] + 7) // 8 * 8
         wop = torch.zeros((npad, 9 * wo.shape[1]))

@@ -74,7 +74,7 @@ class GeneralVAESeg:
     def _pack(self):
         sd, dev = self._sd, self.device
         P = {}
-        P["in_w"], P["in_b"] = sd["decoder.0.weight"].to(dev), sd["decoder.0.bias"].to(dev)
+        P["in_w"], P["in_b"] = ops.pack_small_cin_weight(sd["decoder.0.weight"]).to(dev), sd["decoder.0.bias"].to(dev)
         idx = 2
         P["ups"] = []
         for _ in range(self.num_upscalers):

@@ -151,15 +151,21 @@ def gemv(w, x, out, bias=None, bias2=None, silu=False):
     return out
 
 
+def pack_small_cin_weight(w):
+    """Conv2d weight [cout, cin, 3, 3] (reference layout) -> f32 [cin, 3, 3, cout] for conv3x3_small_cin."""
+    return w.detach().to(f32).permute(1, 2, 3, 0).contiguous()
+
+
 def conv3x3_small_cin(srcs, w, bias, out, scale=1.0):
-    """srcs: list of 1..3 f32 NCHW [B,cps,h,w]; w f32 [cout, len(srcs)*cps, 3, 3]; out bf16 NHWC [B,h,w,cout]."""
+    """srcs: list of 1..3 f32 NCHW [B,cps,h,w]; w f32 [len(srcs)*cps, 3, 3, cout] (pack_small_cin_weight);
+    out bf16 NHWC [B,h,w,cout]."""
     for s in srcs:
         _chk(s, f32, "src")
     _chk(w, f32, "w"); _chk(bias, f32, "bias"); _chk(out, bf16, "out")
     B, cps, h, wd = srcs[0].shape
     s = list(srcs) + [None] * (3 - len(srcs))
     L.check(L.lib().ldm_conv3x3_small_cin(_p(s[0]), _p(s[1]), _p(s[2]), len(srcs), cps, scale, _p(w), _p(bias), _p(out),
-                                          B, h, wd, w.shape[0], _stream()), "ldm_conv3x3_small_cin")
+                                          B, h, wd, w.shape[-1], _stream()), "ldm_conv3x3_small_cin")
     return out
 
 
