@@ -119,6 +119,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();  // set-up done: the next kernel may start its own; q / k / v are needed from here on
+  pdl_wait();
 
   // Register rebalancing (NQ = 2 launches 384 threads at 168 registers): the control warpgroup gives registers back,
   // the softmax warpgroups (a 128-wide score row per thread) take them.
@@ -412,7 +414,8 @@ int launch_attn(const ldm_attn_desc* d, cudaStream_t s) {
     attr_set = true;
   }
   dim3 grid((d->seq + 128 * NQ - 1) / (128 * NQ), BH);
-  kern<<<grid, Cfg::kThreads, Cfg::kSmem, s>>>(tmQ, tmK, tmV, p);
+  cudaError_t le = launch_pdl(kern, grid, dim3(Cfg::kThreads), (size_t)Cfg::kSmem, s, 1, tmQ, tmK, tmV, p);
+  if (le != cudaSuccess) return set_error(LDM_ERR_CUDA, "flash_attn_kernel launch: %s", cudaGetErrorString(le));
   count_launch();
   return check_launch("flash_attn_kernel");
 }

@@ -72,6 +72,13 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, 
   }
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// The large kernels of the UNet plan can be launched with programmatic stream serialisation (host_util.h: launch_pdl,
+// opt-in through LDM_PDL=1): it lets the NEXT kernel's CTAs start (barrier init, TMEM allocation, tensor-map prefetch) while this one drains, and
+// waits for the PREVIOUS kernel's completion before it touches global memory.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- fences
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -16,23 +16,11 @@ cudaError_t launch_epi(bool pair, int grid, int smem_bytes, cudaStream_t stream,
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  if (pair) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = smem_bytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true, kEpi>, tmA1, tmA2, tmB, tmO, tmR, tmE, p);
-  }
-  gemm_tc_kernel<false, kEpi><<<grid, kThreads, smem_bytes, stream>>>(tmA1, tmA2, tmB, tmO, tmR, tmE, p);
-  return cudaGetLastError();
+  if (pair)
+    return ldm_host::launch_pdl(gemm_tc_kernel<true, kEpi>, dim3(grid), dim3(kThreads), (size_t)smem_bytes, stream, 2, tmA1,
+                                tmA2, tmB, tmO, tmR, tmE, p);
+  return ldm_host::launch_pdl(gemm_tc_kernel<false, kEpi>, dim3(grid), dim3(kThreads), (size_t)smem_bytes, stream, 1, tmA1,
+                              tmA2, tmB, tmO, tmR, tmE, p);
 }
 
 }  // namespace ldm_gemm

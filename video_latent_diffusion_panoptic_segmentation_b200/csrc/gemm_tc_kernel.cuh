@@ -122,6 +122,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   if (kPair) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // the set-up above overlapped the previous kernel's tail; from here on its results are needed
+  pdl_launch_dependents();
+  pdl_wait();
 
   // work items: (m_unit, n_tile) with m_unit = one M tile, or a pair of consecutive M tiles
   const int m_units = kPair ? (p.m_tiles + 1) / 2 : p.m_tiles;

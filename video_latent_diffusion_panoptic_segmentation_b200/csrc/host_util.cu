@@ -2,6 +2,7 @@
 
 #include <atomic>
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace ldm_host {
@@ -25,6 +26,15 @@ int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(LDM_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
   return LDM_OK;
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LDM_PDL");
+    v = e ? atoi(e) : 0;
+  }
+  return v != 0;
 }
 
 int num_sms() {

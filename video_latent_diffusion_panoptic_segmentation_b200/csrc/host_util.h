@@ -21,6 +21,39 @@ int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims
               const uint32_t* box, int elem_bytes, bool swizzle128);
 
 inline cudaStream_t as_stream(ldm_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// LDM_PDL=1 turns programmatic dependent launch on. Measured on B200 inside the CUDA graph of the UNet plan: 8.58 fps
+// with it, 8.63 without (launch gaps are already hidden by the graph), so the default is off.
+bool pdl_enabled();
+
+// Launch with programmatic stream serialisation (the kernel must call pdl_wait() before its first global access) and,
+// optionally, a thread-block cluster of `cluster` CTAs.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster,
+                       Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 int num_sms();
 
 }  // namespace ldm_host

@@ -16,6 +16,8 @@ using namespace ldm;
 __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, const __nv_bfloat16* __restrict__ x2, int c1,
                                 int c2, int HW, int groups, float* __restrict__ partial) {
   extern __shared__ float sh[];  // [ppb][C] sums, then [ppb][C] sums of squares
+  pdl_launch_dependents();
+  pdl_wait();
   const int C = c1 + c2;
   const int cpg = C / groups;
   const int b = blockIdx.y;
@@ -92,6 +94,8 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, const __nv
                                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
                                 __nv_bfloat16* __restrict__ out) {
   extern __shared__ float sh[];  // mean[groups], rstd[groups]
+  pdl_launch_dependents();
+  pdl_wait();
   const int C = c1 + c2;
   const int cpg = C / groups;
   const int b = blockIdx.y;
@@ -250,6 +254,8 @@ __global__ void layernorm_rows_kernel(const __nv_bfloat16* __restrict__ x, const
                                       const float* __restrict__ beta, __nv_bfloat16* __restrict__ out, int rows, float eps) {
   constexpr int C = LPR * 40;
   constexpr int RPW = 32 / LPR;  // rows per warp
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int sub = lane / LPR, sl = lane % LPR;
   const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -312,8 +318,10 @@ static int launch_layernorm_rows(const void* x, const float* gamma, const float*
   const int wpb = 8;
   const long long warps = ((long long)rows + RPW - 1) / RPW;
   const int grid = (int)((warps + wpb - 1) / wpb);
-  layernorm_rows_kernel<LPR><<<grid, wpb * 32, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta,
-                                                      reinterpret_cast<__nv_bfloat16*>(out), rows, eps);
+  cudaError_t le = ldm_host::launch_pdl(layernorm_rows_kernel<LPR>, dim3(grid), dim3(wpb * 32), (size_t)0, s, 1,
+                                        reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta,
+                                        reinterpret_cast<__nv_bfloat16*>(out), rows, eps);
+  if (le != cudaSuccess) return ldm_host::set_error(LDM_ERR_CUDA, "layernorm_rows_kernel launch: %s", cudaGetErrorString(le));
   ldm_host::count_launch();
   return ldm_host::check_launch("layernorm_rows_kernel");
 }
@@ -355,15 +363,19 @@ extern "C" int ldm_groupnorm_silu(const ldm_groupnorm_desc* d, ldm_stream_t stre
     attr_set = true;
   }
   LDM_REQUIRE(sh1 <= 96 * 1024, LDM_ERR_BAD_SHAPE, "ldm_groupnorm_silu: C=%d too large", C);
-  gn_stats_kernel<<<dim3(chunks, d->B), dim3(vpp, ppb), sh1, s>>>(
-      reinterpret_cast<const __nv_bfloat16*>(d->x1), reinterpret_cast<const __nv_bfloat16*>(d->x2), d->c1, c2, d->HW,
-      d->groups, partial);
+  cudaError_t le = launch_pdl(gn_stats_kernel, dim3(chunks, d->B), dim3(vpp, ppb), sh1, s, 1,
+                              reinterpret_cast<const __nv_bfloat16*>(d->x1), reinterpret_cast<const __nv_bfloat16*>(d->x2),
+                              d->c1, c2, d->HW, d->groups, partial);
+  if (le != cudaSuccess) return set_error(LDM_ERR_CUDA, "gn_stats_kernel launch: %s", cudaGetErrorString(le));
   count_launch();
   int rc = check_launch("gn_stats_kernel");
   if (rc) return rc;
-  gn_apply_kernel<<<dim3(chunks, d->B), dim3(vpp, ppb), sizeof(float) * 2 * d->groups + sizeof(double) * 2 * 8 * d->groups, s>>>(
-      reinterpret_cast<const __nv_bfloat16*>(d->x1), reinterpret_cast<const __nv_bfloat16*>(d->x2), d->c1, c2, d->HW,
-      d->groups, partial, chunks, d->gamma, d->beta, d->eps, d->silu, reinterpret_cast<__nv_bfloat16*>(d->out));
+  le = launch_pdl(gn_apply_kernel, dim3(chunks, d->B), dim3(vpp, ppb),
+                  sizeof(float) * 2 * d->groups + sizeof(double) * 2 * 8 * d->groups, s, 1,
+                  reinterpret_cast<const __nv_bfloat16*>(d->x1), reinterpret_cast<const __nv_bfloat16*>(d->x2), d->c1, c2,
+                  d->HW, d->groups, (const float*)partial, chunks, d->gamma, d->beta, d->eps, d->silu,
+                  reinterpret_cast<__nv_bfloat16*>(d->out));
+  if (le != cudaSuccess) return set_error(LDM_ERR_CUDA, "gn_apply_kernel launch: %s", cudaGetErrorString(le));
   count_launch();
   return check_launch("gn_apply_kernel");
 }
