@@ -6,45 +6,29 @@
 //     warps 4..4+4*NQ-1   softmax      : one query row per thread. The whole score row of a KV block is read from TMEM
 //                                        into registers in one pass and the S columns are handed back at once
 //                                        (s_free), so the tensor core computes S of the NEXT block while this block's
-//                                        exp2 / bf16 P (swizzled smem, the A operand of the PV MMA) are produced.
+//                                        exp2 / bf16 P are produced. P goes back into TMEM (tcgen05.st) and is the
+//                                        A operand of the PV MMA straight from there: an MMA whose A tile comes from
+//                                        shared memory costs 43 + N/2 cycles, from TMEM 10 + N/2
+//                                        (tools/microbench/tmem_bench.cu), and PV has N = 48.
 //                                        O accumulates in TMEM across blocks; it is rescaled (TMEM ld/st) only when a
 //                                        row maximum grew by more than 2^8 since the last rescale, which is rare after
 //                                        the first blocks, so the steady-state loop is max -> exp2 -> pack -> store.
+//   TMEM columns of one query group: a ring of 1.5*BKV columns shared by S and P, then O. S of an even block sits at
+//   [0, BKV), its P (bf16 pairs) at [0, BKV/2); S of an odd block at [BKV/2, 3BKV/2), its P at [BKV, 3BKV/2). A thread
+//   has its whole score row in registers before it writes P over it, S of block j+1 never overlaps P of block j, and
+//   S of block j+2 is issued after PV of block j on the in-order tensor pipe -- so the softmax threads never wait for
+//   a PV MMA (only the rare rescale of O does).
 //   Layouts: q,k [B*heads, seq, dpad] (dpad = 64*ceil(d/64), zero padded), vt [B*heads, vt_rows, seq_pad] (V transposed
 //   so that both MMAs see K-major operands; vt_rows = 16*ceil(d/16); when d % 16 != 0 the caller keeps row d of every
 //   head at 1.0 so the PV MMA also produces the softmax row sums), out [B*seq, heads*d]; all bf16.
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "attn_common.cuh"
 #include "host_util.h"
 
 namespace {
 using namespace ldm;
-
-struct AttnParams {
-  int seq, heads, head_dim;
-  float scale_log2;  // scale * log2(e)
-  __nv_bfloat16* out;
-};
-
-__device__ __forceinline__ float ex2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-// exp2 on the FMA pipe (Cody-Waite split + degree-3 minimax of 2^f on [-0.5, 0.5], max rel. error 1.0e-4 -- 40x below
-// the bf16 rounding of P): the softmax of the 40-wide heads is bound by the 16/clk/SM MUFU unit, so kPoly of every 8
-// exponentials are computed here instead. x <= 8 (lazy rescale) and x may be -inf (masked tail keys).
-__device__ __forceinline__ float ex2_poly(float x) {
-  x = fmaxf(x, -125.0f);
-  const float t = x + 12582912.0f;         // 1.5 * 2^23: round(x) lands in the low mantissa bits
-  const float f = x - (t - 12582912.0f);  // [-0.5, 0.5]
-  float p = fmaf(f, 0.05500891f, 0.24221097f);
-  p = fmaf(p, f, 0.69328293f);
-  p = fmaf(p, f, 1.0f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
-}
+using namespace ldm_attn;
 
 template <int D, int NQ, int BKV, int STAGES>
 struct AttnCfg {
@@ -58,12 +42,13 @@ struct AttnCfg {
   static constexpr int kVBytes = kVAtoms * kDN * 128;
   static constexpr int kVBytesPad = ((kVBytes + 1023) / 1024) * 1024;
   static constexpr int kStageBytes = kKBytes + kVBytesPad;
-  static constexpr int kPBytes = kVAtoms * 128 * 128;  // per group
-  static constexpr int kSmem = NQ * (kQBytes + kPBytes) + STAGES * kStageBytes + 1024 + 256;
+  static constexpr int kSmem = NQ * kQBytes + STAGES * kStageBytes + 1024 + 256;
   static constexpr int kThreads = 128 + 128 * NQ;  // warpgroup 0: producer, MMA issuer (+2 idle warps); then NQ softmax warpgroups
   static constexpr int kTmemGroupStride = 256;
-  static constexpr int kTmemCols = (NQ == 2) ? 512 : ((BKV + kDN <= 256) ? 256 : 512);
-  static_assert(NQ == 1 || BKV + kDN <= 256, "TMEM budget");
+  static constexpr int kRing = BKV + BKV / 2;          // S / P ring of one group (columns)
+  static constexpr int kTmemCols = (NQ == 2) ? 512 : ((kRing + kDN <= 256) ? 256 : 512);
+  static_assert(NQ == 1 || kRing + kDN <= 256, "TMEM budget");
+  static_assert(kRing + kDN <= 512, "TMEM budget");
   static_assert(kSmem <= 227 * 1024, "smem budget");
 };
 
@@ -75,8 +60,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                                  // NQ * kQBytes
-  uint8_t* sP = sQ + NQ * Cfg::kQBytes;                // NQ * kPBytes
-  uint8_t* sKV = sP + NQ * Cfg::kPBytes;               // STAGES * kStageBytes
+  uint8_t* sKV = sQ + NQ * Cfg::kQBytes;               // STAGES * kStageBytes
   uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + STAGES * Cfg::kStageBytes);
   uint64_t* q_full = bars;               // [NQ]
   uint64_t* kv_full = q_full + 2;        // [STAGES]
@@ -162,10 +146,10 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     {
       const uint32_t idesc_s = umma_idesc_bf16(128, BKV);
       const uint32_t idesc_o = umma_idesc_bf16(128, Cfg::kDN);
-      auto issue_s = [&](int g, int stage) {
+      auto issue_s = [&](int g, int stage, int blk) {
         const uint32_t qa = smem_u32(sQ + g * Cfg::kQBytes);
         const uint32_t ka = smem_u32(sKV + stage * Cfg::kStageBytes);
-        const uint32_t d_tmem = tmem_base + g * Cfg::kTmemGroupStride;
+        const uint32_t d_tmem = tmem_base + g * Cfg::kTmemGroupStride + (blk & 1) * (BKV / 2);
         if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < Cfg::kSteps; ++kk) {
@@ -177,52 +161,46 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         }
         __syncwarp();
       };
-      auto issue_o = [&](int g, int stage, bool accumulate) {
-        const uint32_t pa = smem_u32(sP + g * Cfg::kPBytes);
+      auto issue_o = [&](int g, int stage, int blk) {
+        const uint32_t pa = tmem_base + g * Cfg::kTmemGroupStride + (blk & 1) * BKV;  // 8 columns per k-step
         const uint32_t va = smem_u32(sKV + stage * Cfg::kStageBytes + Cfg::kKBytes);
-        const uint32_t d_tmem = tmem_base + g * Cfg::kTmemGroupStride + BKV;
+        const uint32_t d_tmem = tmem_base + g * Cfg::kTmemGroupStride + Cfg::kRing;
         if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < BKV / 16; ++kk) {
-            const uint64_t da = umma_desc_k_sw128(pa + (kk >> 2) * (128 * 128) + (kk & 3) * 32);
             const uint64_t db = umma_desc_k_sw128(va + (kk >> 2) * (Cfg::kDN * 128) + (kk & 3) * 32);
-            umma_bf16(d_tmem, da, db, idesc_o, accumulate || kk != 0);
+            umma_bf16_ts(d_tmem, pa + kk * 8, db, idesc_o, blk > 0 || kk != 0);
           }
           umma_commit(&o_full[g]);
         }
         __syncwarp();
       };
       for (int g = 0; g < NQ; ++g) mbar_wait(&q_full[g], 0);
-      int stage = 0;
-      uint32_t phase = 0;
       mbar_wait(&kv_full[0], 0);
       tc_fence_after();
-      for (int g = 0; g < NQ; ++g) issue_s(g, 0);
+      for (int g = 0; g < NQ; ++g) issue_s(g, 0, 0);
+      // Fixed order S(g0, j+1) S(g1, j+1) PV(g0, j) PV(g1, j). (An event loop that serves the groups in the order their
+      // barriers complete was measured slower: 1.17 ms against 1.08 ms at d = 40, 7 488 tokens.)
       for (int j = 0; j < nblk; ++j) {
-        int nstage = stage + 1;
-        uint32_t nphase = phase;
-        if (nstage == STAGES) {
-          nstage = 0;
-          nphase ^= 1;
-        }
+        const int stage = j % STAGES, nstage = (j + 1) % STAGES;
         if (j + 1 < nblk) {
           // S of the next block as soon as the softmax threads have pulled this block's scores out of TMEM
-          mbar_wait(&kv_full[nstage], nphase);
+          mbar_wait(&kv_full[nstage], ((j + 1) / STAGES) & 1);
           for (int g = 0; g < NQ; ++g) {
             mbar_wait(&s_free[g], j & 1);
             tc_fence_after();
-            issue_s(g, nstage);
+            TRACE(2 + g, j + 1);
+            issue_s(g, nstage, j + 1);
           }
         }
         for (int g = 0; g < NQ; ++g) {
           mbar_wait(&p_full[g], j & 1);
           tc_fence_after();
-          issue_o(g, stage, j > 0);
+          TRACE(4 + g, j);
+          issue_o(g, stage, j);
         }
         if (elect_one()) umma_commit(&kv_empty[stage]);
         __syncwarp();
-        stage = nstage;
-        phase = nphase;
       }
     }
     __syncwarp();
@@ -234,9 +212,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const int quad = warp & 3;
     const int r = quad * 32 + lane;
     const int qrow = q_base + g * 128 + r;
-    const uint32_t t_s = tmem_base + ((uint32_t)(quad * 32) << 16) + g * Cfg::kTmemGroupStride;
-    const uint32_t t_o = t_s + BKV;
-    uint8_t* myP = sP + g * Cfg::kPBytes;
+    const uint32_t t_g = tmem_base + ((uint32_t)(quad * 32) << 16) + g * Cfg::kTmemGroupStride;
+    const uint32_t t_o = t_g + Cfg::kRing;
     float m = -INFINITY, l = 0.f;      // m: reference maximum the stored P / O are relative to (log2 domain)
     float m_seen = -INFINITY;          // running row maximum including the previous block (m lags behind it)
     constexpr bool kOnes = Cfg::kOnesRow;  // row sums come out of the PV MMA (ones row of V^T at index D)
@@ -245,12 +222,17 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 
     for (int j = 0; j < nblk; ++j) {
       const int nvalid = p.seq - j * BKV;  // keys of this block inside the sequence (>= 1)
+      const uint32_t t_s = t_g + (j & 1) * (BKV / 2);  // this block's scores ...
+      const uint32_t t_p = t_g + (j & 1) * BKV;        // ... and where its P goes (see the column ring above)
+      TRACE(0, j);
       mbar_wait(&s_full[g], j & 1);
       tc_fence_after();
+      TRACE(1, j);
       uint32_t sv[BKV];  // the whole score row of this block stays in registers: one TMEM pass
 #pragma unroll
       for (int c = 0; c < BKV; c += 32) tmem_ld32(t_s + c, sv + c);
       tmem_ld_wait();
+      TRACE(2, j);
       tc_fence_before();
       mbar_arrive(&s_free[g]);  // the S columns may be overwritten by the next block's QK^T now
       if (nvalid < BKV) {  // only the last block of a ragged sequence
@@ -261,6 +243,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 
       // O (TMEM) and l move to the new reference max(m, target) for the rows that need it
       auto rescale = [&](bool need, float target) {
+        if (j > 0) mbar_wait(&o_full[g], (j - 1) & 1);  // PV of the previous block has landed in O
         tc_fence_after();
         const float m_new = need ? target : m;
         const float alpha = ex2(m - m_new);  // 1 for the rows that keep their reference
@@ -277,32 +260,35 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         }
         tmem_st_wait();
       };
-      // P = exp2(s*scale - m) as bf16 into the swizzled A-operand tile; the block maximum is tracked in the same
-      // pass (the FMNMX issue between the MUFUs instead of in a MUFU-idle phase of their own)
+      // P = exp2(s*scale - m) as bf16 pairs into TMEM (the A operand of the PV MMA); the block maximum is tracked in
+      // the same pass (the FMNMX issue between the MUFUs instead of in a MUFU-idle phase of their own)
       auto exp_pass = [&](float& bmax, float& bsum) {
         float mx0 = -INFINITY, mx1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+        const uint64_t scale2 = pack2(p.scale_log2, p.scale_log2), negm2 = pack2(-m, -m);
 #pragma unroll
-        for (int c = 0; c < BKV; c += 8) {
-          float e[8];
+        for (int c = 0; c < BKV; c += 16) {
+          uint32_t u[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float sraw = __uint_as_float(sv[c + i]);
-            const float x = fmaf(sraw, p.scale_log2, -m);
-            e[i] = (i < 8 - kPoly) ? ex2(x) : ex2_poly(x);
-            if (i & 1) mx1 = fmaxf(mx1, sraw); else mx0 = fmaxf(mx0, sraw);
+          for (int q = 0; q < 8; ++q) {  // pairs of keys; kPoly of every 8 pairs take the FMA-pipe exp2
+            const float s0 = __uint_as_float(sv[c + 2 * q]), s1 = __uint_as_float(sv[c + 2 * q + 1]);
+            if (q & 1) mx1 = fmax3(mx1, s0, s1); else mx0 = fmax3(mx0, s0, s1);
+            const uint64_t x = ffma2(pack2(s0, s1), scale2, negm2);
+            float e0, e1;
+            if (q % 8 < 8 - kPoly) {
+              float x0, x1;
+              unpack2(x, x0, x1);
+              e0 = ex2(x0);
+              e1 = ex2(x1);
+            } else {
+              ex2_poly2(x, e0, e1);
+            }
+            if (!kOnes) {
+              l0 += e0;
+              l1 += e1;
+            }
+            u[q] = pack_bf16(e0, e1);
           }
-          if (!kOnes) {
-            l0 += (e[0] + e[1]) + (e[2] + e[3]);
-            l1 += (e[4] + e[5]) + (e[6] + e[7]);
-          }
-          uint4 u;
-          u.x = pack_bf16(e[0], e[1]);
-          u.y = pack_bf16(e[2], e[3]);
-          u.z = pack_bf16(e[4], e[5]);
-          u.w = pack_bf16(e[6], e[7]);
-          // row r of the K-major SWIZZLE_128B tile: 16-byte chunk index XOR (r & 7)
-          uint8_t* rowp = myP + (c >> 6) * (128 * 128) + r * 128;
-          *reinterpret_cast<uint4*>(rowp + ((((c & 63) >> 3) ^ (r & 7)) << 4)) = u;
+          tmem_st8(t_p + (c >> 1), u);  // keys c .. c+15 of this thread's row = 8 columns of bf16 pairs
         }
         bmax = fmaxf(mx0, mx1) * p.scale_log2;  // scale > 0
         bsum = l0 + l1;
@@ -310,19 +296,15 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 
       if (j == 0) {
         // the first block needs its true maximum up front (nothing to be relative to yet)
-        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+        float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
         for (int i = 0; i < BKV; i += 4) {
-          mx0 = fmaxf(mx0, __uint_as_float(sv[i]));
-          mx1 = fmaxf(mx1, __uint_as_float(sv[i + 1]));
-          mx2 = fmaxf(mx2, __uint_as_float(sv[i + 2]));
-          mx3 = fmaxf(mx3, __uint_as_float(sv[i + 3]));
+          mx0 = fmax3(mx0, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
+          mx1 = fmax3(mx1, __uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3]));
         }
-        m = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
+        m = fmaxf(mx0, mx1) * p.scale_log2;
         m_seen = m;
       } else {
-        // PV of the previous block has finished: P smem may be rewritten and O may be touched
-        mbar_wait(&o_full[g], (j - 1) & 1);
         const bool need = m_seen - m > kLazy;
         if (__any_sync(0xffffffffu, need)) rescale(need, m_seen);
       }
@@ -337,9 +319,11 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       }
       m_seen = fmaxf(m_seen, bmax);
       if (!kOnes) l += bsum;
-      fence_proxy_async_smem();
+      TRACE(3, j);
+      tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_full[g]);
+      TRACE(4, j);
     }
     mbar_wait(&o_full[g], (nblk - 1) & 1);
     tc_fence_after();
@@ -437,14 +421,22 @@ extern "C" int ldm_flash_attn_fwd(const ldm_attn_desc* d, ldm_stream_t stream) {
   cudaStream_t s = as_stream(stream);
   switch (d->head_dim) {
     case 40: {
-      static int poly = -1;  // LDM_ATTN_POLY=0/1/2: A/B timing of the FMA-pipe exp2 share (default 1 of 8)
+      static int split = -1;  // LDM_ATTN40=0: the generic kernel below instead of attn40_tc.cu (A/B timing)
+      if (split < 0) {
+        const char* e = getenv("LDM_ATTN40");
+        split = e ? atoi(e) : 1;
+      }
+      if (split) return ldm_launch_attn40(d, s);
+      static int poly = -1;  // LDM_ATTN_POLY=0..4: A/B timing of the FMA-pipe exp2 share (n of 8)
       if (poly < 0) {
         const char* e = getenv("LDM_ATTN_POLY");
-        poly = e ? atoi(e) : 1;
+        poly = e ? atoi(e) : 2;
       }
       if (poly == 0) return launch_attn<40, 2, 128, 4, 0>(d, s);
-      if (poly == 2) return launch_attn<40, 2, 128, 4, 2>(d, s);
-      return launch_attn<40, 2, 128, 4, 1>(d, s);
+      if (poly == 1) return launch_attn<40, 2, 128, 4, 1>(d, s);
+      if (poly == 3) return launch_attn<40, 2, 128, 4, 3>(d, s);
+      if (poly == 4) return launch_attn<40, 2, 128, 4, 4>(d, s);
+      return launch_attn<40, 2, 128, 4, 2>(d, s);
     }
     case 80: {
       static int v = -1;  // LDM_ATTN_D80=0: one query group, 128-key blocks; 1 (default): two groups, 64-key blocks
