@@ -122,7 +122,9 @@ int ldm_flash_attn_fwd(const ldm_attn_desc* d, ldm_stream_t stream);
  * Replaces: torch.nn.GroupNorm + SiLU in ResnetBlock2D.norm1/norm2, Transformer2DModel.norm,
  * UNet.conv_norm_out (unet.py:428-430), seg-AE decoder GroupNorm (vae.py:163-164).
  * stats: caller-provided scratch of ldm_groupnorm_scratch_bytes(B, groups) bytes (per-chunk partial moments; the
- * reduction order is fixed, so results are bit-reproducible run to run).
+ * reduction order is fixed, so results are bit-reproducible run to run) followed by the barrier counters of the
+ * one-launch path. The scratch must be ZERO before its first use; every call leaves the counters zero. One scratch
+ * must not be shared by GroupNorms running concurrently on different streams.
  * ---------------------------------------------------------------------------------------------------------- */
 typedef struct ldm_groupnorm_desc {
   const void* x1;

@@ -48,10 +48,28 @@ bench(int mode, int ld_warps, int n_mma, int ts, int mma_iters, int cols_per_ld,
           for (int kk = 0; kk < 4; ++kk) {
             const uint64_t da = umma_desc_k_sw128(a + kk * 32);
             const uint64_t db = umma_desc_k_sw128(b + kk * 32);
-            if (ts)
-              umma_bf16_ts(tmem_base + 256, tmem_base + 128 + kk * 8, db, idesc, 1);
+            // cols_per_ld doubles as a switch here: 1 = alternate between two accumulators (are back-to-back MMAs into the
+            // same D serialised?), 2 = one accumulator per k-step (four)
+            const uint32_t d_off = cols_per_ld == 1 ? (kk & 1) * n_mma : (cols_per_ld == 2 ? kk * n_mma : 0);
+            if (ts == 2) {
+              // stage this k-step's A slab (128 rows x 32 B) in TMEM, then read it from there
+              const uint32_t stage_col = tmem_base + 128 + ((it & 1) * 4 + kk) * 8;
+              asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(stage_col), "l"(da) : "memory");
+              umma_bf16_ts(tmem_base + 256 + d_off, stage_col, db, idesc, 1);
+            } else if (ts == 3) {
+              // the four copies of a k-block first, then its four MMAs
+              if (kk == 0) {
+#pragma unroll
+                for (int k2 = 0; k2 < 4; ++k2)
+                  asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(tmem_base + 128 + ((it & 1) * 4 + k2) * 8),
+                               "l"(umma_desc_k_sw128(a + k2 * 32))
+                               : "memory");
+              }
+              umma_bf16_ts(tmem_base + 256 + d_off, tmem_base + 128 + ((it & 1) * 4 + kk) * 8, db, idesc, 1);
+            } else if (ts)
+              umma_bf16_ts(tmem_base + 256 + d_off, tmem_base + 128 + kk * 8, db, idesc, 1);
             else
-              umma_bf16(tmem_base + 256, da, db, idesc, 1);
+              umma_bf16(tmem_base + 256 + d_off, da, db, idesc, 1);
           }
         }
         umma_commit(&bar);
@@ -174,17 +192,6 @@ int main() {
   for (int w : {4, 8, 16}) run_ld<128>(w);
   for (int w : {4, 8, 16}) run_ld<64>(w);
   for (int w : {4, 8, 16}) run_ld<32>(w);
-  printf("== (A) tcgen05.ld 32x32b.x32, 128 columns per thread per iteration\n");
-  for (int w : {4, 8, 16}) {
-    const double cyc = run(0, w, 128, 0, 0);
-    const double bytes = (double)w * 32 * 128 * 4 * kLdIters;
-    printf("ld_warps=%2d : %.0f cycles, %.1f B/clk/SM\n", w, cyc, bytes / cyc);
-  }
-  for (int w : {4, 8}) {
-    const double cyc = run(0, w, 128, 0, 0, 32);
-    const double bytes = (double)w * 32 * 128 * 4 * kLdIters;
-    printf("ld_warps=%2d (same 64 columns): %.0f cycles, %.1f B/clk/SM\n", w, cyc, bytes / cyc);
-  }
   printf("== (B) tcgen05.mma M=128 K=16 bf16, back to back from one thread\n");
   const int iters = 4000;
   for (int ts = 0; ts < 2; ++ts)
@@ -193,13 +200,18 @@ int main() {
       printf("A in %s, N=%3d : %.1f cycles per MMA (math floor %.1f)\n", ts ? "TMEM" : "smem", n, cyc / (4.0 * iters),
              128.0 * n * 16 / 4096);
     }
-  printf("== (C) 8 ld warps + MMA stream (N=48 / N=128, A in smem)\n");
-  for (int n : {48, 128}) {
-    // size the MMA stream so both finish at about the same time
-    const double cyc = run(2, 8, n, 0, 6000);
-    const double bytes = 8.0 * 32 * 128 * 4 * kLdIters;
-    printf("N=%3d : %.0f cycles total; alone the loads would give %.1f B/clk/SM, the MMAs %.1f cycles each\n", n, cyc,
-           bytes / cyc, cyc / (4.0 * 6000));
-  }
+  printf("== (B3) A staged into TMEM by tcgen05.cp (128x256b) in front of every TS MMA / in front of every four\n");
+  for (int mode : {2, 3})
+    for (int n : {64, 128, 192, 256}) {
+      const double cyc = run(1, 0, n, mode, iters);
+      printf("cp+TS mode %d, N=%3d : %.1f cycles per MMA (SS: %.0f, TS: %.0f)\n", mode, n, cyc / (4.0 * iters), 43.0 + n / 2, 10.0 + n / 2);
+    }
+  printf("== (B2) same, alternating between two / four accumulators\n");
+  for (int alt : {1, 2})
+    for (int n : {32, 64, 128}) {
+      const double cyc = run(1, 0, n, 0, iters, alt);
+      printf("A in smem, N=%3d, %d accumulators : %.1f cycles per MMA (math floor %.1f)\n", n, alt * 2, cyc / (4.0 * iters),
+             128.0 * n * 16 / 4096);
+    }
   return 0;
 }

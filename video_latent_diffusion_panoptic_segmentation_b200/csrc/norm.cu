@@ -1,6 +1,8 @@
 // HBM-bound normalisation kernels on NHWC bf16 activations: GroupNorm(+SiLU) over a (virtual) channel concat and
 // LayerNorm over the channel dim. 16-byte vector loads/stores, warp-shuffle + shared-memory reductions, fp32 math,
 // fp64 cross-CTA accumulation of the GroupNorm moments.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "host_util.h"
 
@@ -13,11 +15,9 @@ using namespace ldm;
 // pixels with stride ppb*chunks (4 independent 16-byte loads in flight); per-thread sums go to shared memory and one
 // thread per group folds its channels x pixel-lanes in a fixed order. partial: f32 [B, chunks, groups, 2].
 // ---------------------------------------------------------------------------------------------------------
-__global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, const __nv_bfloat16* __restrict__ x2, int c1,
-                                int c2, int HW, int groups, float* __restrict__ partial) {
-  extern __shared__ float sh[];  // [ppb][C] sums, then [ppb][C] sums of squares
-  pdl_launch_dependents();
-  pdl_wait();
+__device__ __forceinline__ void gn_stats_body(float* sh, const __nv_bfloat16* __restrict__ x1,
+                                              const __nv_bfloat16* __restrict__ x2, int c1, int c2, int HW, int groups,
+                                              float* __restrict__ partial) {
   const int C = c1 + c2;
   const int cpg = C / groups;
   const int b = blockIdx.y;
@@ -86,16 +86,22 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, const __nv
   }
 }
 
+__global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, const __nv_bfloat16* __restrict__ x2, int c1,
+                                int c2, int HW, int groups, float* __restrict__ partial) {
+  extern __shared__ float sh[];  // [ppb][C] sums, then [ppb][C] sums of squares
+  pdl_launch_dependents();
+  pdl_wait();
+  gn_stats_body(sh, x1, x2, c1, c2, HW, groups, partial);
+}
+
 // GroupNorm pass 2: fold the partials (fixed order, fp64), then normalise + affine (+ SiLU). Same thread layout as
 // pass 1: a thread owns one 8-channel vector position, so its scale/shift (rstd*gamma, beta - mean*rstd*gamma) are
 // computed once and the pixel loop is load -> 8 FMA (+ SiLU) -> store with 4 independent 16-byte loads in flight.
-__global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, const __nv_bfloat16* __restrict__ x2, int c1,
-                                int c2, int HW, int groups, const float* __restrict__ partial, int chunks,
-                                const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
-                                __nv_bfloat16* __restrict__ out) {
-  extern __shared__ float sh[];  // mean[groups], rstd[groups]
-  pdl_launch_dependents();
-  pdl_wait();
+__device__ __forceinline__ void gn_apply_body(float* sh, const __nv_bfloat16* __restrict__ x1,
+                                              const __nv_bfloat16* __restrict__ x2, int c1, int c2, int HW, int groups,
+                                              const float* partial, int chunks, const float* __restrict__ gamma,
+                                              const float* __restrict__ beta, float eps, int silu,
+                                              __nv_bfloat16* __restrict__ out) {
   const int C = c1 + c2;
   const int cpg = C / groups;
   const int b = blockIdx.y;
@@ -103,7 +109,8 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, const __nv
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
   const double n = (double)cpg * (double)HW;
   // fold the per-chunk partials in fp64: kFoldSlices threads per group take every kFoldSlices-th chunk, then one
-  // thread per group adds the slices in order (fixed order -> bit-reproducible)
+  // thread per group adds the slices in order (fixed order -> bit-reproducible). (A warp per group with a shuffle tree
+  // was measured slower: three rounds of L2 latency for the 32 groups instead of one.)
   constexpr int kFoldSlices = 8;
   double* shd = reinterpret_cast<double*>(sh + 2 * groups);  // [kFoldSlices][groups][2]
   const int nthr = blockDim.x * blockDim.y;
@@ -112,8 +119,10 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, const __nv
     double a = 0.0, q = 0.0;
     const float* pp = partial + ((long long)b * chunks * groups + g) * 2;
     for (int k = sl; k < chunks; k += kFoldSlices) {
-      a += (double)pp[(long long)k * groups * 2];
-      q += (double)pp[(long long)k * groups * 2 + 1];
+      // (L2 loads: in the fused kernel other CTAs wrote these after this kernel started)
+      const float2 v = __ldcg(reinterpret_cast<const float2*>(pp + (long long)k * groups * 2));
+      a += (double)v.x;
+      q += (double)v.y;
     }
     shd[(sl * groups + g) * 2] = a;
     shd[(sl * groups + g) * 2 + 1] = q;
@@ -181,6 +190,49 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, const __nv
     apply8(u0, pix); apply8(u1, pix + stride); apply8(u2, pix + 2 * stride); apply8(u3, pix + 3 * stride);
   }
   for (; pix < HW; pix += stride) apply8(ld_nc_v4(src + (long long)pix * cs), pix);
+}
+
+__global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, const __nv_bfloat16* __restrict__ x2, int c1,
+                                int c2, int HW, int groups, const float* __restrict__ partial, int chunks,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
+                                __nv_bfloat16* __restrict__ out) {
+  extern __shared__ float sh[];  // mean[groups], rstd[groups], fp64 fold scratch
+  pdl_launch_dependents();
+  pdl_wait();
+  gn_apply_body(sh, x1, x2, c1, c2, HW, groups, partial, chunks, gamma, beta, eps, silu, out);
+}
+
+// Both passes in ONE cooperative launch (all CTAs co-resident: grid <= 2 x SM count): the CTAs of an image meet at a
+// counter barrier between the passes, so a GroupNorm costs one launch and the second read of x comes out of L2 while
+// it is still warm. Half of the 61 GroupNorms of a UNet forward are small (7-30 MB) and were bound by the two launches,
+// not by bandwidth. counters: u32 [2][B], zero before the first use; the kernel leaves them zero.
+__global__ void __launch_bounds__(512, 2)
+gn_fused_kernel(const __nv_bfloat16* __restrict__ x1, const __nv_bfloat16* __restrict__ x2, int c1, int c2, int HW,
+                int groups, float* partial, unsigned int* counters, const float* __restrict__ gamma,
+                const float* __restrict__ beta, float eps, int silu, __nv_bfloat16* __restrict__ out) {
+  extern __shared__ float sh[];
+  const int b = blockIdx.y, B = gridDim.y, chunks = gridDim.x;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  gn_stats_body(sh, x1, x2, c1, c2, HW, groups, partial);
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    atomicAdd(&counters[b], 1u);
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counters + b) : "memory");
+      if (seen < (unsigned int)chunks) __nanosleep(64);
+    } while (seen < (unsigned int)chunks);
+  }
+  __syncthreads();
+  gn_apply_body(sh, x1, x2, c1, c2, HW, groups, partial, chunks, gamma, beta, eps, silu, out);
+  if (tid == 0) {
+    // the last CTA of the image to get here has seen everybody pass the barrier: reset for the next launch
+    if (atomicAdd(&counters[B + b], 1u) == (unsigned int)chunks - 1u) {
+      counters[b] = 0u;
+      counters[B + b] = 0u;
+    }
+  }
 }
 
 // LayerNorm: one warp per row, row cached in registers (C <= 32*8*kMaxVec).
@@ -335,9 +387,13 @@ static int gn_chunks(int B, int HW, int ppb) {
   return chunks < 1 ? 1 : chunks;
 }
 
-extern "C" size_t ldm_groupnorm_scratch_bytes(int32_t B, int32_t groups) {
-  // upper bound of chunks over all shapes: 2 * SM count per image
+static size_t gn_partial_bytes(int B, int groups) {
   return sizeof(float) * 2 * (size_t)groups * (size_t)B * (size_t)(2 * ldm_host::num_sms());
+}
+
+extern "C" size_t ldm_groupnorm_scratch_bytes(int32_t B, int32_t groups) {
+  // per-chunk partial moments (upper bound of chunks over all shapes: 2 * SM count per image) + the barrier counters
+  return gn_partial_bytes(B, groups) + sizeof(unsigned int) * 2 * (size_t)B;
 }
 
 extern "C" int ldm_groupnorm_silu(const ldm_groupnorm_desc* d, ldm_stream_t stream) {
@@ -363,6 +419,38 @@ extern "C" int ldm_groupnorm_silu(const ldm_groupnorm_desc* d, ldm_stream_t stre
     attr_set = true;
   }
   LDM_REQUIRE(sh1 <= 96 * 1024, LDM_ERR_BAD_SHAPE, "ldm_groupnorm_silu: C=%d too large", C);
+  const size_t sh2 = sizeof(float) * 2 * d->groups + sizeof(double) * 2 * 8 * d->groups;
+  static int fused = -1;  // LDM_GN_FUSED=0: the two-launch path (A/B timing)
+  if (fused < 0) {
+    const char* e = getenv("LDM_GN_FUSED");
+    fused = e ? atoi(e) : 1;
+  }
+  if (fused && (long long)chunks * d->B <= 2LL * num_sms() && vpp * ppb <= 512) {
+    static bool attr2 = false;
+    if (!attr2) {
+      cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      attr2 = true;
+    }
+    unsigned int* counters = reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(d->stats) +
+                                                             gn_partial_bytes(d->B, d->groups));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(chunks, d->B);
+    cfg.blockDim = dim3(vpp, ppb);
+    cfg.dynamicSmemBytes = sh1 > sh2 ? sh1 : sh2;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;  // the runtime checks that the whole grid is co-resident
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, gn_fused_kernel, reinterpret_cast<const __nv_bfloat16*>(d->x1),
+                                        reinterpret_cast<const __nv_bfloat16*>(d->x2), d->c1, c2, d->HW, d->groups, partial,
+                                        counters, d->gamma, d->beta, d->eps, d->silu,
+                                        reinterpret_cast<__nv_bfloat16*>(d->out));
+    if (le != cudaSuccess) return set_error(LDM_ERR_CUDA, "gn_fused_kernel launch: %s", cudaGetErrorString(le));
+    count_launch();
+    return check_launch("gn_fused_kernel");
+  }
   cudaError_t le = launch_pdl(gn_stats_kernel, dim3(chunks, d->B), dim3(vpp, ppb), sh1, s, 1,
                               reinterpret_cast<const __nv_bfloat16*>(d->x1), reinterpret_cast<const __nv_bfloat16*>(d->x2),
                               d->c1, c2, d->HW, d->groups, partial);
@@ -371,7 +459,7 @@ extern "C" int ldm_groupnorm_silu(const ldm_groupnorm_desc* d, ldm_stream_t stre
   int rc = check_launch("gn_stats_kernel");
   if (rc) return rc;
   le = launch_pdl(gn_apply_kernel, dim3(chunks, d->B), dim3(vpp, ppb),
-                  sizeof(float) * 2 * d->groups + sizeof(double) * 2 * 8 * d->groups, s, 1,
+                  sh2, s, 1,
                   reinterpret_cast<const __nv_bfloat16*>(d->x1), reinterpret_cast<const __nv_bfloat16*>(d->x2), d->c1, c2,
                   d->HW, d->groups, (const float*)partial, chunks, d->gamma, d->beta, d->eps, d->silu,
                   reinterpret_cast<__nv_bfloat16*>(d->out));

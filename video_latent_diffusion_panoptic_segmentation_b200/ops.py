@@ -126,7 +126,8 @@ def groupnorm(x1, gamma, beta, out, stats, *, x2=None, groups=32, eps=1e-5, silu
 
 
 def gn_scratch(B, groups, device):
-    return torch.empty(L.lib().ldm_groupnorm_scratch_bytes(B, groups) // 4, dtype=f32, device=device)
+    # zeros: the tail of the scratch holds the fused kernel's barrier counters (zero before first use, left zero)
+    return torch.zeros(L.lib().ldm_groupnorm_scratch_bytes(B, groups) // 4, dtype=f32, device=device)
 
 
 def layernorm(x, gamma, beta, out, eps=1e-5):
