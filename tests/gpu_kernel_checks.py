@@ -334,19 +334,29 @@ def check_gemm_convt():
 
 
 # ----------------------------------------------------------------------------------------------------------- attention
-def check_attention(B=1, heads=2, d=40, seq=300):
+def check_attention(B=1, heads=2, d=40, seq=300, log2_units=False, spread=1.0):
+    """log2_units: q arrives pre-multiplied by d^-0.5 * log2(e) (as the UNet's packed QKV weight produces it) and the
+    kernel is told scale = ln 2; spread > 1 widens the score range (running maxima that keep growing, lazy rescales)."""
     q, k, vt, dpad, seq_pad = _alloc_qkv(B, heads, seq, d)
-    qf = _randn((B * heads, seq, d), 55, 1.0, bf16)
+    qf = _randn((B * heads, seq, d), 55, spread, bf16)
     kf = _randn((B * heads, seq, d), 56, 1.0, bf16)
     vf = _randn((B * heads, seq, d), 57, 1.0, bf16)
     q[:, :, :d] = qf
     k[:, :, :d] = kf
     vt[:, :d, :seq] = vf.transpose(1, 2)
     out = _empty((B * seq, heads * d), dtype=bf16, device=DEV)
-    ops.flash_attn(q, k, vt, out, B=B, heads=heads, seq=seq, head_dim=d, dpad=dpad, seq_pad=seq_pad, scale=d ** -0.5)
-    ref = F.scaled_dot_product_attention(qf.float(), kf.float(), vf.float())  # [BH, seq, d]
+    if log2_units:
+        import math
+        qs = (qf.float() * (d ** -0.5 * math.log2(math.e))).to(bf16)
+        q[:, :, :d] = qs
+        ops.flash_attn(q, k, vt, out, B=B, heads=heads, seq=seq, head_dim=d, dpad=dpad, seq_pad=seq_pad,
+                       scale=math.log(2.0))
+        ref = F.scaled_dot_product_attention(qs.float(), kf.float(), vf.float(), scale=math.log(2.0))
+    else:
+        ops.flash_attn(q, k, vt, out, B=B, heads=heads, seq=seq, head_dim=d, dpad=dpad, seq_pad=seq_pad, scale=d ** -0.5)
+        ref = F.scaled_dot_product_attention(qf.float(), kf.float(), vf.float())  # [BH, seq, d]
     ref = ref.view(B, heads, seq, d).permute(0, 2, 1, 3).reshape(B * seq, heads * d)
-    return _stats(out, ref, f"flash_attn d={d} seq={seq}", 2e-2, 2e-2)
+    return _stats(out, ref, f"flash_attn d={d} seq={seq} log2_units={log2_units} spread={spread}", 2e-2, 2e-2)
 
 
 # ----------------------------------------------------------------------------------------------------------- integer tail
@@ -477,6 +487,12 @@ CHECKS = {
     "gemm_convt": check_gemm_convt,
     "attn_40_tail": check_attention,
     "attn_40_long": lambda: check_attention(1, 2, 40, 1872),
+    "attn_40_fold_tail": lambda: check_attention(1, 2, 40, 300, log2_units=True),
+    "attn_40_fold_long": lambda: check_attention(1, 2, 40, 1872, log2_units=True),
+    "attn_40_fold_tiny": lambda: check_attention(1, 1, 40, 40, log2_units=True),
+    "attn_40_fold_spread": lambda: check_attention(1, 2, 40, 1000, log2_units=True, spread=4.0),
+    "attn_40_spread": lambda: check_attention(1, 2, 40, 1000, spread=4.0),
+    "attn_80_fold": lambda: check_attention(1, 2, 80, 468, log2_units=True),
     "attn_80": lambda: check_attention(1, 2, 80, 468),
     "attn_160": lambda: check_attention(2, 2, 160, 120),
     "attn_160_b": lambda: check_attention(1, 2, 160, 468),

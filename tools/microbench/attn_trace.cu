@@ -28,10 +28,11 @@ int main(int argc, char** argv) {
   const size_t nq = (size_t)BH * seq * dpad, nv = (size_t)BH * vt_rows * seq_pad, no = (size_t)B * seq * heads * d;
   std::vector<uint16_t> hq(nq, 0), hk(nq, 0), hv(nv, 0);
   srand(1);
+  const bool fold = getenv("LDM_TRACE_FOLD") && atoi(getenv("LDM_TRACE_FOLD"));  // scores in log2 units (scale = ln 2)
   auto rnd = [] { return ((rand() & 0xffff) / 65536.0f - 0.5f) * 4.0f; };
   for (size_t r = 0; r < (size_t)BH * seq; ++r)
     for (int c = 0; c < d; ++c) {
-      hq[r * dpad + c] = f2bf(rnd());
+      hq[r * dpad + c] = f2bf(rnd() * (fold ? 0.15811388f * 1.44269504f : 1.0f));
       hk[r * dpad + c] = f2bf(rnd());
     }
   for (int bh = 0; bh < BH; ++bh)
@@ -45,7 +46,7 @@ int main(int argc, char** argv) {
   cudaMemcpy(q, hq.data(), nq * 2, cudaMemcpyHostToDevice);
   cudaMemcpy(k, hk.data(), nq * 2, cudaMemcpyHostToDevice);
   cudaMemcpy(vt, hv.data(), nv * 2, cudaMemcpyHostToDevice);
-  ldm_attn_desc desc = {q, k, vt, out, B, heads, seq, d, dpad, seq_pad, vt_rows, 0.15811388f};
+  ldm_attn_desc desc = {q, k, vt, out, B, heads, seq, d, dpad, seq_pad, vt_rows, fold ? 0.69314718f : 0.15811388f};
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
@@ -90,8 +91,14 @@ int main(int argc, char** argv) {
       a[3] += at(w, j, 4) - at(w, j, 3);
       a[4] += at(w, j + 1, 0) - at(w, j, 0);
     }
-    printf("warp %2d avg: s_full wait %5.0f  tmem ld %5.0f  exp pass %5.0f  st wait %5.0f  period %5.0f\n", w, a[0] / n,
-           a[1] / n, a[2] / n, a[3] / n, a[4] / n);
+    double b5 = 0, b6 = 0, b7 = 0;
+    for (int j = 8; j < 50; ++j) {
+      b5 += at(w, j, 5) - at(w, j, 2);
+      b6 += at(w, j, 6) - at(w, j, 5);
+      b7 += at(w, j, 7) - at(w, j, 6);
+    }
+    printf("warp %2d avg: s_full wait %5.0f  tmem ld %5.0f  exp pass %5.0f  st wait %5.0f  period %5.0f | fold: to prefill %5.0f  o_full wait %5.0f  fill %5.0f\n", w, a[0] / n,
+           a[1] / n, a[2] / n, a[3] / n, a[4] / n, b5 / n, b6 / n, b7 / n);
   }
   return 0;
 }

@@ -51,6 +51,11 @@ def cases():
             out[f"attn_{lv}"] = (lambda qkv=qkv, ao=ao, h=h, w=w, d=d: ops.flash_attn(
                 qkv["q"], qkv["k"], qkv["vt"], ao, B=B, heads=8, seq=h * w, head_dim=d, dpad=qkv["dpad"],
                 seq_pad=qkv["seq_pad"], scale=d ** -0.5), 4 * B * 8 * (h * w) ** 2 * d, 2 * 4 * M * C)
+            import math
+            q2 = (qkv["q"].float() * (d ** -0.5 * math.log2(math.e))).to(bf16)  # scores in log2 units, same spread
+            out[f"attnfold_{lv}"] = (lambda qkv=qkv, q2=q2, ao=ao, h=h, w=w, d=d: ops.flash_attn(
+                q2, qkv["k"], qkv["vt"], ao, B=B, heads=8, seq=h * w, head_dim=d, dpad=qkv["dpad"],
+                seq_pad=qkv["seq_pad"], scale=math.log(2.0)), 4 * B * 8 * (h * w) ** 2 * d, 2 * 4 * M * C)
             ln_g, ln_b = rn((C,), f32), rn((C,), f32)
             out[f"layernorm_{lv}"] = (lambda a=a, o=o, ln_g=ln_g, ln_b=ln_b: ops.layernorm(a, ln_g, ln_b, o, 1e-5), 0,
                                      2 * 2 * M * C)
