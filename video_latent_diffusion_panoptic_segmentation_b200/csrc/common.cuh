@@ -321,8 +321,14 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank
 }
 
 // ---------------------------------------------------------------- math
-// x * sigmoid(x) with MUFU ex2 + rcp (rel. error ~1e-6, far below the bf16 rounding of every consumer)
-__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu_f(float x) {
+  // x * sigmoid(x) = h * tanh(h) + h with h = x / 2: ONE MUFU op (tanh.approx, relative error 2^-11) instead of the
+  // two of ex2 + rcp. GroupNorm + SiLU at the 48x156 level was bound by the MUFU unit (2 x 38 M ops = 18 us), not by HBM.
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 // GELU (erf form) with the Abramowitz-Stegun 7.1.26 erf (|abs err| < 2e-7 before the bf16 rounding of the result):
