@@ -308,7 +308,7 @@ def run_ours(args):
         gm = by.get("gemm", {"ms": 1e-9, "flops": 0, "n": 1})
         ach = gm["flops"] / (gm["ms"] / 1e3) / 1e12
         traffic = None  # DRAM bytes per launch of the contraction kernel, from the committed ncu capture of one forward
-        tpath = os.path.join(ROOT, "profiles", "r01f_unet_forward_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r01g_unet_forward_traffic.json")
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
             if "gemm_tc_kernel" in tj:
@@ -332,7 +332,7 @@ def run_ours(args):
                 hb["ms"] += r["ms"]
         if hb["ms"] > 0:
             gbs = hb["bytes"] / (hb["ms"] / 1e3) / 1e9
-            line["hbm_kernels"] = {"kernels": "gn_stats+gn_apply, layernorm", "achieved": gbs, "peak": hbm, "unit": "GB/s",
+            line["hbm_kernels"] = {"kernels": "gn_fused, layernorm_rows", "achieved": gbs, "peak": hbm, "unit": "GB/s",
                                    "frac": gbs / hbm, "note": "48x156-level launches (>= 38 MB), CUDA events around each launch"}
         if world == 1 and not args.no_cpu_baseline:
             try:

@@ -236,6 +236,18 @@ int ldm_pan_insert(const int32_t* sem, const int32_t* labels, int32_t target, in
 int ldm_id_mask(int32_t* x, const int32_t* a, int32_t va, const int32_t* b, int32_t vb, int32_t fill, int64_t n,
                 ldm_stream_t stream);
 
+/* Depth-aware masking of a DVPQ window (eval/eval_dvpq.py:123-145: `depth_mask = depth_gts > 0`, abs-rel error,
+ * `pred_in_depth_mask[ignored_pred_mask] = 19 * max_ins`). For every pixel of the [H, Wd] depth maps with depth_gt > 0:
+ *   rel = |depth_pred - depth_gt| / depth_gt in float64, with numpy's arithmetic of the PNG sample type -- elem_bits 8 / 16:
+ *   unsigned subtraction modulo 2^bits (np.abs is then the identity), 32: signed int32; pred[y, x] = fill where rel > thres.
+ * pred: int32 [H, pred_stride] (the window's id map, pred_stride >= Wd: only its first Wd columns are touched).
+ * depth_pred / depth_gt: the samples widened to int32 by the caller. partial_sum / partial_cnt [nblocks]: per-CTA sum of
+ * rel and number of valid pixels, added by the caller in index order (abs_rel = sum / count; the reference's np.mean is a
+ * pairwise sum -- agreement to ~1e-15 relative, not bitwise; the masking itself is exact). */
+int ldm_depth_mask_pred(int32_t* pred, int32_t pred_stride, const int32_t* depth_pred, const int32_t* depth_gt, int32_t H,
+                        int32_t Wd, int32_t elem_bits, double thres, int32_t fill, double* partial_sum,
+                        unsigned long long* partial_cnt, int32_t nblocks, ldm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

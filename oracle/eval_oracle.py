@@ -7,6 +7,7 @@ ldmseg/evaluations/cityscapes_pap_eval.py:9-249 ``CityscapesPanopticEvaluator``)
   vpq_stats            eval/eval_dvpq.py:25-101
   dvpq_aggregate       eval/eval_dvpq.py:190-210
   depth_mask_pred      eval/eval_dvpq.py:123-145
+  dvpq_window          eval/eval_dvpq.py:104-150 (pinned by tests/golden/dvpq_files.json, made by the real eval())
   CityscapesPQOracle   ldmseg/evaluations/cityscapes_pap_eval.py:64-249
 """
 import numpy as np
@@ -85,6 +86,20 @@ def depth_mask_pred(pred, depth_pred, depth_gt, depth_thres, max_ins=2 ** 20):
     sub[valid] = vals
     pred[:, :depth_pred.shape[1]] = sub
     return pred, np.mean(rel)
+
+
+def dvpq_window(pred_cat, pred_ins, gt_cat, gt_ins, depth_pred=None, depth_gt=None, depth_thres=0.0, max_ins=2 ** 20):
+    """eval_dvpq.py:104-150 on decoded arrays (lists of k [H, W] maps, the PNG sample types untouched: the uint16
+    depth arithmetic wraps exactly as in the reference). Returns (iou, tp, fn, fp, abs_rel)."""
+    pc = np.concatenate(pred_cat, axis=1)
+    pi = np.concatenate(pred_ins, axis=1)
+    pred = pc.astype(np.int32) * max_ins + pi.astype(np.int32)
+    gt = np.concatenate([c.astype(np.int32) * max_ins + i.astype(np.int32) for c, i in zip(gt_cat, gt_ins)], axis=1)
+    abs_rel = 0
+    if depth_thres > 0:
+        pred, abs_rel = depth_mask_pred(pred, np.concatenate(depth_pred, axis=1), np.concatenate(depth_gt, axis=1),
+                                        depth_thres, max_ins)
+    return vpq_stats(pred.astype(np.int64), gt.astype(np.int64), max_ins=max_ins) + (abs_rel,)
 
 
 class CityscapesPQOracle:

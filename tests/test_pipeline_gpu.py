@@ -112,6 +112,24 @@ def test_unet_eps_vs_oracle(models, shape):
     assert isinstance(tup, tuple) and torch.equal(tup[0], out.sample)  # graph replay is deterministic
 
 
+@pytest.mark.parametrize("shape,t", [((1, 48, 156), 499), ((1, 96, 312), 999)])
+def test_unet_eps_frame_sizes_vs_oracle(models, shape, t):
+    """One frame at the latent sizes of BASELINE.json: 384x1248 (configs[0..3]: 7 488 tokens at the first level) and
+    768x2496 (configs[4]: 29 952 tokens, attention-dominated). The oracle materialises the score matrices in fp32
+    (29 GB at the larger size), so one image and one timestep each."""
+    B, h, w = shape
+    x = torch.randn((B, 8, h, w), generator=torch.Generator().manual_seed(12)).to(DEV)
+    ts = torch.tensor(t, device=DEV)
+    out = models["unet"](x, ts, encoder_hidden_states=None)
+    with torch.no_grad():
+        ref = models["o_unet"](x, ts, encoder_hidden_states=None)
+    rel = _rel(out.sample, ref)
+    mx = (out.sample - ref).abs().max().item() / ref.abs().max().item()
+    del ref
+    torch.cuda.empty_cache()
+    assert out.sample.shape == (B, 4, h, w) and rel < 3e-2 and mx < 0.15, (shape, t, rel, mx)
+
+
 def test_sampler_vs_oracle(models):
     from oracle import ldmseg_oracle as LO
     from video_latent_diffusion_panoptic_segmentation_b200.ldmseg.schedulers import DDIMNoiseScheduler

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-end evidence: launch list of the bench command, per-launch DRAM traffic of one UNet forward, ncu --set full of the top kernels.
 set -u
-TAG=${1:-r01f}
+TAG=${1:-r01g}
 mkdir -p gpurun_out
 BENCH="python bench.py --steps 1 --warmup 3 --no-cpu-baseline"
 $BENCH > gpurun_out/${TAG}_bench_plain.log 2>&1 && \

@@ -551,6 +551,74 @@ extern "C" int ldm_pan_insert(const int32_t* sem, const int32_t* labels, int32_t
   return check_launch("pan_insert_kernel");
 }
 
+// Depth-aware masking of DVPQ (eval/eval_dvpq.py:123-145). One thread per depth pixel; the per-CTA (sum, count) of the
+// abs-rel error go to partial[] in a fixed order (warp shuffles, then warp 0 over the warps), the host adds the CTAs.
+__global__ void depth_mask_kernel(int32_t* __restrict__ pred, int pred_stride, const int32_t* __restrict__ dp,
+                                  const int32_t* __restrict__ dg, int H, int Wd, uint32_t wrap_mask, double thres,
+                                  int32_t fill, double* __restrict__ psum, unsigned long long* __restrict__ pcnt) {
+  __shared__ double sh_s[32];
+  __shared__ unsigned int sh_c[32];
+  const long long n = (long long)H * Wd;
+  double s = 0.0;
+  unsigned int c = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int32_t g = dg[i];
+    if (g > 0) {
+      const int32_t d = dp[i] - g;
+      // numpy: unsigned 8 / 16 bit PNG arrays subtract modulo 2^bits (np.abs is then the identity), int32 ones are signed
+      const double diff = wrap_mask ? (double)((uint32_t)d & wrap_mask) : (double)(d < 0 ? -(long long)d : (long long)d);
+      const double rel = diff / (double)g;
+      s += rel;
+      ++c;
+      if (rel > thres) {
+        const long long y = i / Wd, x = i - y * Wd;
+        pred[y * pred_stride + x] = fill;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    sh_s[warp] = s;
+    sh_c[warp] = c;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = blockDim.x >> 5;
+    s = lane < nw ? sh_s[lane] : 0.0;
+    c = lane < nw ? sh_c[lane] : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      c += __shfl_xor_sync(0xffffffffu, c, o);
+    }
+    if (lane == 0) {
+      psum[blockIdx.x] = s;
+      pcnt[blockIdx.x] = c;
+    }
+  }
+}
+
+extern "C" int ldm_depth_mask_pred(int32_t* pred, int32_t pred_stride, const int32_t* depth_pred, const int32_t* depth_gt,
+                                   int32_t H, int32_t Wd, int32_t elem_bits, double thres, int32_t fill, double* partial_sum,
+                                   unsigned long long* partial_cnt, int32_t nblocks, ldm_stream_t stream) {
+  using namespace ldm_host;
+  LDM_REQUIRE(pred && depth_pred && depth_gt && partial_sum && partial_cnt, LDM_ERR_BAD_ARG, "ldm_depth_mask_pred: null arg");
+  LDM_REQUIRE(H > 0 && Wd > 0 && pred_stride >= Wd && nblocks > 0, LDM_ERR_BAD_SHAPE,
+              "ldm_depth_mask_pred: H=%d Wd=%d pred_stride=%d nblocks=%d", H, Wd, pred_stride, nblocks);
+  LDM_REQUIRE(elem_bits == 8 || elem_bits == 16 || elem_bits == 32, LDM_ERR_BAD_ARG,
+              "ldm_depth_mask_pred: elem_bits=%d (8 / 16: unsigned PNG samples, 32: int32)", elem_bits);
+  const uint32_t wrap = elem_bits == 8 ? 0xffu : (elem_bits == 16 ? 0xffffu : 0u);
+  depth_mask_kernel<<<nblocks, 256, 0, as_stream(stream)>>>(pred, pred_stride, depth_pred, depth_gt, H, Wd, wrap, thres, fill,
+                                                          partial_sum, partial_cnt);
+  count_launch();
+  return check_launch("depth_mask_kernel");
+}
+
 extern "C" int ldm_id_mask(int32_t* x, const int32_t* a, int32_t va, const int32_t* b, int32_t vb, int32_t fill,
                            int64_t n, ldm_stream_t stream) {
   using namespace ldm_host;

@@ -300,3 +300,23 @@ def id_mask(x, a, va, b=None, vb=0, fill=-1):
     _chk(x, i32, "x"); _chk(a, i32, "a"); _chk(b, i32, "b")
     L.check(L.lib().ldm_id_mask(_p(x), _p(a), va, _p(b), vb, fill, x.numel(), _stream()), "ldm_id_mask")
     return x
+
+
+def depth_mask_pred(pred, depth_pred, depth_gt, elem_bits, thres, fill):
+    """In place on pred (int32 [H, Wp]): ids of the pixels whose abs-rel depth error exceeds thres become `fill`
+    (eval_dvpq.py:123-145). depth maps: int32 [H, Wd], Wd <= Wp. Returns abs_rel (float, mean over depth_gt > 0)."""
+    _chk(pred, i32, "pred"); _chk(depth_pred, i32, "depth_pred"); _chk(depth_gt, i32, "depth_gt")
+    H, Wd = depth_gt.shape
+    if depth_pred.shape != depth_gt.shape or pred.shape[0] != H or pred.shape[1] < Wd:
+        raise L.LdmError(f"depth_mask_pred: shapes pred={tuple(pred.shape)} depth={tuple(depth_pred.shape)}/{tuple(depth_gt.shape)}")
+    nb = 64
+    psum = torch.empty(nb, dtype=torch.float64, device=pred.device)
+    pcnt = torch.empty(nb, dtype=torch.int64, device=pred.device)
+    L.check(L.lib().ldm_depth_mask_pred(_p(pred), pred.stride(0), _p(depth_pred), _p(depth_gt), H, Wd, elem_bits, float(thres),
+                                        fill, _p(psum), _p(pcnt), nb, _stream()), "ldm_depth_mask_pred")
+    s, c = psum.cpu().numpy(), pcnt.cpu().numpy()
+    tot, n = 0.0, 0
+    for a, b in zip(s.tolist(), c.tolist()):  # fixed order
+        tot += a
+        n += b
+    return tot / n if n else float("nan")
