@@ -165,6 +165,10 @@ int ldm_gemv_bf16(const void* w, const float* bias, const float* bias2, const fl
 int ldm_conv3x3_small_cin(const float* s0, const float* s1, const float* s2, int32_t nsrc, int32_t cps, float scale,
                           const float* w, const float* bias, void* out, int32_t B, int32_t h, int32_t wd,
                           int32_t cout, ldm_stream_t stream);
+/* the same with an optional SiLU on the result: seg-AE encoder[0..1] (Conv2d + SiLU on the bit planes, vae.py:191-195) */
+int ldm_conv3x3_small_cin_act(const float* s0, const float* s1, const float* s2, int32_t nsrc, int32_t cps, float scale,
+                              const float* w, const float* bias, void* out, int32_t B, int32_t h, int32_t wd,
+                              int32_t cout, int32_t silu, ldm_stream_t stream);
 
 /* conv_out: bf16 NHWC [B,h,w,Cin] (already GroupNorm+SiLU'ed) -> conv3x3 -> f32 NCHW [B,Cout,h,w] (Cout <= 8).
  * w f32 [Cout,Cin,3,3] (unet.py:431). */

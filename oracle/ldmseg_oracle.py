@@ -101,6 +101,35 @@ class SegDecoderOracle(nn.Module):
         return x
 
 
+class SegEncoderOracle(nn.Module):
+    """encoder of GeneralVAESeg (vae.py:175-240: default topology, num_mid_blocks=0, gaussian posterior) with the
+    reference's nn.Sequential indices, so its state_dict keys are the reference's ``encoder.N.*``. ``encode`` returns the
+    moments; mean / logvar / std follow DiagonalGaussianDistribution (vae.py:385-392). Pinned bit-exactly to
+    tests/golden/seg_encoder_small.npz (made by the real class)."""
+
+    def __init__(self, in_channels=16, block_out_channels=(32, 64, 128, 256), int_channels=256, norm_num_groups=32,
+                 latent_channels=4, num_latents=2, **unused):
+        super().__init__()
+        boc = block_out_channels
+        layers = [nn.Conv2d(in_channels, boc[0], 3, padding=1), nn.SiLU()]
+        for i in range(len(boc) - 1):
+            layers += [nn.Conv2d(boc[i], boc[i], 3, padding=1), nn.Conv2d(boc[i], boc[i + 1], 3, padding=1, stride=2),
+                       nn.SiLU()]
+        layers += [nn.Conv2d(boc[-1], int_channels, 3, padding=1), nn.Identity(),
+                   nn.GroupNorm(norm_num_groups, int_channels, eps=1e-6), nn.SiLU(),
+                   nn.Conv2d(int_channels, latent_channels * num_latents, 3, padding=1)]
+        self.encoder = nn.Sequential(*layers)
+
+    def encode(self, semseg):
+        return self.encoder(semseg)
+
+    @staticmethod
+    def posterior(moments):
+        mean, logvar = torch.chunk(moments, 2, dim=1)
+        logvar = torch.clamp(logvar, -30.0, 20.0)
+        return mean, logvar, torch.exp(0.5 * logvar)
+
+
 def build_seg_decoder(seed=0, **kw):
     torch.manual_seed(seed)
     return SegDecoderOracle(**kw).eval()

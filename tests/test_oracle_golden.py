@@ -119,3 +119,23 @@ def test_merge_hand_computed():
     assert kept == [0]
     assert (cleaned[:, :5] == 0).all() and (cleaned[:, 5:] == -1).all()
     assert (pred[:, 6:] == 3).all() and (pred[:, 5] == 1).all()
+
+
+def test_seg_encoder_bit_exact_with_reference():
+    """oracle.SegEncoderOracle / SegDecoderOracle == the real GeneralVAESeg encoder, posterior and forward()."""
+    import ast
+    from oracle import ldmseg_oracle as LO
+    z = np.load(os.path.join(G, "seg_encoder_small.npz"))
+    cfg = ast.literal_eval(str(z["cfg"]))
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+    enc = LO.SegEncoderOracle(**cfg).eval()
+    enc.load_state_dict({k: v for k, v in sd.items() if k.startswith("encoder.")})
+    dec = LO.SegDecoderOracle(**cfg).eval()
+    dec.load_state_dict({k: v for k, v in sd.items() if k.startswith("decoder.")})
+    with torch.no_grad():
+        m = enc.encode(torch.from_numpy(z["bits"]))
+        mean, _, std = enc.posterior(m)
+        fwd = dec.decode(mean, interpolate=False)
+    assert np.array_equal(m.numpy(), z["moments"])
+    assert np.array_equal(mean.numpy(), z["mode"]) and np.array_equal(std.numpy(), z["std"])
+    assert np.array_equal(fwd.numpy(), z["forward"])

@@ -85,6 +85,50 @@ def test_seg_decoder_small_reference_fixture():
     assert _rel(hi.cpu(), torch.from_numpy(z["logits_hi"])) < 3e-2
 
 
+def test_seg_encoder_reference_fixture():
+    """encode / posterior / forward of the seg-AE against the real reference (tests/golden/seg_encoder_small.npz)."""
+    import ast
+    from video_latent_diffusion_panoptic_segmentation_b200.ldmseg.models import GeneralVAESeg
+    z = np.load(os.path.join(G, "seg_encoder_small.npz"))
+    cfg = ast.literal_eval(str(z["cfg"]))
+    vae = GeneralVAESeg(**cfg, device=DEV)
+    vae.load_state_dict({k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")})
+    bits = torch.from_numpy(z["bits"]).to(DEV)
+    post = vae.encode(bits).latent_dist
+    assert post.parameters.shape == z["moments"].shape
+    assert _rel(post.parameters.cpu(), torch.from_numpy(z["moments"])) < 3e-2
+    assert _rel(post.mode().cpu(), torch.from_numpy(z["mode"])) < 3e-2
+    assert _rel(post.std.cpu(), torch.from_numpy(z["std"])) < 3e-2
+    out = vae(bits, sample_posterior=False)
+    assert list(out.keys()) == ["sample", "posterior"] and out.sample.shape == z["forward"].shape
+    assert _rel(out.sample.cpu(), torch.from_numpy(z["forward"])) < 4e-2
+    smp = post.sample(generator=torch.Generator(device=DEV).manual_seed(0))
+    assert smp.shape == post.mode().shape and torch.isfinite(smp).all()
+    with pytest.raises(Exception):
+        vae.encode(bits.cpu())  # no CPU fallback
+
+
+def test_seg_encoder_frame_size_vs_oracle():
+    """The default seg-AE (base.yaml:14-33) on the bit planes of one 384x1248 frame against the fp32 oracle."""
+    from oracle import ldmseg_oracle as LO
+    from video_latent_diffusion_panoptic_segmentation_b200.ldmseg.models import GeneralVAESeg
+    kw = dict(in_channels=16, int_channels=256, out_channels=128, latent_channels=4, num_upscalers=2,
+              upscale_channels=256, norm_num_groups=32, scaling_factor=0.2)
+    torch.manual_seed(21)
+    o_enc = LO.SegEncoderOracle(**kw).eval()
+    sd = {k: v.clone() for k, v in o_enc.state_dict().items()}
+    sd.update({k: v for k, v in LO.SegDecoderOracle(**kw).state_dict().items()})
+    vae = GeneralVAESeg(**kw, device=DEV)
+    vae.load_state_dict(sd)
+    g = torch.Generator().manual_seed(22)
+    bits = ((torch.rand((1, 16, 384, 1248), generator=g) < 0.5).float() * 2 - 1).to(DEV)
+    got = vae.encode(bits).latent_dist.parameters
+    with torch.no_grad():
+        ref = o_enc.to(DEV).encode(bits)
+    assert got.shape == ref.shape == (1, 8, 48, 156)
+    assert _rel(got, ref) < 3e-2
+
+
 def test_seg_decoder_full_size_vs_oracle(models):
     zz = torch.randn((2, 4, 12, 39), generator=torch.Generator().manual_seed(3)).to(DEV)
     got = models["vae"].decode(zz)

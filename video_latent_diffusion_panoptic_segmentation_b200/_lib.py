@@ -65,6 +65,8 @@ SIGNATURES = {
     "ldm_gemv_bf16": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
     "ldm_conv3x3_small_cin": (C.c_int, [c_vp, c_vp, c_vp, c_i32, c_i32, c_f32, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32,
                                         c_i32, c_vp]),
+    "ldm_conv3x3_small_cin_act": (C.c_int, [c_vp, c_vp, c_vp, c_i32, c_i32, c_f32, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32,
+                                        c_i32, c_i32, c_vp]),
     "ldm_conv_out": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "ldm_ddim_step": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "ldm_upsample_nearest": (C.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),

@@ -89,7 +89,7 @@ constexpr int kStrip = 32;
 __global__ void conv3x3_small_cin_kernel(const float* __restrict__ s0, const float* __restrict__ s1,
                                          const float* __restrict__ s2, int nsrc, int cps, float scale,
                                          const float* __restrict__ w, const float* __restrict__ bias,
-                                         __nv_bfloat16* __restrict__ out, int B, int h, int wd, int cout) {
+                                         __nv_bfloat16* __restrict__ out, int B, int h, int wd, int cout, int silu) {
   extern __shared__ float patch[];  // [cin][3][kStrip+2]
   const int cin = nsrc * cps;
   const int strips = (wd + kStrip - 1) / kStrip;
@@ -133,7 +133,7 @@ __global__ void conv3x3_small_cin_kernel(const float* __restrict__ s0, const flo
   }
   for (int i = 0; i < kStrip; ++i) {
     const int x = x0 + i;
-    if (x < wd) out[(((long long)b * h + y) * wd + x) * cout + co] = __float2bfloat16_rn(acc[i]);
+    if (x < wd) out[(((long long)b * h + y) * wd + x) * cout + co] = __float2bfloat16_rn(silu ? silu_f(acc[i]) : acc[i]);
   }
 }
 
@@ -286,6 +286,12 @@ extern "C" int ldm_gemv_bf16(const void* w, const float* bias, const float* bias
 extern "C" int ldm_conv3x3_small_cin(const float* s0, const float* s1, const float* s2, int32_t nsrc, int32_t cps,
                                      float scale, const float* w, const float* bias, void* out, int32_t B, int32_t h,
                                      int32_t wd, int32_t cout, ldm_stream_t stream) {
+  return ldm_conv3x3_small_cin_act(s0, s1, s2, nsrc, cps, scale, w, bias, out, B, h, wd, cout, 0, stream);
+}
+
+extern "C" int ldm_conv3x3_small_cin_act(const float* s0, const float* s1, const float* s2, int32_t nsrc, int32_t cps,
+                                         float scale, const float* w, const float* bias, void* out, int32_t B, int32_t h,
+                                         int32_t wd, int32_t cout, int32_t silu, ldm_stream_t stream) {
   using namespace ldm_host;
   LDM_REQUIRE(s0 && w && out && nsrc >= 1 && nsrc <= 3 && (nsrc < 2 || s1) && (nsrc < 3 || s2), LDM_ERR_BAD_ARG,
               "ldm_conv3x3_small_cin: bad sources");
@@ -295,7 +301,7 @@ extern "C" int ldm_conv3x3_small_cin(const float* s0, const float* s1, const flo
   const int strips = (wd + kStrip - 1) / kStrip;
   const size_t shb = sizeof(float) * nsrc * cps * 3 * (kStrip + 2);
   conv3x3_small_cin_kernel<<<B * h * strips, threads, shb, as_stream(stream)>>>(
-      s0, s1, s2, nsrc, cps, scale, w, bias, reinterpret_cast<__nv_bfloat16*>(out), B, h, wd, cout);
+      s0, s1, s2, nsrc, cps, scale, w, bias, reinterpret_cast<__nv_bfloat16*>(out), B, h, wd, cout, silu);
   count_launch();
   return check_launch("conv3x3_small_cin_kernel");
 }

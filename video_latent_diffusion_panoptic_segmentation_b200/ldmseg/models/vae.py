@@ -1,4 +1,4 @@
-"""B200 host mirror of the segmentation auto-encoder ``GeneralVAESeg`` (ldmseg/models/vae.py:42-307), decoder side.
+"""B200 host mirror of the segmentation auto-encoder ``GeneralVAESeg`` (ldmseg/models/vae.py:42-307).
 
 ``decode(z, interpolate=True)`` keeps the reference signature and returns NCHW fp32 logits; internally it is
   conv3x3 4->int (few-channel kernel, fused 1/scaling_factor)            vae.py:134
@@ -9,7 +9,13 @@
   bilinear x interpolation_factor                                         vae.py:271
 The sampler's integer tail consumes the NHWC logits *before* the bilinear step (``decode_nhwc``) and fuses the
 up-sampling into the argmax kernel, so the 245 MB/frame full-resolution logits never hit HBM on that path.
-The encoder / posteriors (vae.py:175-266) are SURVEY section 8(f) rank 3 ("next") and raise NotImplementedError.
+``encode(semseg)`` (vae.py:175-266, default topology: no resize_input / skip_encoder /
+mid blocks, gaussian parametrisation) runs the bit planes through
+  conv3x3 in->c0 + SiLU (few-channel kernel)                              vae.py:191-195
+  [conv3x3 ci->ci ; conv3x3 stride 2 ci->ci+1 + SiLU] per level           vae.py:199-208  (implicit GEMM; im2col + GEMM)
+  conv3x3 c_last->int ; GroupNorm(eps 1e-6) + SiLU ; conv3x3 int->2*latent  vae.py:215-237
+and returns ``EncoderOutput(latent_dist=DiagonalGaussianDistribution)`` (vae.py:371-425). Channel counts below 64 are
+zero-padded to 64 in the packed weights (the tensor-core conv wants K blocks of 64 channels).
 """
 import torch
 
@@ -29,6 +35,48 @@ class VAEOutput(U.OutputDict):
     posterior: object
 
 
+class DiagonalGaussianDistribution:
+    """vae.py:371-425 (mean | logvar halves of the encoder's moments; clamp, activation, mode / sample / kl)."""
+
+    def __init__(self, parameters, clamp_output=False, act_fn="none"):
+        self.parameters = parameters
+        if clamp_output:
+            parameters = torch.clamp(parameters, -5.0, 5.0)
+        self.mean, self.logvar = torch.chunk(parameters, 2, dim=1)
+        self.mean = self.to_range(self.mean, act_fn)
+        self.logvar = torch.clamp(self.logvar, -30.0, 20.0)
+        self.std = torch.exp(0.5 * self.logvar)
+        self.var = torch.exp(self.logvar)
+        self.clamp_output, self.act_fn = clamp_output, act_fn
+
+    @staticmethod
+    def to_range(x, act_fn):
+        if act_fn == "sigmoid":
+            return 2 * torch.sigmoid(x) - 1
+        if act_fn == "tanh":
+            return torch.tanh(x)
+        if act_fn == "clip":
+            return torch.clamp(x, -1, 1)
+        if act_fn == "none":
+            return x
+        raise NotImplementedError
+
+    def mode(self):
+        return self.mean
+
+    def sample(self, generator=None):
+        noise = torch.randn(self.mean.shape, generator=generator, device=self.parameters.device,
+                            dtype=self.parameters.dtype)
+        return self.mean + self.std * noise
+
+    def kl(self):
+        return 0.5 * torch.sum(torch.pow(self.mean, 2) + self.var - 1.0 - self.logvar, dim=[1, 2, 3])
+
+
+def _pad64(c):
+    return (c + 63) // 64 * 64
+
+
 class GeneralVAESeg:
     def __init__(self, in_channels=3, int_channels=256, out_channels=19, block_out_channels=(32, 64, 128, 256),
                  latent_channels=4, norm_num_groups=32, scaling_factor=0.18215, pretrained_path=None, encoder=None,
@@ -41,6 +89,10 @@ class GeneralVAESeg:
         self.in_channels, self.int_channels, self.out_channels = in_channels, int_channels, out_channels
         self.latent_channels, self.norm_num_groups = latent_channels, norm_num_groups
         self.num_upscalers, self.upscale_channels = num_upscalers, upscale_channels
+        self.block_out_channels = tuple(block_out_channels)
+        self.enc_in_channels = in_channels + (3 if fuse_rgb else 0)
+        self._enc_unbuilt = ("resize_input" if resize_input else "") or ("skip_encoder" if skip_encoder else "") or \
+                            ("external encoder" if encoder is not None else "")
         self.scaling_factor = scaling_factor
         self.downsample_factor = 2 ** (len(block_out_channels) - 1)
         self.interpolation_factor = self.downsample_factor // (2 ** num_upscalers)
@@ -48,6 +100,7 @@ class GeneralVAESeg:
         self.device = torch.device(device)
         self.dtype = torch.float32
         self._sd, self._packed, self._bufs = None, None, {}
+        self._enc_packed, self._enc_bufs = None, {}
         if pretrained_path is not None:
             self.load_pretrained(pretrained_path)
 
@@ -60,6 +113,7 @@ class GeneralVAESeg:
     def load_state_dict(self, sd, strict=True):
         self._sd = {k: v.detach().to("cpu", f32) for k, v in sd.items()}
         self._packed, self._bufs = None, {}
+        self._enc_packed, self._enc_bufs = None, {}
         return "<All keys matched successfully>"
 
     def state_dict(self):
@@ -135,11 +189,98 @@ class GeneralVAESeg:
         ops.bilinear_up_nchw(logits, out, up)
         return out
 
+    # ------------------------------------------------------------------ encode (vae.py:175-266)
+    def _pack_encoder(self):
+        sd, dev, boc = self._sd, self.device, self.block_out_channels
+
+        def conv_w(name, cin_pad, cout_pad):  # [cout, cin, 3, 3] -> bf16 [cout_pad, 9 * cin_pad], tap-major / channel-minor
+            w, b = sd[name + ".weight"], sd[name + ".bias"]
+            wp = torch.zeros((cout_pad, 3, 3, cin_pad), dtype=f32)
+            wp[: w.shape[0], :, :, : w.shape[1]] = w.permute(0, 2, 3, 1)
+            bp = torch.zeros(cout_pad, dtype=f32)
+            bp[: b.shape[0]] = b
+            return wp.reshape(cout_pad, -1).contiguous().to(dev, bf16), bp.to(dev)
+
+        P = {}
+        w0, b0 = sd["encoder.0.weight"], sd["encoder.0.bias"]
+        c0p = _pad64(boc[0])
+        w0p = torch.zeros((c0p,) + tuple(w0.shape[1:]), dtype=f32)
+        w0p[: w0.shape[0]] = w0
+        b0p = torch.zeros(c0p, dtype=f32)
+        b0p[: b0.shape[0]] = b0
+        P["in_w"], P["in_b"] = ops.pack_small_cin_weight(w0p).to(dev), b0p.to(dev)
+        idx, P["down"] = 2, []
+        for i in range(len(boc) - 1):
+            cip, cop = _pad64(boc[i]), _pad64(boc[i + 1])
+            P["down"].append((conv_w(f"encoder.{idx}", cip, cip), conv_w(f"encoder.{idx + 1}", cip, cop), cip, cop))
+            idx += 3
+        P["mid"] = conv_w(f"encoder.{idx}", _pad64(boc[-1]), self.int_channels)
+        P["gn"] = (sd[f"encoder.{idx + 2}.weight"].to(dev), sd[f"encoder.{idx + 2}.bias"].to(dev))
+        P["out_w"], P["out_b"] = sd[f"encoder.{idx + 4}.weight"].contiguous().to(dev), sd[f"encoder.{idx + 4}.bias"].to(dev)
+        self._enc_packed = P
+
+    @torch.no_grad()
+    def encode_moments(self, semseg):
+        """semseg f32 NCHW [B, in_channels, H, W] on the GPU -> moments f32 NCHW [B, 2*latent, H/f, W/f]."""
+        if self._enc_unbuilt:
+            raise NotImplementedError(f"GeneralVAESeg.encode: the {self._enc_unbuilt} variant is not built")
+        if self.int_channels % 64 != 0 or 2 * self.latent_channels > 8:
+            raise NotImplementedError("GeneralVAESeg.encode: int_channels must be a multiple of 64 and 2*latent <= 8")
+        if not semseg.is_cuda:
+            raise L.LdmError("GeneralVAESeg.encode needs CUDA tensors: there is no CPU fallback")
+        if self._enc_packed is None:
+            self._pack_encoder()
+        P, dev = self._enc_packed, self.device
+        x_in = semseg.contiguous().float()
+        B, cin, H, W = x_in.shape
+        if cin != self.enc_in_channels:
+            raise L.LdmError(f"GeneralVAESeg.encode: {cin} input channels, expected {self.enc_in_channels}")
+        key = (B, H, W)
+        if key not in self._enc_bufs:
+            bufs = {"x0": torch.empty((B, H, W, P["in_b"].numel()), dtype=bf16, device=dev), "lv": []}
+            h, w = H, W
+            for (_, _, cip, cop) in P["down"]:
+                oh, ow = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+                bufs["lv"].append((torch.empty((B, h, w, cip), dtype=bf16, device=dev),
+                                   torch.empty((B * oh * ow, 9 * cip), dtype=bf16, device=dev),
+                                   torch.empty((B, oh, ow, cop), dtype=bf16, device=dev)))
+                h, w = oh, ow
+            bufs["mid"] = torch.empty((B, h, w, self.int_channels), dtype=bf16, device=dev)
+            bufs["gn"] = torch.empty_like(bufs["mid"])
+            bufs["stats"] = ops.gn_scratch(B, self.norm_num_groups, dev)
+            self._enc_bufs = {key: bufs}
+        bufs = self._enc_bufs[key]
+        x = ops.conv3x3_small_cin([x_in], P["in_w"], P["in_b"], bufs["x0"], silu=True)
+        for ((wa, ba), (wb, bb), cip, cop), (ta, col, tb) in zip(P["down"], bufs["lv"]):
+            ops.gemm(x, wa, ta, taps=9, bias=ba)
+            ops.im2col3x3_s2(ta, col)
+            ops.gemm(col, wb, tb.view(col.shape[0], cop), bias=bb, flags=L.LDM_GEMM_SILU)
+            x = tb
+        ops.gemm(x, P["mid"][0], bufs["mid"], taps=9, bias=P["mid"][1])
+        ops.groupnorm(bufs["mid"], *P["gn"], bufs["gn"], bufs["stats"], groups=self.norm_num_groups, eps=1e-6, silu=True)
+        moments = torch.empty((B, P["out_b"].numel(), x.shape[1], x.shape[2]), dtype=f32, device=dev)
+        ops.conv_out(bufs["gn"], P["out_w"], P["out_b"], moments)
+        return moments
+
     def encode(self, semseg):
-        raise NotImplementedError("seg-AE encoder is SURVEY section 8(f) rank 3 (next); only decode() is on the path")
+        moments = self.encode_moments(semseg)
+        if self.parametrization != "gaussian":
+            raise NotImplementedError(f"GeneralVAESeg.encode: parametrization {self.parametrization!r} is not built "
+                                      "(base.yaml uses 'gaussian')")
+        return EncoderOutput(latent_dist=DiagonalGaussianDistribution(moments, clamp_output=self.clamp_output,
+                                                                      act_fn=self.act_fn))
 
     def forward(self, sample, sample_posterior=True, return_dict=True, generator=None, rgb_sample=None,
                 valid_mask=None):
-        raise NotImplementedError("GeneralVAESeg.forward needs the encoder (SURVEY section 8(f) rank 3)")
+        """vae.py:274-307: encode -> sample / mode of the posterior -> (mask) -> decode without the bilinear step."""
+        x = sample if rgb_sample is None else torch.cat([sample, rgb_sample], dim=1)
+        posterior = self.encode(x).latent_dist
+        z = posterior.sample(generator=generator) if sample_posterior else posterior.mode()
+        if valid_mask is not None:
+            z = z * valid_mask[:, None]
+        dec = self.decode(z, interpolate=False)
+        if not return_dict:
+            return (dec,)
+        return VAEOutput(sample=dec, posterior=posterior)
 
     __call__ = forward

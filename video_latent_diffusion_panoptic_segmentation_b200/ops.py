@@ -157,16 +157,17 @@ def pack_small_cin_weight(w):
     return w.detach().to(f32).permute(1, 2, 3, 0).contiguous()
 
 
-def conv3x3_small_cin(srcs, w, bias, out, scale=1.0):
+def conv3x3_small_cin(srcs, w, bias, out, scale=1.0, silu=False):
     """srcs: list of 1..3 f32 NCHW [B,cps,h,w]; w f32 [len(srcs)*cps, 3, 3, cout] (pack_small_cin_weight);
-    out bf16 NHWC [B,h,w,cout]."""
+    out bf16 NHWC [B,h,w,cout]; silu: SiLU on the result."""
     for s in srcs:
         _chk(s, f32, "src")
     _chk(w, f32, "w"); _chk(bias, f32, "bias"); _chk(out, bf16, "out")
     B, cps, h, wd = srcs[0].shape
     s = list(srcs) + [None] * (3 - len(srcs))
-    L.check(L.lib().ldm_conv3x3_small_cin(_p(s[0]), _p(s[1]), _p(s[2]), len(srcs), cps, scale, _p(w), _p(bias), _p(out),
-                                          B, h, wd, w.shape[-1], _stream()), "ldm_conv3x3_small_cin")
+    L.check(L.lib().ldm_conv3x3_small_cin_act(_p(s[0]), _p(s[1]), _p(s[2]), len(srcs), cps, scale, _p(w), _p(bias),
+                                              _p(out), B, h, wd, w.shape[-1], int(silu), _stream()),
+            "ldm_conv3x3_small_cin_act")
     return out
 
 
