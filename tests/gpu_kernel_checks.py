@@ -484,6 +484,10 @@ CHECKS = {
     "gemm_geglu": check_gemm_geglu,
     "gemm_qkv_40": check_gemm_qkv,
     "gemm_qkv_160": lambda: check_gemm_qkv(1, 8, 160, 468),
+    # seq % 8 == 0: V^T leaves through the per-warp transpose (16-byte stores); image boundaries inside a warp's rows
+    "gemm_qkv_40_vec": lambda: check_gemm_qkv(2, 8, 40, 304),
+    "gemm_qkv_80_vec": lambda: check_gemm_qkv(3, 8, 80, 472),
+    "gemm_qkv_40_vec_level0": lambda: check_gemm_qkv(1, 8, 40, 7488),
     "gemm_convt": check_gemm_convt,
     "attn_40_tail": check_attention,
     "attn_40_long": lambda: check_attention(1, 2, 40, 1872),

@@ -196,6 +196,30 @@ def test_sampler_vs_oracle(models):
     assert _rel(logits, ref_logits) < 3e-2
 
 
+def test_sampler_self_condition_vs_oracle():
+    """H1 with train_kwargs.self_condition=True (trainers_ldm_cond.py:1135-1136,1152-1153): the 12-channel conv_in reads
+    x_t, rgb_latents and the previous step's pred_original_sample; cond weights random so the branch matters."""
+    from oracle import ldmseg_oracle as LO
+    from oracle import unet_oracle as UO
+    from video_latent_diffusion_panoptic_segmentation_b200.ldmseg.models import UNet
+    from video_latent_diffusion_panoptic_segmentation_b200.ldmseg.schedulers import DDIMNoiseScheduler
+    from video_latent_diffusion_panoptic_segmentation_b200.ldmseg.trainers import TrainerDiffusion
+    mk = dict(in_channels=8, init_mode_seg="copy", init_mode_image="copy", cond_channels=4, init_mode_cond="random")
+    o_unet = UO.build_unet(seed=3, model_kwargs=mk)
+    assert o_unet.conv_in.weight.shape[1] == 12
+    unet = UNet(device=DEV)
+    unet.load_state_dict(o_unet.state_dict())
+    unet.remove_cross_attention()
+    o_unet = o_unet.to(DEV)
+    B, h, w, T = 2, 16, 24, 4
+    rgb = (0.18215 * torch.randn((B, 4, h, w), generator=torch.Generator().manual_seed(1234))).to(DEV)
+    tr = TrainerDiffusion(p={"train_kwargs": {"self_condition": True}}, unet_model=unet,
+                          noise_scheduler=DDIMNoiseScheduler(**SCHED_KW), args={"gpu": 0})
+    lat = tr.sample([""] * B, num_inference_steps=T, seed=42, rgb_latents=rgb)
+    ref = LO.sample(o_unet, LO.DDIMOracle(), rgb, num_inference_steps=T, seed=42, self_condition=True)
+    assert _rel(lat, ref) < 8e-2
+
+
 def test_tail_ids_bit_exact_given_identical_logits(models):
     """H6/H7: feed the SAME fp32 logits to the CUDA tail and to the restated reference tail."""
     from oracle import ldmseg_oracle as LO

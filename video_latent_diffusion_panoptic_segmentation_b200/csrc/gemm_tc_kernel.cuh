@@ -282,6 +282,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       const long long grow = ((long long)b * p.H + y) * p.W + x;
       const int n0 = n_tile * p.block_n;
       int qkv_bi = 0, qkv_s = 0;  // QKV_SPLIT: image and token of this thread's row
+      // vectorised V^T stores need 8-token groups that never straddle an image and rows that are consecutive tokens
+      const bool qkv_vec = kEpi == kEpiQkv && (p.seq % 8 == 0) && p.bh == 1 && p.bw == kBlockM;
       if (kEpi == kEpiQkv) {
         qkv_bi = (int)(((unsigned long long)grow * p.magic_seq) >> 40);
         qkv_s = (int)(grow - (long long)qkv_bi * p.seq);
@@ -459,7 +461,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           uint32_t v[32];
           tmem_ld32(t_addr + c, v);
           tmem_ld_wait();
-          if (!valid) continue;
+          if (!valid && kEpi != kEpiQkv) continue;  // (QKV: the V transpose below needs every lane of the warp)
           const int nc = n0 + c;
           if (nc >= p.N) continue;
           float f[32];
@@ -507,9 +509,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
               const int e = cc - head * p.head_dim;
               const long long bh = (long long)qkv_bi * p.heads + head;
               if (which < 2) {
-                __nv_bfloat16* dst = (which == 0 ? p.q : p.k) + (bh * p.seq + qkv_s) * p.dpad + e;
-                store_bf16x8(dst, f + g * 8);
-              } else {
+                if (valid) {
+                  __nv_bfloat16* dst = (which == 0 ? p.q : p.k) + (bh * p.seq + qkv_s) * p.dpad + e;
+                  store_bf16x8(dst, f + g * 8);
+                }
+              } else if (qkv_vec) {
+                // V^T through a per-warp 8 x 32 transpose in shared memory: lane (c, tq) then stores channel e + c of
+                // the 8 tokens [8 tq, 8 tq + 8) of this warp's rows with ONE 16-byte store. (Eight 2-byte stores per lane
+                // at a row stride of seq_pad cost ~17 cycles each and made this epilogue 4x longer than its main loop.)
+                __nv_bfloat16* sT = reinterpret_cast<__nv_bfloat16*>(epi_smem) + (warp - 2) * 256;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) sT[j * 32 + lane] = __float2bfloat16_rn(f[g * 8 + j]);
+                __syncwarp();
+                const int cch = lane >> 2, tq = lane & 3;
+                const uint4 u = *reinterpret_cast<const uint4*>(sT + cch * 32 + tq * 8);
+                __syncwarp();
+                // the 8-token group starts at a row that is a multiple of 8 and seq % 8 == 0: one image, all valid or none
+                const int g_bi = __shfl_sync(0xffffffffu, qkv_bi, tq * 8), g_s = __shfl_sync(0xffffffffu, qkv_s, tq * 8);
+                const int g_ok = __shfl_sync(0xffffffffu, (int)valid, tq * 8);
+                if (g_ok) {
+                  __nv_bfloat16* dst =
+                      p.vt + (((long long)g_bi * p.heads + head) * p.vt_rows + e + cch) * p.seq_pad + g_s;
+                  *reinterpret_cast<uint4*>(dst) = u;
+                }
+              } else if (valid) {
                 __nv_bfloat16* dst = p.vt + (bh * p.vt_rows + e) * p.seq_pad + qkv_s;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) dst[(long long)j * p.seq_pad] = __float2bfloat16_rn(f[g * 8 + j]);
