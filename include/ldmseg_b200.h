@@ -170,6 +170,13 @@ int ldm_conv3x3_small_cin_act(const float* s0, const float* s1, const float* s2,
                               const float* w, const float* bias, void* out, int32_t B, int32_t h, int32_t wd,
                               int32_t cout, int32_t silu, ldm_stream_t stream);
 
+/* the same with an affine map of the input samples, v = x * scale + shift (two roundings): conv_in of the RGB VAE encoder
+ * fused with `images = 2. * images - 1.` (trainers_ldm_cond.py:372 -> diffusers Encoder.conv_in).
+ * The conv's zero padding is applied after the map, as in the reference. */
+int ldm_conv3x3_small_cin_affine(const float* s0, const float* s1, const float* s2, int32_t nsrc, int32_t cps,
+                                 float scale, float shift, const float* w, const float* bias, void* out, int32_t B,
+                                 int32_t h, int32_t wd, int32_t cout, int32_t silu, ldm_stream_t stream);
+
 /* conv_out: bf16 NHWC [B,h,w,Cin] (already GroupNorm+SiLU'ed) -> conv3x3 -> f32 NCHW [B,Cout,h,w] (Cout <= 8).
  * w f32 [Cout,Cin,3,3] (unet.py:431). */
 int ldm_conv_out(const void* x, const float* w, const float* bias, float* out, int32_t B, int32_t h, int32_t wd,
@@ -187,6 +194,19 @@ int ldm_upsample_nearest(const void* x, void* out, int32_t B, int32_t h, int32_t
                          int32_t ow, ldm_stream_t stream); /* F.interpolate(mode="nearest") */
 int ldm_im2col3x3_s2(const void* x, void* out, int32_t B, int32_t h, int32_t w, int32_t C, int32_t oh, int32_t ow,
                      ldm_stream_t stream); /* Downsample2D conv (stride 2, pad 1) -> [B*oh*ow, 9*C] */
+
+/* im2col of a 3x3 stride-2 conv with pad_lo (0 or 1) zero rows / columns in front of the image and one after it:
+ * pad_lo = 1 is ldm_im2col3x3_s2; pad_lo = 0 is diffusers Downsample2D(padding=0) of the RGB VAE encoder
+ * (F.pad(x, (0, 1, 0, 1)) then Conv2d(stride 2, padding 0)). out [B*oh*ow, 9*C], oh = (h + pad_lo - 2) / 2 + 1. */
+int ldm_im2col3x3_s2_pad(const void* x, void* out, int32_t B, int32_t h, int32_t w, int32_t C, int32_t oh, int32_t ow,
+                         int32_t pad_lo, ldm_stream_t stream);
+
+/* Row softmax of an unfused attention: p[r, c] = softmax_c(scale * s[r, c]) for c < cols, fp32 math, bf16 result.
+ * s f32 [rows, ld_s]; p bf16 [rows, ld_p] (columns >= cols are not written). Replaces the softmax of diffusers
+ * Attention in the RGB VAE mid block (one head of 512 channels: too wide for the fused flash kernels, whose O
+ * accumulator lives in TMEM), between two ldm_gemm_bf16 calls (Q K^T with LDM_GEMM_OUT_F32, then P V). */
+int ldm_softmax_rows(const float* s, void* p, int64_t rows, int32_t cols, int64_t ld_s, int64_t ld_p, float scale,
+                     ldm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Integer tail.
@@ -206,6 +226,10 @@ int ldm_bilinear_up_nchw(const float* logits, float* out, int32_t B, int32_t h, 
  * (trainers_ldm_cond.py:1264-1269), crop_padding (:1175-1181,1276) and the resize to meta.im_size (:1279-1284). */
 int ldm_resize_bilinear_nhwc(const float* in, float* out, int32_t B, int32_t h, int32_t w, int32_t C, int32_t y0,
                              int32_t x0, int32_t ch, int32_t cw, int32_t oh, int32_t ow, ldm_stream_t stream);
+/* The same arithmetic on planar f32 maps [P, h, w] -> [P, oh, ow] (NCHW tensors with P = B*C): the image / latent
+ * resizes of encode_inputs (trainers_ldm_cond.py:368-369,382-393). */
+int ldm_resize_bilinear_planar(const float* in, float* out, int32_t P, int32_t h, int32_t w, int32_t oh, int32_t ow,
+                               ldm_stream_t stream);
 /* Panoptic merge (trainers_ldm_cond.py:1303-1325): for every class c, keep[c] = count[c] >= count_th and
  * c != ignore_label and not (count[c] / over[c] < overlap_th) (float64 ratio as numpy computes it); then
  * cleaned[i] = keep[ids[i]] ? ids[i] : -1.  counts is the [B,2,C] array written by ldm_logits_to_ids. */

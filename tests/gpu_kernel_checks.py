@@ -198,6 +198,60 @@ def check_upsample_im2col():
     return {"name": "upsample/im2col", "bit_exact": True}
 
 
+def check_vae_helpers():
+    """Kernels added for the RGB VAE encoder: affine few-channel conv, pad-(0,1) stride-2 im2col, row softmax, planar
+    bilinear resize, and the unfused attention chain S = Q K^T -> softmax -> P V built from them."""
+    B, h, w, cout = 2, 10, 37, 128
+    img = torch.rand((B, 3, h, w), generator=_gen(70)).to(DEV)
+    wt, bias = _randn((cout, 3, 3, 3), 71, 0.2), _randn((cout,), 72)
+    out = _empty((B, h, w, cout), dtype=bf16, device=DEV)
+    ops.conv3x3_small_cin([img], ops.pack_small_cin_weight(wt), bias, out, scale=2.0, shift=-1.0)
+    ref = F.conv2d(2. * img - 1., wt, bias, padding=1).permute(0, 2, 3, 1)
+    r = _stats(out, ref, "conv3x3_small_cin(3->128, 2x-1)", 2e-2, 1e-2)
+    # Downsample2D(padding=0): F.pad(x, (0, 1, 0, 1)) + unfold(stride 2, no padding); even and odd extents
+    for (hh, ww) in ((12, 38), (11, 39)):
+        C = 64
+        x3 = _randn((B, hh, ww, C), 73, dtype=bf16)
+        oh, ow = (hh - 2) // 2 + 1, (ww - 2) // 2 + 1
+        col = _empty((B * oh * ow, 9 * C), dtype=bf16, device=DEV)
+        ops.im2col3x3_s2(x3, col, pad_lo=0)
+        unf = F.unfold(F.pad(x3.float().permute(0, 3, 1, 2), (0, 1, 0, 1)), 3, padding=0, stride=2)
+        assert unf.shape[-1] == oh * ow
+        unf = unf.view(B, C, 9, oh * ow).permute(0, 3, 2, 1).reshape(B * oh * ow, 9 * C)
+        assert torch.equal(col.float(), unf), "im2col3x3_s2 pad_lo=0 mismatch"
+    # row softmax (vector and scalar paths)
+    for (rows, cols) in ((100, 7488), (33, 333)):
+        sc = _randn((rows, cols), 74, 6.0)
+        pr = _empty((rows, cols), dtype=bf16, device=DEV)
+        ops.softmax_rows(sc, pr, 512 ** -0.5)
+        ref_p = torch.softmax(sc * 512 ** -0.5, dim=-1)
+        _stats(pr, ref_p, f"softmax_rows {rows}x{cols}", 1e-5, 1e-2)
+    # planar bilinear resize against F.interpolate (same fp32 formulation)
+    xin = _randn((2, 3, 21, 50), 75)
+    for size in ((16, 32), (48, 156), (21, 50)):
+        o = _empty((2, 3) + size, dtype=torch.float32, device=DEV)
+        ops.resize_bilinear_planar(xin, o)
+        ref_r = F.interpolate(xin, size=size, mode="bilinear", align_corners=False)
+        _stats(o, ref_r, f"resize_bilinear_planar {size}", 2e-6, 1e-6)
+    # unfused single-head attention, d = 512: V^T by a role-swapped GEMM, fp32 scores, softmax, P V
+    seq, d = 160, 512
+    xq, xk, xv = _randn((seq, d), 76, dtype=bf16), _randn((seq, d), 77, dtype=bf16), _randn((seq, d), 78, dtype=bf16)
+    wv = _randn((d, d), 79, d ** -0.5, dtype=bf16)
+    vt = _empty((d, seq), dtype=bf16, device=DEV)
+    ops.gemm(wv, xv, vt)
+    sc = _empty((seq, seq), dtype=torch.float32, device=DEV)
+    ops.gemm(xq, xk, sc, flags=L.LDM_GEMM_OUT_F32)
+    pr = _empty((seq, seq), dtype=bf16, device=DEV)
+    ops.softmax_rows(sc, pr, d ** -0.5)
+    o = _empty((seq, d), dtype=bf16, device=DEV)
+    ops.gemm(pr, vt, o)
+    v_ref = xv.float() @ wv.float().t()
+    ref_o = torch.softmax(xq.float() @ xk.float().t() * d ** -0.5, dim=-1) @ v_ref
+    _stats(vt, v_ref.t(), "V^T by swapped GEMM", 3e-2, 1e-2)
+    _stats(o, ref_o, "unfused attention d=512", 3e-2, 2e-2)
+    return r
+
+
 # ----------------------------------------------------------------------------------------------------------- GEMM
 def _gemm_ref(a, w, bias=None, residual=None):
     ref = a.float() @ w.float().t()
@@ -471,6 +525,7 @@ CHECKS = {
     "conv_out": check_conv_out,
     "gemm_conv_out_nchw": check_gemm_conv_out_nchw,
     "upsample_im2col": check_upsample_im2col,
+    "vae_helpers": check_vae_helpers,
     "gemm_tiny": check_gemm_tiny,
     "gemm_plain_320": check_gemm_plain,
     "gemm_plain_f32_k1280": lambda: check_gemm_plain(777, 1280, 1280, f32out=True),

@@ -220,6 +220,58 @@ def test_sampler_self_condition_vs_oracle():
     assert _rel(lat, ref) < 8e-2
 
 
+@pytest.fixture(scope="module")
+def vae_image():
+    from oracle import vae_image_oracle as VO
+    from video_latent_diffusion_panoptic_segmentation_b200.ldmseg.models import GeneralVAEImage
+    o = VO.build_vae_image(seed=5)
+    g = torch.Generator().manual_seed(11)
+    sd = o.state_dict()
+    for k in sd:  # non-trivial norm affine parameters and biases
+        if sd[k].dim() == 1:
+            sd[k] = sd[k] + 0.1 * torch.randn(sd[k].shape, generator=g)
+    o.load_state_dict(sd)
+    assert sum(p.numel() for p in o.parameters()) == 34163664  # SD-1.4 VAE encoder + quant_conv
+    m = GeneralVAEImage.from_pretrained(state_dict=sd, device=DEV)
+    m.set_scaling_factor(0.18215)
+    return dict(o=o.to(DEV), m=m)
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 128), (1, 384, 1248)])
+def test_vae_image_encoder_vs_oracle(vae_image, shape):
+    """moments of the RGB VAE encoder (+ quant_conv) against the restated diffusers AutoencoderKL,
+    at a small size and at the 384x1248 frame size (7 488-token single-head attention in the mid block)."""
+    B, H, W = shape
+    x = torch.rand((B, 3, H, W), generator=torch.Generator().manual_seed(21)).to(DEV)
+    xin = 2. * x - 1.
+    with torch.no_grad():
+        ref = vae_image["o"].moments(xin)
+    got = vae_image["m"].encode_moments(xin)
+    assert got.shape == ref.shape == (B, 8, H // 8, W // 8) and got.dtype == torch.float32
+    assert _rel(got, ref) < 3e-2, _rel(got, ref)
+    dist = vae_image["m"].encode(xin).latent_dist
+    assert torch.equal(dist.mode(), got[:, :4])
+    assert dist.sample().shape == (B, 4, H // 8, W // 8)
+    # the fused affine map of encode_inputs gives the same moments as the explicit 2x - 1
+    got2 = vae_image["m"].encode_moments(x, scale=2.0, shift=-1.0)
+    assert torch.equal(got2, got)
+
+
+def test_encode_inputs_vs_oracle(vae_image):
+    """trainers_ldm_cond.py:336-396: resize of the image, 2x - 1, mode of the posterior, resize of the latents, scaling."""
+    from oracle import vae_image_oracle as VO
+    from video_latent_diffusion_panoptic_segmentation_b200.ldmseg.trainers import TrainerDiffusion
+    x = torch.rand((2, 3, 96, 200), generator=torch.Generator().manual_seed(22)).to(DEV)
+    tr = TrainerDiffusion(p={"latent_size": (6, 20)}, vae_image=vae_image["m"], args={"gpu": 0})
+    lat, mean = tr.encode_inputs(x, resize=(64, 128))
+    ref, ref_mean = VO.encode_inputs(vae_image["o"], x, resize=(64, 128), latent_size=(6, 20))
+    assert lat.shape == ref.shape == (2, 4, 6, 20)
+    assert _rel(lat, ref) < 3e-2 and torch.equal(lat, mean)
+    lat2, _ = tr.encode_inputs(x[:, :, :64, :128].contiguous(), resize=None)  # no resize at all
+    ref2, _ = VO.encode_inputs(vae_image["o"], x[:, :, :64, :128])
+    assert lat2.shape == (2, 4, 8, 16) and _rel(lat2, ref2) < 3e-2
+
+
 def test_tail_ids_bit_exact_given_identical_logits(models):
     """H6/H7: feed the SAME fp32 logits to the CUDA tail and to the restated reference tail."""
     from oracle import ldmseg_oracle as LO

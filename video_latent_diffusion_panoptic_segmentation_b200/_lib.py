@@ -67,6 +67,11 @@ SIGNATURES = {
                                         c_i32, c_vp]),
     "ldm_conv3x3_small_cin_act": (C.c_int, [c_vp, c_vp, c_vp, c_i32, c_i32, c_f32, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32,
                                         c_i32, c_i32, c_vp]),
+    "ldm_conv3x3_small_cin_affine": (C.c_int, [c_vp, c_vp, c_vp, c_i32, c_i32, c_f32, c_f32, c_vp, c_vp, c_vp, c_i32, c_i32,
+                                               c_i32, c_i32, c_i32, c_vp]),
+    "ldm_im2col3x3_s2_pad": (C.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    "ldm_softmax_rows": (C.c_int, [c_vp, c_vp, c_i64, c_i32, c_i64, c_i64, c_f32, c_vp]),
+    "ldm_resize_bilinear_planar": (C.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "ldm_conv_out": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "ldm_ddim_step": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "ldm_upsample_nearest": (C.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),

@@ -87,7 +87,7 @@ __global__ void gemv_bf16_kernel(const __nv_bfloat16* __restrict__ w, const floa
 // strip of pixels in one image row; the input patch is staged in shared memory (broadcast reads).
 constexpr int kStrip = 32;
 __global__ void conv3x3_small_cin_kernel(const float* __restrict__ s0, const float* __restrict__ s1,
-                                         const float* __restrict__ s2, int nsrc, int cps, float scale,
+                                         const float* __restrict__ s2, int nsrc, int cps, float scale, float shift,
                                          const float* __restrict__ w, const float* __restrict__ bias,
                                          __nv_bfloat16* __restrict__ out, int B, int h, int wd, int cout, int silu) {
   extern __shared__ float patch[];  // [cin][3][kStrip+2]
@@ -108,7 +108,8 @@ __global__ void conv3x3_small_cin_kernel(const float* __restrict__ s0, const flo
     if (yy >= 0 && yy < h && xx >= 0 && xx < wd) {
       const int si = c / cps, cc = c % cps;
       const float* src = si == 0 ? s0 : (si == 1 ? s1 : s2);
-      v = __fmul_rn(src[(((long long)b * cps + cc) * h + yy) * wd + xx], scale);
+      // (two roundings, as `2. * images - 1.` of encode_inputs; the conv's zero padding stays zero)
+      v = __fadd_rn(__fmul_rn(src[(((long long)b * cps + cc) * h + yy) * wd + xx], scale), shift);
     }
     patch[i] = v;
   }
@@ -214,7 +215,7 @@ __global__ void upsample_nearest_kernel(const __nv_bfloat16* __restrict__ x, __n
 
 // ---------------------------------------------------------------- im2col for the stride-2 Downsample2D conv
 __global__ void im2col3x3_s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int h,
-                                    int w, int C, int oh, int ow) {
+                                    int w, int C, int oh, int ow, int pad) {
   const int vpp = C / 8;
   const long long total = (long long)B * oh * ow * 9 * vpp;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -227,7 +228,7 @@ __global__ void im2col3x3_s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bf
     p /= ow;
     const int oy = (int)(p % oh);
     const int b = (int)(p / oh);
-    const int sy = 2 * oy + t / 3 - 1, sx = 2 * ox + t % 3 - 1;
+    const int sy = 2 * oy + t / 3 - pad, sx = 2 * ox + t % 3 - pad;
     uint4 u = make_uint4(0, 0, 0, 0);
     if (sy >= 0 && sy < h && sx >= 0 && sx < w)
       u = __ldg(reinterpret_cast<const uint4*>(x + (((long long)b * h + sy) * w + sx) * C) + v);
@@ -292,6 +293,13 @@ extern "C" int ldm_conv3x3_small_cin(const float* s0, const float* s1, const flo
 extern "C" int ldm_conv3x3_small_cin_act(const float* s0, const float* s1, const float* s2, int32_t nsrc, int32_t cps,
                                          float scale, const float* w, const float* bias, void* out, int32_t B, int32_t h,
                                          int32_t wd, int32_t cout, int32_t silu, ldm_stream_t stream) {
+  return ldm_conv3x3_small_cin_affine(s0, s1, s2, nsrc, cps, scale, 0.f, w, bias, out, B, h, wd, cout, silu, stream);
+}
+
+extern "C" int ldm_conv3x3_small_cin_affine(const float* s0, const float* s1, const float* s2, int32_t nsrc,
+                                            int32_t cps, float scale, float shift, const float* w, const float* bias,
+                                            void* out, int32_t B, int32_t h, int32_t wd, int32_t cout, int32_t silu,
+                                            ldm_stream_t stream) {
   using namespace ldm_host;
   LDM_REQUIRE(s0 && w && out && nsrc >= 1 && nsrc <= 3 && (nsrc < 2 || s1) && (nsrc < 3 || s2), LDM_ERR_BAD_ARG,
               "ldm_conv3x3_small_cin: bad sources");
@@ -301,7 +309,7 @@ extern "C" int ldm_conv3x3_small_cin_act(const float* s0, const float* s1, const
   const int strips = (wd + kStrip - 1) / kStrip;
   const size_t shb = sizeof(float) * nsrc * cps * 3 * (kStrip + 2);
   conv3x3_small_cin_kernel<<<B * h * strips, threads, shb, as_stream(stream)>>>(
-      s0, s1, s2, nsrc, cps, scale, w, bias, reinterpret_cast<__nv_bfloat16*>(out), B, h, wd, cout, silu);
+      s0, s1, s2, nsrc, cps, scale, shift, w, bias, reinterpret_cast<__nv_bfloat16*>(out), B, h, wd, cout, silu);
   count_launch();
   return check_launch("conv3x3_small_cin_kernel");
 }
@@ -342,13 +350,21 @@ extern "C" int ldm_upsample_nearest(const void* x, void* out, int32_t B, int32_t
 
 extern "C" int ldm_im2col3x3_s2(const void* x, void* out, int32_t B, int32_t h, int32_t w, int32_t C, int32_t oh,
                                 int32_t ow, ldm_stream_t stream) {
+  return ldm_im2col3x3_s2_pad(x, out, B, h, w, C, oh, ow, 1, stream);
+}
+
+extern "C" int ldm_im2col3x3_s2_pad(const void* x, void* out, int32_t B, int32_t h, int32_t w, int32_t C, int32_t oh,
+                                    int32_t ow, int32_t pad_lo, ldm_stream_t stream) {
   using namespace ldm_host;
-  LDM_REQUIRE(x && out && C % 8 == 0 && B > 0, LDM_ERR_BAD_ARG, "ldm_im2col3x3_s2: bad arg");
-  LDM_REQUIRE(oh == (h - 1) / 2 + 1 && ow == (w - 1) / 2 + 1, LDM_ERR_BAD_SHAPE,
-              "ldm_im2col3x3_s2: output %dx%d does not match stride-2 pad-1 conv of %dx%d", oh, ow, h, w);
+  LDM_REQUIRE(x && out && C % 8 == 0 && B > 0 && (pad_lo == 0 || pad_lo == 1), LDM_ERR_BAD_ARG,
+              "ldm_im2col3x3_s2: bad arg");
+  // rows / columns before the image: pad_lo; after it: 1 (conv pad 1, or F.pad(x, (0, 1, 0, 1)) in front of a pad-0 conv)
+  LDM_REQUIRE(oh == (h + pad_lo - 2) / 2 + 1 && ow == (w + pad_lo - 2) / 2 + 1, LDM_ERR_BAD_SHAPE,
+              "ldm_im2col3x3_s2: output %dx%d does not match the stride-2 conv of %dx%d (pad %d before, 1 after)", oh, ow,
+              h, w, pad_lo);
   const long long total = (long long)B * oh * ow * 9 * (C / 8);
   im2col3x3_s2_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(out), B, h, w, C, oh, ow);
+      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(out), B, h, w, C, oh, ow, pad_lo);
   count_launch();
   return check_launch("im2col3x3_s2_kernel");
 }

@@ -378,6 +378,66 @@ static int launch_layernorm_rows(const void* x, const float* gamma, const float*
   return ldm_host::check_launch("layernorm_rows_kernel");
 }
 
+// Row softmax of the unfused attention (RGB VAE mid block, one 512-wide head): one CTA per row, three sweeps over the
+// row (maximum, sum of exponentials, normalised bf16 result); sweeps two and three hit L1 / L2. fp32 throughout, exp2 of
+// log2(e)-scaled differences like the fused kernels.
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ p, int cols, long long ld_s, long long ld_p,
+                    float scale) {
+  __shared__ float red[8];
+  const float* row = s + (long long)blockIdx.x * ld_s;
+  __nv_bfloat16* dst = p + (long long)blockIdx.x * ld_p;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const bool vec = (cols % 4 == 0) && (ld_s % 4 == 0) && (ld_p % 4 == 0);
+  float m = -INFINITY;
+  if (vec) {
+    for (int c = tid * 4; c < cols; c += 1024) {
+      const float4 v = *reinterpret_cast<const float4*>(row + c);
+      m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+    }
+  } else {
+    for (int c = tid; c < cols; c += 256) m = fmaxf(m, row[c]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) red[wid] = m;
+  __syncthreads();
+  m = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+  __syncthreads();
+  // scale > 0: max(scale * s) = scale * max(s)
+  const float k = scale * 1.4426950408889634f;
+  const float mk = m * k;
+  float sum = 0.f;
+  if (vec) {
+    for (int c = tid * 4; c < cols; c += 1024) {
+      const float4 v = *reinterpret_cast<const float4*>(row + c);
+      sum += exp2f(fmaf(v.x, k, -mk)) + exp2f(fmaf(v.y, k, -mk)) + exp2f(fmaf(v.z, k, -mk)) + exp2f(fmaf(v.w, k, -mk));
+    }
+  } else {
+    for (int c = tid; c < cols; c += 256) sum += exp2f(fmaf(row[c], k, -mk));
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) red[wid] = sum;
+  __syncthreads();
+  sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sum += red[i];
+  const float inv = 1.f / sum;
+  if (vec) {
+    for (int c = tid * 4; c < cols; c += 1024) {
+      const float4 v = *reinterpret_cast<const float4*>(row + c);
+      uint2 o;
+      o.x = pack_bf16(exp2f(fmaf(v.x, k, -mk)) * inv, exp2f(fmaf(v.y, k, -mk)) * inv);
+      o.y = pack_bf16(exp2f(fmaf(v.z, k, -mk)) * inv, exp2f(fmaf(v.w, k, -mk)) * inv);
+      *reinterpret_cast<uint2*>(dst + c) = o;
+    }
+  } else {
+    for (int c = tid; c < cols; c += 256) dst[c] = __float2bfloat16_rn(exp2f(fmaf(row[c], k, -mk)) * inv);
+  }
+}
+
 }  // namespace
 
 static int gn_chunks(int B, int HW, int ppb) {
@@ -485,4 +545,15 @@ extern "C" int ldm_layernorm(const void* x, const float* gamma, const float* bet
                                                              reinterpret_cast<__nv_bfloat16*>(out), rows, C, eps);
   count_launch();
   return check_launch("layernorm_kernel");
+}
+
+extern "C" int ldm_softmax_rows(const float* s, void* p, int64_t rows, int32_t cols, int64_t ld_s, int64_t ld_p,
+                                float scale, ldm_stream_t stream) {
+  using namespace ldm_host;
+  LDM_REQUIRE(s && p && rows > 0 && rows < (1LL << 31) && cols > 0 && ld_s >= cols && ld_p >= cols && scale > 0.f,
+              LDM_ERR_BAD_ARG, "ldm_softmax_rows: bad arg (rows=%lld cols=%d)", (long long)rows, cols);
+  softmax_rows_kernel<<<(unsigned int)rows, 256, 0, as_stream(stream)>>>(s, reinterpret_cast<__nv_bfloat16*>(p), cols,
+                                                                        (long long)ld_s, (long long)ld_p, scale);
+  count_launch();
+  return check_launch("softmax_rows_kernel");
 }

@@ -212,6 +212,25 @@ __global__ void resize_bilinear_nhwc_kernel(const float* __restrict__ in, float*
   }
 }
 
+// The same resize on planar maps [P, h, w] (NCHW images / latents of encode_inputs, trainers_ldm_cond.py:368-393).
+__global__ void resize_bilinear_planar_kernel(const float* __restrict__ in, float* __restrict__ out, int P, int h, int w,
+                                              int oh, int ow) {
+  const float sy = (float)h / (float)oh, sx = (float)w / (float)ow;
+  const long long total = (long long)P * oh * ow;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % ow);
+    long long t = i / ow;
+    const int oy = (int)(t % oh);
+    const long long pl = t / oh;
+    const Axis ay = axis_scaled(oy, h, sy), ax = axis_scaled(ox, w, sx);
+    const float* img = in + pl * h * w;
+    const float a = __ldg(img + (long long)ay.i0 * w + ax.i0), b = __ldg(img + (long long)ay.i0 * w + ax.i1);
+    const float c = __ldg(img + (long long)ay.i1 * w + ax.i0), d = __ldg(img + (long long)ay.i1 * w + ax.i1);
+    out[i] = lerp2(lerp2(a, ax.w0, b, ax.w1), ay.w0, lerp2(c, ax.w0, d, ax.w1), ay.w1);
+  }
+}
+
 // Merge filter (trainers_ldm_cond.py:1307-1325). counts = [B][2][C] (argmax area, sigmoid>=th area).
 __global__ void segment_filter_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ counts,
                                       int32_t* __restrict__ cleaned, long long hw, int C, int count_th,
@@ -466,6 +485,17 @@ extern "C" int ldm_resize_bilinear_nhwc(const float* in, float* out, int32_t B, 
                                                                                 ow);
   count_launch();
   return check_launch("resize_bilinear_nhwc_kernel");
+}
+
+extern "C" int ldm_resize_bilinear_planar(const float* in, float* out, int32_t P, int32_t h, int32_t w, int32_t oh,
+                                          int32_t ow, ldm_stream_t stream) {
+  using namespace ldm_host;
+  LDM_REQUIRE(in && out && P > 0 && h > 0 && w > 0 && oh > 0 && ow > 0, LDM_ERR_BAD_ARG,
+              "ldm_resize_bilinear_planar: bad arg");
+  const long long total = (long long)P * oh * ow;
+  resize_bilinear_planar_kernel<<<grid1d(total, 256), 256, 0, as_stream(stream)>>>(in, out, P, h, w, oh, ow);
+  count_launch();
+  return check_launch("resize_bilinear_planar_kernel");
 }
 
 extern "C" int ldm_segment_filter(const int32_t* ids, const int32_t* counts, int32_t* cleaned, int32_t B, int64_t hw,

@@ -55,6 +55,42 @@ class TrainerDiffusion:
             self.args["gpu"])
         self._loop = {}
 
+    # ------------------------------------------------------------------ encode_inputs (:336-396)
+    @torch.no_grad()
+    def encode_inputs(self, images, sample_posterior=False, encode_func=None, scaling_factor=None, resize=(192, 640),
+                      weight_dtype=None):
+        """Images [B,3,H,W] in [0,1] -> (latents, latents_mean), both [B,4,h,w] f32 times the scaling factor:
+        optional bilinear resize of the image, ``2 * images - 1`` (fused into the VAE's conv_in), ``encode(...)
+        .latent_dist.mode()`` (or ``.sample()``), optional bilinear resize of the latents to ``self.latent_size``
+        (an int as in the reference, or an (h, w) pair: SURVEY fact 7)."""
+        own = encode_func is None or getattr(encode_func, "__self__", None) is self.vae_image
+        if own and self.vae_image is None:
+            raise L.LdmError("encode_inputs: no vae_image was given to the trainer")
+        if scaling_factor is None:
+            scaling_factor = self.vae_image.scaling_factor
+        if not images.is_cuda:
+            raise L.LdmError("encode_inputs needs CUDA tensors: there is no CPU fallback")
+        images = images.contiguous().float()
+        if resize is not None and tuple(images.shape[-2:]) != tuple(resize):
+            resized = torch.empty(images.shape[:2] + tuple(resize), dtype=f32, device=images.device)
+            images = ops.resize_bilinear_planar(images, resized)
+        if own:
+            from ..models.vae import DiagonalGaussianDistribution
+            latent_dist = DiagonalGaussianDistribution(self.vae_image.encode_moments(images, scale=2.0, shift=-1.0))
+        else:
+            latent_dist = encode_func(2. * images - 1.).latent_dist
+        latents_mean = latent_dist.mode()
+        latents = latent_dist.sample() if sample_posterior else latents_mean.clone()
+        if resize is not None:
+            ls = self.latent_size
+            size = (int(ls), int(ls)) if isinstance(ls, int) else tuple(int(v) for v in ls)
+            if tuple(latents.shape[-2:]) != size:
+                def rs(t):
+                    out = torch.empty(t.shape[:2] + size, dtype=f32, device=t.device)
+                    return ops.resize_bilinear_planar(t.contiguous().float(), out)
+                latents, latents_mean = rs(latents), rs(latents_mean)
+        return latents * scaling_factor, latents_mean * scaling_factor
+
     # ------------------------------------------------------------------ sample (:1048-1173)
     def _loop_state(self, B, h, w):
         """Static buffers + UNet plan for the DDIM loop at this shape (built once, reused for every batch)."""
@@ -214,8 +250,8 @@ class TrainerDiffusion:
     @torch.no_grad()
     def compute_pq(self, num_inference_steps=50, guidance_scale=7.5, seed=None, threshold_output=True,
                    save_images=False, max_iter=None, dataloader=None, threshold_mode="max", save_model=False):
-        """`dataloader` yields dicts with 'rgb_latents' [B,4,h,w] (the RGB-VAE encode is the step before this path,
-        SURVEY section 8(f) rank 1), 'semseg' ground-truth labels ([B,H,W], or a list of per-image [h_i,w_i] maps at
+        """`dataloader` yields dicts with 'rgb_latents' [B,4,h,w], or 'image' [B,3,H,W] in [0,1] that goes through the
+        RGB VAE encoder first (:1234-1239), 'semseg' ground-truth labels ([B,H,W], or a list of per-image [h_i,w_i] maps at
         meta.im_size), optional 'mask' [B,Hrgb,Wrgb] padding masks (their size is the RGB input size) and 'meta'
         (per image {'im_size': (h_i, w_i)}). When every resize / crop of :1264-1284 is the identity the fused tail runs;
         otherwise the logits are resized, cropped and resized again as the reference does."""
@@ -232,7 +268,12 @@ class TrainerDiffusion:
         scheduler.move_timesteps_to(self.device)
         all_cleaned = []
         for batch_idx, data in enumerate(dataloader):
-            rgb_latents = data["rgb_latents"].to(self.device)
+            if "rgb_latents" in data:
+                rgb_latents = data["rgb_latents"].to(self.device)
+            else:  # :1234-1239: frames go through the RGB VAE encoder first
+                rgb_latents, _ = self.encode_inputs(data["image"].to(self.device), encode_func=self.vae_image.encode,
+                                                    scaling_factor=self.vae_image.scaling_factor,
+                                                    resize=p_get(self.p, "rgb_size"))
             gt_semseg = data["semseg"]  # [B,H,W] tensor, or a list of [h_i,w_i] tensors (original image sizes)
             gt_semseg = ([g.to(self.device) for g in gt_semseg] if isinstance(gt_semseg, (list, tuple))
                          else gt_semseg.to(self.device))
@@ -289,6 +330,16 @@ class TrainerDiffusion:
         if is_dist_avail_and_initialized():
             torch.distributed.barrier()
         return self.last_results
+
+
+def p_get(p, key):
+    """`self.rgb_size` of the reference trainer (:159): p['transformation_kwargs']['size_rgb'], an int that
+    F.interpolate takes for both dims (:369), or an (h, w) pair here; None = no resize. p['rgb_size'] overrides."""
+    if key in p:
+        size = p[key]
+    else:
+        size = p.get("transformation_kwargs", {}).get("size_rgb") if key == "rgb_size" else None
+    return (size, size) if isinstance(size, int) else size
 
 
 def reduce_evaluator_(evaluator, device):

@@ -157,17 +157,17 @@ def pack_small_cin_weight(w):
     return w.detach().to(f32).permute(1, 2, 3, 0).contiguous()
 
 
-def conv3x3_small_cin(srcs, w, bias, out, scale=1.0, silu=False):
-    """srcs: list of 1..3 f32 NCHW [B,cps,h,w]; w f32 [len(srcs)*cps, 3, 3, cout] (pack_small_cin_weight);
-    out bf16 NHWC [B,h,w,cout]; silu: SiLU on the result."""
+def conv3x3_small_cin(srcs, w, bias, out, scale=1.0, silu=False, shift=0.0):
+    """srcs: list of 1..3 f32 NCHW [B,cps,h,w], mapped to x*scale + shift on the fly; w f32 [len(srcs)*cps, 3, 3, cout]
+    (pack_small_cin_weight); out bf16 NHWC [B,h,w,cout]; silu: SiLU on the result."""
     for s in srcs:
         _chk(s, f32, "src")
     _chk(w, f32, "w"); _chk(bias, f32, "bias"); _chk(out, bf16, "out")
     B, cps, h, wd = srcs[0].shape
     s = list(srcs) + [None] * (3 - len(srcs))
-    L.check(L.lib().ldm_conv3x3_small_cin_act(_p(s[0]), _p(s[1]), _p(s[2]), len(srcs), cps, scale, _p(w), _p(bias),
-                                              _p(out), B, h, wd, w.shape[-1], int(silu), _stream()),
-            "ldm_conv3x3_small_cin_act")
+    L.check(L.lib().ldm_conv3x3_small_cin_affine(_p(s[0]), _p(s[1]), _p(s[2]), len(srcs), cps, scale, shift, _p(w),
+                                                 _p(bias), _p(out), B, h, wd, w.shape[-1], int(silu), _stream()),
+            "ldm_conv3x3_small_cin_affine")
     return out
 
 
@@ -195,11 +195,32 @@ def upsample_nearest(x, out):
     return out
 
 
-def im2col3x3_s2(x, out):
+def im2col3x3_s2(x, out, pad_lo=1):
+    """pad_lo = 1: Conv2d(stride 2, padding 1); pad_lo = 0: F.pad(x, (0, 1, 0, 1)) + Conv2d(stride 2, padding 0)."""
     _chk(x, bf16, "x"); _chk(out, bf16, "out")
     B, h, w, Cc = x.shape
-    oh, ow = (h - 1) // 2 + 1, (w - 1) // 2 + 1
-    L.check(L.lib().ldm_im2col3x3_s2(_p(x), _p(out), B, h, w, Cc, oh, ow, _stream()), "ldm_im2col3x3_s2")
+    oh, ow = (h + pad_lo - 2) // 2 + 1, (w + pad_lo - 2) // 2 + 1
+    L.check(L.lib().ldm_im2col3x3_s2_pad(_p(x), _p(out), B, h, w, Cc, oh, ow, pad_lo, _stream()),
+            "ldm_im2col3x3_s2_pad")
+    return out
+
+
+def softmax_rows(s, p, scale, cols=None):
+    """p[r, :cols] = softmax(scale * s[r, :cols]); s f32 [rows, ld_s], p bf16 [rows, ld_p]."""
+    _chk(s, f32, "s"); _chk(p, bf16, "p")
+    cols = s.shape[1] if cols is None else cols
+    L.check(L.lib().ldm_softmax_rows(_p(s), _p(p), s.shape[0], cols, s.shape[1], p.shape[1], scale, _stream()),
+            "ldm_softmax_rows")
+    return p
+
+
+def resize_bilinear_planar(x, out):
+    """x f32 [..., h, w] -> out f32 [..., oh, ow], F.interpolate(mode="bilinear", align_corners=False) per plane."""
+    _chk(x, f32, "x"); _chk(out, f32, "out")
+    h, w = x.shape[-2:]
+    oh, ow = out.shape[-2:]
+    L.check(L.lib().ldm_resize_bilinear_planar(_p(x), _p(out), x.numel() // (h * w), h, w, oh, ow, _stream()),
+            "ldm_resize_bilinear_planar")
     return out
 
 
