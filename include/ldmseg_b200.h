@@ -86,6 +86,10 @@ typedef struct ldm_gemm_desc {
   int32_t heads, head_dim, dpad, seq, seq_pad; /* QKV_SPLIT geometry (seq = tokens per image)    */
   int32_t vt_rows;      /* rows per head of vt (ldm_attn_vt_rows(head_dim)); 0 = head_dim         */
   int32_t n_store;      /* OUT_NCHW_F32: channels stored (0 = N)                                 */
+  int32_t qkv_part0;    /* QKV_SPLIT: the N = nparts*heads*head_dim columns hold parts qkv_part0 .. of (q, k, v): 0 with
+                           N = 3C is the fused self-attention projection; 0 with N = C writes q only (cross-attention
+                           to_q); 1 with N = 2C writes k and vt from the context rows (to_k | to_v). Buffers of parts
+                           that are not written may be NULL.                                                    */
   const void* identity; /* optional bf16 [256,256] identity matrix (caller-owned, may be shared by all calls). When
                            given, a short-K pointwise GEMM adds `residual` on the tensor core: the residual rows
                            are streamed by TMA as extra K blocks against identity weights instead of being read
@@ -98,7 +102,7 @@ int ldm_gemm_bf16(const ldm_gemm_desc* d, ldm_stream_t stream);
  * Fused flash-style self-attention, softmax(Q K^T * scale) V, per (image, head).
  * Replaces: diffusers Attention / AttnProcessor2_0 (F.scaled_dot_product_attention) in BasicTransformerBlock.attn1
  * (cross-attention removed by ldmseg/models/unet.py:83-105).
- *   q, k : bf16 [B*heads, seq, dpad]   (dpad = 64*ceil(d/64), columns >= d are zero)
+ *   q, k : bf16 [B*heads, seq, dpad]   (dpad = 64*ceil(d/64), columns >= d are zero; k has kv_seq rows when kv_seq > 0)
  *   vt   : bf16 [B*heads, vt_rows, seq_pad]  (V transposed; seq_pad % 8 == 0; vt_rows = ldm_attn_vt_rows(d) =
  *          16*ceil(d/16); when d % 16 != 0 row d of every head must hold 1.0 for the valid keys and rows > d zero:
  *          the P.V MMA then also yields the softmax row sums)
@@ -110,7 +114,10 @@ typedef struct ldm_attn_desc {
   const void* vt;
   void* out;
   int32_t B, heads, seq, head_dim, dpad, seq_pad, vt_rows;
-  float scale; /* head_dim^-0.5 */
+  float scale;    /* head_dim^-0.5 */
+  int32_t kv_seq; /* keys / values per (image, head); 0 = seq (self-attention). Cross-attention (BasicTransformerBlock
+                     .attn2 against encoder_hidden_states, unet.py:319-323 / SURVEY 8f rank 4): q [B*heads, seq, dpad],
+                     k [B*heads, kv_seq, dpad], vt [B*heads, vt_rows, seq_pad] with seq_pad >= kv_seq.               */
 } ldm_attn_desc;
 
 int ldm_attn_vt_rows(int head_dim);

@@ -9,7 +9,9 @@ What it restates
   * ``ldmseg/models/unet.py:281-436``  forward (timestep expand, conv_in, 4 down blocks with 12 skips, mid block,
     4 up blocks popping 3 skips each, conv_norm_out + SiLU + conv_out).
   * ``ldmseg/models/unet.py:178-233``  modify_encoder (8/12-channel conv_in built from the 4-channel one).
-  * ``ldmseg/models/unet.py:83-105``   remove_cross_attention (attn2 / norm2 dropped -> self-attention only).
+  * ``ldmseg/models/unet.py:83-105``   remove_cross_attention (attn2 / norm2 dropped -> self-attention only); with
+    ``cross_attention_dim=768`` the blocks keep norm2 / attn2 against ``encoder_hidden_states`` (unet.py:319-323:
+    ``encoder_hid_proj``, learnable ``object_queries``).
 
 PARITY UNPINNED at the diffusers boundary: the reference holds no test, golden vector or fixture for the UNet and
 diffusers cannot be imported here, so nothing independent pins this restatement (DESIGN.md says the same).
@@ -78,22 +80,25 @@ class Resnet(nn.Module):
 
 
 class SelfAttn(nn.Module):
-    def __init__(self, dim, heads):
+    """diffusers Attention: self-attention (ctx_dim None) or cross-attention against `context` [b, L, ctx_dim]."""
+
+    def __init__(self, dim, heads, ctx_dim=None):
         super().__init__()
         self.heads = heads
         self.to_q = nn.Linear(dim, dim, bias=False)
-        self.to_k = nn.Linear(dim, dim, bias=False)
-        self.to_v = nn.Linear(dim, dim, bias=False)
+        self.to_k = nn.Linear(ctx_dim or dim, dim, bias=False)
+        self.to_v = nn.Linear(ctx_dim or dim, dim, bias=False)
         self.to_out = nn.ModuleList([nn.Linear(dim, dim), nn.Identity()])
 
-    def forward(self, x):
+    def forward(self, x, context=None):
         b, n, c = x.shape
         d = c // self.heads
+        ctx = x if context is None else context
 
         def split(t):
-            return t.view(b, n, self.heads, d).transpose(1, 2)
+            return t.view(b, t.shape[1], self.heads, d).transpose(1, 2)
 
-        q, k, v = split(self.to_q(x)), split(self.to_k(x)), split(self.to_v(x))
+        q, k, v = split(self.to_q(x)), split(self.to_k(ctx)), split(self.to_v(ctx))
         w = torch.softmax((q @ k.transpose(-1, -2)) * (d ** -0.5), dim=-1)
         o = (w @ v).transpose(1, 2).reshape(b, n, c)
         return self.to_out[0](o)
@@ -119,32 +124,38 @@ class FeedForward(nn.Module):
 
 
 class TransformerBlock(nn.Module):
-    """BasicTransformerBlock with attn2/norm2 removed (ldmseg/models/unet.py:83-105)."""
+    """BasicTransformerBlock; with ctx_dim None attn2/norm2 are removed (ldmseg/models/unet.py:83-105), otherwise the
+    block is norm1/attn1, norm2/attn2 (cross-attention against encoder_hidden_states), norm3/ff as in diffusers."""
 
-    def __init__(self, dim, heads):
+    def __init__(self, dim, heads, ctx_dim=None):
         super().__init__()
         self.norm1 = nn.LayerNorm(dim)
         self.attn1 = SelfAttn(dim, heads)
         self.norm3 = nn.LayerNorm(dim)
         self.ff = FeedForward(dim)
+        if ctx_dim is not None:  # (created last so that the default path draws the same random weights as before)
+            self.norm2 = nn.LayerNorm(dim)
+            self.attn2 = SelfAttn(dim, heads, ctx_dim)
 
-    def forward(self, x):
+    def forward(self, x, context=None):
         x = x + self.attn1(self.norm1(x))
+        if hasattr(self, "attn2"):
+            x = x + self.attn2(self.norm2(x), context)
         return x + self.ff(self.norm3(x))
 
 
 class Transformer2D(nn.Module):
-    def __init__(self, dim, heads, groups):
+    def __init__(self, dim, heads, groups, ctx_dim=None):
         super().__init__()
         self.norm = nn.GroupNorm(groups, dim, eps=1e-6)
         self.proj_in = nn.Conv2d(dim, dim, 1)
-        self.transformer_blocks = nn.ModuleList([TransformerBlock(dim, heads)])
+        self.transformer_blocks = nn.ModuleList([TransformerBlock(dim, heads, ctx_dim)])
         self.proj_out = nn.Conv2d(dim, dim, 1)
 
-    def forward(self, x):
+    def forward(self, x, context=None):
         b, c, h, w = x.shape
         t = self.proj_in(self.norm(x)).permute(0, 2, 3, 1).reshape(b, h * w, c)
-        t = self.transformer_blocks[0](t)
+        t = self.transformer_blocks[0](t, context)
         t = t.reshape(b, h, w, c).permute(0, 3, 1, 2)
         return self.proj_out(t) + x
 
@@ -156,20 +167,20 @@ class ConvHolder(nn.Module):
 
 
 class DownStage(nn.Module):
-    def __init__(self, cin, cout, n, temb, heads, groups, eps, attn, down):
+    def __init__(self, cin, cout, n, temb, heads, groups, eps, attn, down, ctx_dim=None):
         super().__init__()
         self.resnets = nn.ModuleList([Resnet(cin if i == 0 else cout, cout, temb, groups, eps) for i in range(n)])
         if attn:
-            self.attentions = nn.ModuleList([Transformer2D(cout, heads, groups) for _ in range(n)])
+            self.attentions = nn.ModuleList([Transformer2D(cout, heads, groups, ctx_dim) for _ in range(n)])
         if down:
             self.downsamplers = nn.ModuleList([ConvHolder(cout, 2)])
 
-    def forward(self, x, emb):
+    def forward(self, x, emb, context=None):
         skips = []
         for i, r in enumerate(self.resnets):
             x = r(x, emb)
             if hasattr(self, "attentions"):
-                x = self.attentions[i](x)
+                x = self.attentions[i](x, context)
             skips.append(x)
         if hasattr(self, "downsamplers"):
             x = self.downsamplers[0].conv(x)
@@ -178,31 +189,31 @@ class DownStage(nn.Module):
 
 
 class MidStage(nn.Module):
-    def __init__(self, c, temb, heads, groups, eps):
+    def __init__(self, c, temb, heads, groups, eps, ctx_dim=None):
         super().__init__()
         self.resnets = nn.ModuleList([Resnet(c, c, temb, groups, eps) for _ in range(2)])
-        self.attentions = nn.ModuleList([Transformer2D(c, heads, groups)])
+        self.attentions = nn.ModuleList([Transformer2D(c, heads, groups, ctx_dim)])
 
-    def forward(self, x, emb):
+    def forward(self, x, emb, context=None):
         x = self.resnets[0](x, emb)
-        x = self.attentions[0](x)
+        x = self.attentions[0](x, context)
         return self.resnets[1](x, emb)
 
 
 class UpStage(nn.Module):
-    def __init__(self, cins, cout, temb, heads, groups, eps, attn, up):
+    def __init__(self, cins, cout, temb, heads, groups, eps, attn, up, ctx_dim=None):
         super().__init__()
         self.resnets = nn.ModuleList([Resnet(ci, cout, temb, groups, eps) for ci in cins])
         if attn:
-            self.attentions = nn.ModuleList([Transformer2D(cout, heads, groups) for _ in cins])
+            self.attentions = nn.ModuleList([Transformer2D(cout, heads, groups, ctx_dim) for _ in cins])
         if up:
             self.upsamplers = nn.ModuleList([ConvHolder(cout, 1)])
 
-    def forward(self, x, emb, skips, upsample_size):
+    def forward(self, x, emb, skips, upsample_size, context=None):
         for i, r in enumerate(self.resnets):
             x = r(torch.cat([x, skips.pop()], dim=1), emb)
             if hasattr(self, "attentions"):
-                x = self.attentions[i](x)
+                x = self.attentions[i](x, context)
         if hasattr(self, "upsamplers"):
             if upsample_size is None:
                 x = F.interpolate(x, scale_factor=2.0, mode="nearest")
@@ -221,14 +232,15 @@ class UNetOracle(nn.Module):
         ch = list(c["block_out_channels"])
         n, heads, groups, eps = c["layers_per_block"], c["heads"], c["norm_groups"], c["norm_eps"]
         temb = ch[0] * c["temb_mult"]
+        xd = c.get("cross_attention_dim")  # None: cross-attention removed (the default path)
         self.conv_in = nn.Conv2d(c["in_channels"], ch[0], 3, padding=1)
         self.time_embedding = TimeMLP(ch[0], temb)
         self.down_blocks = nn.ModuleList()
         prev = ch[0]
         for i, co in enumerate(ch):
-            self.down_blocks.append(DownStage(prev, co, n, temb, heads, groups, eps, c["attn_levels"][i], i < len(ch) - 1))
+            self.down_blocks.append(DownStage(prev, co, n, temb, heads, groups, eps, c["attn_levels"][i], i < len(ch) - 1, xd))
             prev = co
-        self.mid_block = MidStage(ch[-1], temb, heads, groups, eps)
+        self.mid_block = MidStage(ch[-1], temb, heads, groups, eps, xd)
         self.up_blocks = nn.ModuleList()
         rev = ch[::-1]
         prev = rev[0]
@@ -240,7 +252,7 @@ class UNetOracle(nn.Module):
                 res_in = prev if j == 0 else co
                 cins.append(res_in + res_skip)
             attn = c["attn_levels"][::-1][i]
-            self.up_blocks.append(UpStage(cins, co, temb, heads, groups, eps, attn, i < len(ch) - 1))
+            self.up_blocks.append(UpStage(cins, co, temb, heads, groups, eps, attn, i < len(ch) - 1, xd))
             prev = co
         self.conv_norm_out = nn.GroupNorm(groups, ch[0], eps=eps)
         self.conv_out = nn.Conv2d(ch[0], c["out_channels"], 3, padding=1)
@@ -274,9 +286,22 @@ class UNetOracle(nn.Module):
         self.new_conv = new
         self.conv_in = new
 
+    # ldmseg/models/unet.py:122-123 and the 'learnable' descriptor branch (descriptors.py:89-91)
+    def modify_encoder_hidden_state_proj(self, in_channels, out_channels):
+        self.encoder_hid_proj = nn.Linear(in_channels, out_channels)
+
+    def define_learnable_embeddings(self, num_queries, dim):
+        self.object_queries = nn.Embedding(num_queries, dim)
+
     def forward(self, sample, timestep, encoder_hidden_states=None):
         """Returns the epsilon prediction tensor (the reference wraps it in UNetOutput(sample=...))."""
-        assert encoder_hidden_states is None, "cross-attention is removed on this path (base.yaml:71)"
+        ctx = encoder_hidden_states
+        if self.cfg.get("cross_attention_dim") is None:
+            assert ctx is None, "cross-attention is removed on this path (base.yaml:71)"
+        if hasattr(self, "encoder_hid_proj") and ctx is not None:   # unet.py:319-320
+            ctx = self.encoder_hid_proj(ctx)
+        if hasattr(self, "object_queries"):                          # unet.py:322-323
+            ctx = self.object_queries.weight.unsqueeze(0).repeat(sample.shape[0], 1, 1)
         ts = torch.as_tensor(timestep, device=sample.device).expand(sample.shape[0])
         emb = self.time_embedding(timestep_features(ts, self.conv_in.out_channels).to(sample.dtype))
         n_up = len(self.up_blocks) - 1
@@ -284,23 +309,25 @@ class UNetOracle(nn.Module):
         x = self.conv_in(sample)
         skips = [x]
         for blk in self.down_blocks:
-            x, s = blk(x, emb)
+            x, s = blk(x, emb, ctx)
             skips.extend(s)
-        x = self.mid_block(x, emb)
+        x = self.mid_block(x, emb, ctx)
         for i, blk in enumerate(self.up_blocks):
             n_res = len(blk.resnets)
             size = None
             if need_size and i < n_up:
                 size = skips[-n_res - 1].shape[-2:]
-            x = blk(x, emb, skips, size)
+            x = blk(x, emb, skips, size, ctx)
         return self.conv_out(F.silu(self.conv_norm_out(x)))
 
 
-def build_unet(seed=0, model_kwargs=None, **cfg):
+def build_unet(seed=0, model_kwargs=None, learnable_queries=None, **cfg):
     """Random-init oracle UNet the way tools/main_ldm.py:147-160 builds it (from_pretrained -> random init here,
     remove_cross_attention, modify_encoder(**model_kwargs))."""
     torch.manual_seed(seed)
     net = UNetOracle(**cfg)
+    if learnable_queries:  # descriptors.py:89-91: image_descriptors == 'learnable'
+        net.define_learnable_embeddings(*learnable_queries)
     mk = dict(in_channels=8, init_mode_seg="copy", init_mode_image="zero", cond_channels=0)
     mk.update(model_kwargs or {})
     net.modify_encoder(**mk)

@@ -413,6 +413,41 @@ def check_attention(B=1, heads=2, d=40, seq=300, log2_units=False, spread=1.0):
     return _stats(out, ref, f"flash_attn d={d} seq={seq} log2_units={log2_units} spread={spread}", 2e-2, 2e-2)
 
 
+def check_cross_attention(B=2, heads=8, d=40, seq=300, kv_seq=77, ctx_dim=768):
+    """attn2 of BasicTransformerBlock built from the C-ABI pieces: to_q through the head-split epilogue (q only),
+    to_k | to_v of the context rows through the same epilogue with part0 = 1, flash attention with kv_seq keys."""
+    C = heads * d
+    x = _randn((B * seq, C), 80, 1.0, bf16)
+    ctx = _randn((B * kv_seq, ctx_dim), 81, 1.0, bf16)
+    wq = _randn((C, C), 82, C ** -0.5, bf16)
+    wkv = _randn((2 * C, ctx_dim), 83, ctx_dim ** -0.5, bf16)
+    qb = ops.alloc_qkv(B, heads, seq, d, DEV)
+    kv = ops.alloc_kv(B, heads, kv_seq, d, DEV)
+    _poison(qb["q"][:, :, :d])
+    _poison(kv["k"][:, :, :d])
+    _poison(kv["vt"][:, :d, :kv_seq])
+    ops.gemm(x, wq, None, flags=L.LDM_GEMM_QKV_SPLIT,
+             qkv=dict(q=qb["q"], heads=heads, head_dim=d, dpad=qb["dpad"], seq=seq, seq_pad=qb["seq_pad"]))
+    ops.gemm(ctx, wkv, None, flags=L.LDM_GEMM_QKV_SPLIT, qkv=dict(kv, part0=1))
+    out = _empty((B * seq, C), dtype=bf16, device=DEV)
+    ops.flash_attn(qb["q"], kv["k"], kv["vt"], out, B=B, heads=heads, seq=seq, head_dim=d, dpad=kv["dpad"],
+                   seq_pad=kv["seq_pad"], scale=d ** -0.5, kv_seq=kv_seq)
+    qr = (x.float() @ wq.float().t()).view(B, seq, heads, d).permute(0, 2, 1, 3)
+    kvr = (ctx.float() @ wkv.float().t()).view(B, kv_seq, 2, heads, d)
+    kr, vr = kvr[:, :, 0].permute(0, 2, 1, 3), kvr[:, :, 1].permute(0, 2, 1, 3)
+    _stats(qb["q"][:, :, :d], qr.reshape(B * heads, seq, d), "cross q", 3e-2, 1e-2)
+    _stats(kv["k"][:, :, :d], kr.reshape(B * heads, kv_seq, d), "cross k", 3e-2, 1e-2)
+    _stats(kv["vt"][:, :d, :kv_seq], vr.transpose(-1, -2).reshape(B * heads, d, kv_seq), "cross vt", 3e-2, 1e-2)
+    if kv["vt"].shape[1] != d:
+        assert float((kv["vt"][:, d, :kv_seq] - 1).abs().max()) == 0.0, "ones row of the context V^T overwritten"
+    # the checker uses the bf16-rounded projections the kernel saw
+    ref = F.scaled_dot_product_attention(qb["q"][:, :, :d].float().view(B, heads, seq, d),
+                                         kv["k"][:, :, :d].float().view(B, heads, kv_seq, d),
+                                         kv["vt"][:, :d, :kv_seq].float().transpose(1, 2).view(B, heads, kv_seq, d))
+    ref = ref.permute(0, 2, 1, 3).reshape(B * seq, C)
+    return _stats(out, ref, f"cross attention d={d} seq={seq} kv={kv_seq}", 2e-2, 2e-2)
+
+
 # ----------------------------------------------------------------------------------------------------------- integer tail
 def check_logits_to_ids(up=2):
     B, h, w, C = 2, 24, 78, 128
@@ -516,6 +551,10 @@ CHECKS = {
     "ddim": check_ddim,
     "layernorm_320": lambda: check_layernorm(320),
     "layernorm_1280": lambda: check_layernorm(1280, 468),
+    # more row groups than resident warps (the persistent kernel's grid-stride loop + prefetch), ragged last group
+    "layernorm_320_long": lambda: check_layernorm(320, 59905),
+    "layernorm_640_long": lambda: check_layernorm(640, 14977),
+    "layernorm_1280_long": lambda: check_layernorm(1280, 9001),
     "groupnorm_320": lambda: check_groupnorm(320),
     "groupnorm_960cat": lambda: check_groupnorm(640, 320, 1872),
     "groupnorm_1920cat_nosilu": lambda: check_groupnorm(1280, 640, 468, silu=False, eps=1e-6),
@@ -555,6 +594,10 @@ CHECKS = {
     "attn_80": lambda: check_attention(1, 2, 80, 468),
     "attn_160": lambda: check_attention(2, 2, 160, 120),
     "attn_160_b": lambda: check_attention(1, 2, 160, 468),
+    "cross_attn_40_kv77": check_cross_attention,
+    "cross_attn_40_kv128_long": lambda: check_cross_attention(1, 8, 40, 7488, 128),
+    "cross_attn_80_kv257": lambda: check_cross_attention(2, 8, 80, 468, 257, 1024),
+    "cross_attn_160_kv16": lambda: check_cross_attention(2, 8, 160, 120, 16, 64),
     "logits_to_ids_up2": check_logits_to_ids,
     "logits_to_ids_up1": lambda: check_logits_to_ids(1),
     "bitmap": check_bitmap,

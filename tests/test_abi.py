@@ -34,5 +34,5 @@ def test_struct_sizes_match_header_layout():
     import ctypes as C
     # 12 pointers + float + 14 int32, 8-byte aligned
     assert C.sizeof(L.GemmDesc) == 12 * 8 + 4 + 14 * 4 + 0 or C.sizeof(L.GemmDesc) % 8 == 0
-    assert C.sizeof(L.AttnDesc) == 4 * 8 + 6 * 4 + 4 + 4
+    assert C.sizeof(L.AttnDesc) == 4 * 8 + 6 * 4 + 4 + 4 + 4 + 4  # kv_seq + tail padding to 8 bytes
     assert C.sizeof(L.GroupNormDesc) == 6 * 8 + 5 * 4 + 4 + 4 + 4

@@ -107,7 +107,7 @@ def test_unet_forward_without_gpu_fails_loudly():
     m.load_state_dict(unet_init.random_unet_state_dict(0, in_channels=8, **cfg))
     with pytest.raises(L.LdmError):
         m(torch.zeros(1, 8, 8, 8), torch.tensor(999), encoder_hidden_states=None)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(L.LdmError):  # CPU tensors are refused before anything else, with or without a context
         m(torch.zeros(1, 8, 8, 8), torch.tensor(999), encoder_hidden_states=torch.zeros(1, 77, 768))
 
 

@@ -272,6 +272,50 @@ def test_encode_inputs_vs_oracle(vae_image):
     assert lat2.shape == (2, 4, 8, 16) and _rel(lat2, ref2) < 3e-2
 
 
+def test_unet_cross_attention_vs_oracle():
+    """the UNet with its cross-attention layers kept (SD-1.4 cross_attention_dim 768). (a) explicit
+    encoder_hidden_states of 77 tokens (the CLIP text context length); (b) the 'learnable' descriptor variant
+    (descriptors.py:89-91, unet.py:322-323): 128 object queries are the context and the sampler needs no extra input."""
+    from oracle import ldmseg_oracle as LO
+    from oracle import unet_oracle as UO
+    from video_latent_diffusion_panoptic_segmentation_b200.ldmseg.models import UNet
+    from video_latent_diffusion_panoptic_segmentation_b200.ldmseg.schedulers import DDIMNoiseScheduler
+    from video_latent_diffusion_panoptic_segmentation_b200.ldmseg.trainers import TrainerDiffusion
+    g = torch.Generator().manual_seed(5)
+    B, h, w = 2, 16, 24
+    x = torch.randn((B, 8, h, w), generator=g).to(DEV)
+    t = torch.tensor(499, device=DEV)
+    # (a) explicit context
+    o_unet = UO.build_unet(seed=4, cross_attention_dim=768)
+    unet = UNet(device=DEV)
+    unet.load_state_dict(o_unet.state_dict())
+    o_unet = o_unet.to(DEV)
+    ehs = torch.randn((B, 77, 768), generator=g).to(DEV)
+    with torch.no_grad():
+        ref = o_unet(x, t, encoder_hidden_states=ehs)
+        ref0 = o_unet(x, t, encoder_hidden_states=torch.zeros_like(ehs))
+    got = unet(x, t, encoder_hidden_states=ehs).sample
+    assert _rel(got, ref) < 3e-2, _rel(got, ref)
+    assert _rel(ref0, ref) > 3 * _rel(got, ref)  # the context moves the output by more than the error
+    got_b = unet(x, t, encoder_hidden_states=0.5 * ehs).sample  # a new context re-projects k / v of every layer
+    with torch.no_grad():
+        ref_b = o_unet(x, t, encoder_hidden_states=0.5 * ehs)
+    assert _rel(got_b, ref_b) < 3e-2
+    with pytest.raises(ValueError):
+        unet(x, t, encoder_hidden_states=None)
+    del unet, o_unet
+    # (b) learnable object queries, through the sampler
+    o_unet = UO.build_unet(seed=6, cross_attention_dim=768, learnable_queries=(128, 768))
+    unet = UNet(device=DEV)
+    unet.load_state_dict(o_unet.state_dict())
+    o_unet = o_unet.to(DEV)
+    rgb = (0.18215 * torch.randn((B, 4, h, w), generator=torch.Generator().manual_seed(1234))).to(DEV)
+    tr = TrainerDiffusion(p={}, unet_model=unet, noise_scheduler=DDIMNoiseScheduler(**SCHED_KW), args={"gpu": 0})
+    lat = tr.sample([""] * B, num_inference_steps=3, seed=42, rgb_latents=rgb)
+    ref = LO.sample(o_unet, LO.DDIMOracle(), rgb, num_inference_steps=3, seed=42)
+    assert _rel(lat, ref) < 8e-2, _rel(lat, ref)
+
+
 def test_tail_ids_bit_exact_given_identical_logits(models):
     """H6/H7: feed the SAME fp32 logits to the CUDA tail and to the restated reference tail."""
     from oracle import ldmseg_oracle as LO

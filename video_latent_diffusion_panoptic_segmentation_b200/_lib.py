@@ -29,7 +29,7 @@ class GemmDesc(C.Structure):
         ("B", c_i32), ("H", c_i32), ("W", c_i32), ("c1", c_i32), ("c2", c_i32), ("N", c_i32), ("taps", c_i32),
         ("block_n", c_i32), ("flags", c_i32),
         ("heads", c_i32), ("head_dim", c_i32), ("dpad", c_i32), ("seq", c_i32), ("seq_pad", c_i32),
-        ("vt_rows", c_i32), ("n_store", c_i32),
+        ("vt_rows", c_i32), ("n_store", c_i32), ("qkv_part0", c_i32),
         ("identity", c_vp),
     ]
 
@@ -38,7 +38,7 @@ class AttnDesc(C.Structure):
     _fields_ = [
         ("q", c_vp), ("k", c_vp), ("vt", c_vp), ("out", c_vp),
         ("B", c_i32), ("heads", c_i32), ("seq", c_i32), ("head_dim", c_i32), ("dpad", c_i32), ("seq_pad", c_i32),
-        ("vt_rows", c_i32), ("scale", c_f32),
+        ("vt_rows", c_i32), ("scale", c_f32), ("kv_seq", c_i32),
     ]
 
 

@@ -77,7 +77,7 @@ flash_attn40_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int lane = threadIdx.x & 31;
   const int bh = blockIdx.y;
   const int q_base = blockIdx.x * 256;
-  const int nblk = (p.seq + kBKV - 1) / kBKV;
+  const int nblk = (p.kv_seq + kBKV - 1) / kBKV;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -215,7 +215,7 @@ flash_attn40_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     constexpr float kRedo = 64.0f;      // ... and redo a block's exponentials if it alone jumps by more than 2^64
 
     for (int j = 0; j < nblk; ++j) {
-      const int nvalid = p.seq - j * kBKV - h * kHalf;  // keys of this half inside the sequence (may be <= 0)
+      const int nvalid = p.kv_seq - j * kBKV - h * kHalf;  // keys of this half inside the sequence (may be <= 0)
       const uint32_t t_s = t_g + (j & 1) * (kBKV / 2) + h * kHalf;  // this half's scores ...
       const uint32_t t_p = t_g + (j & 1) * kBKV + h * (kHalf / 2);  // ... and where its P goes
       TRACE(0, j);
@@ -368,19 +368,22 @@ template <int kPoly>
 int launch(const ldm_attn_desc* d, cudaStream_t s) {
   using namespace ldm_host;
   const int BH = d->B * d->heads;
+  const int kv_seq = d->kv_seq > 0 ? d->kv_seq : d->seq;
   CUtensorMap tmQ, tmK, tmV;
   {
     const uint64_t dims[3] = {(uint64_t)d->dpad, (uint64_t)d->seq, (uint64_t)BH};
     const uint64_t str[2] = {(uint64_t)d->dpad * 2, (uint64_t)d->dpad * 2 * d->seq};
+    const uint64_t dimsk[3] = {(uint64_t)d->dpad, (uint64_t)kv_seq, (uint64_t)BH};
+    const uint64_t strk[2] = {(uint64_t)d->dpad * 2, (uint64_t)d->dpad * 2 * kv_seq};
     const uint32_t boxq[3] = {64, 128, 1};
     const uint32_t boxk[3] = {64, (uint32_t)kBKV, 1};
     int rc = make_tmap(&tmQ, d->q, 3, dims, str, boxq, 2, true);
     if (rc) return rc;
-    rc = make_tmap(&tmK, d->k, 3, dims, str, boxk, 2, true);
+    rc = make_tmap(&tmK, d->k, 3, dimsk, strk, boxk, 2, true);
     if (rc) return rc;
   }
   {
-    const uint64_t dims[3] = {(uint64_t)d->seq, (uint64_t)d->vt_rows, (uint64_t)BH};
+    const uint64_t dims[3] = {(uint64_t)kv_seq, (uint64_t)d->vt_rows, (uint64_t)BH};
     const uint64_t str[2] = {(uint64_t)d->seq_pad * 2, (uint64_t)d->seq_pad * 2 * d->vt_rows};
     const uint32_t box[3] = {64, (uint32_t)kDN, 1};
     int rc = make_tmap(&tmV, d->vt, 3, dims, str, box, 2, true);
@@ -388,6 +391,7 @@ int launch(const ldm_attn_desc* d, cudaStream_t s) {
   }
   AttnParams p;
   p.seq = d->seq;
+  p.kv_seq = kv_seq;
   p.heads = d->heads;
   p.head_dim = d->head_dim;
   p.scale_log2 = d->scale * 1.4426950408889634f;

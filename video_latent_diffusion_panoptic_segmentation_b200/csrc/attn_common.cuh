@@ -27,6 +27,7 @@ using namespace ldm;
 
 struct AttnParams {
   int seq, heads, head_dim;
+  int kv_seq;  // keys / values per (image, head): seq for self-attention, the context length for cross-attention
   float scale_log2;  // scale * log2(e)
   __nv_bfloat16* out;
 };

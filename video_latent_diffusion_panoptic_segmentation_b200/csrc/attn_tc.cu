@@ -76,7 +76,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   const int lane = threadIdx.x & 31;
   const int bh = blockIdx.y;
   const int q_base = blockIdx.x * 128 * NQ;
-  const int nblk = (p.seq + BKV - 1) / BKV;
+  const int nblk = (p.kv_seq + BKV - 1) / BKV;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -221,7 +221,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     constexpr float kRedo = 64.0f;      // ... and redo a block's exponentials if it alone jumps by more than 2^64
 
     for (int j = 0; j < nblk; ++j) {
-      const int nvalid = p.seq - j * BKV;  // keys of this block inside the sequence (>= 1)
+      const int nvalid = p.kv_seq - j * BKV;  // keys of this block inside the sequence (>= 1)
       const uint32_t t_s = t_g + (j & 1) * (BKV / 2);  // this block's scores ...
       const uint32_t t_p = t_g + (j & 1) * BKV;        // ... and where its P goes (see the column ring above)
       TRACE(0, j);
@@ -366,19 +366,22 @@ int launch_attn(const ldm_attn_desc* d, cudaStream_t s) {
   using namespace ldm_host;
   using Cfg = AttnCfg<D, NQ, BKV, STAGES>;
   const int BH = d->B * d->heads;
+  const int kv_seq = d->kv_seq > 0 ? d->kv_seq : d->seq;
   CUtensorMap tmQ, tmK, tmV;
   {
     const uint64_t dims[3] = {(uint64_t)d->dpad, (uint64_t)d->seq, (uint64_t)BH};
     const uint64_t str[2] = {(uint64_t)d->dpad * 2, (uint64_t)d->dpad * 2 * d->seq};
+    const uint64_t dimsk[3] = {(uint64_t)d->dpad, (uint64_t)kv_seq, (uint64_t)BH};
+    const uint64_t strk[2] = {(uint64_t)d->dpad * 2, (uint64_t)d->dpad * 2 * kv_seq};
     const uint32_t boxq[3] = {64, 128, 1};
     const uint32_t boxk[3] = {64, (uint32_t)BKV, 1};
     int rc = make_tmap(&tmQ, d->q, 3, dims, str, boxq, 2, true);
     if (rc) return rc;
-    rc = make_tmap(&tmK, d->k, 3, dims, str, boxk, 2, true);
+    rc = make_tmap(&tmK, d->k, 3, dimsk, strk, boxk, 2, true);
     if (rc) return rc;
   }
   {
-    const uint64_t dims[3] = {(uint64_t)d->seq, (uint64_t)d->vt_rows, (uint64_t)BH};
+    const uint64_t dims[3] = {(uint64_t)kv_seq, (uint64_t)d->vt_rows, (uint64_t)BH};
     const uint64_t str[2] = {(uint64_t)d->seq_pad * 2, (uint64_t)d->seq_pad * 2 * d->vt_rows};
     const uint32_t box[3] = {64, (uint32_t)Cfg::kDN, 1};
     int rc = make_tmap(&tmV, d->vt, 3, dims, str, box, 2, true);
@@ -386,6 +389,7 @@ int launch_attn(const ldm_attn_desc* d, cudaStream_t s) {
   }
   AttnParams p;
   p.seq = d->seq;
+  p.kv_seq = kv_seq;
   p.heads = d->heads;
   p.head_dim = d->head_dim;
   p.scale_log2 = d->scale * 1.4426950408889634f;
@@ -415,9 +419,10 @@ extern "C" int ldm_flash_attn_fwd(const ldm_attn_desc* d, ldm_stream_t stream) {
   LDM_REQUIRE(d->vt_rows == ldm_attn_vt_rows(d->head_dim), LDM_ERR_BAD_SHAPE,
               "ldm_flash_attn_fwd: vt_rows=%d, expected ldm_attn_vt_rows(%d)=%d", d->vt_rows, d->head_dim,
               ldm_attn_vt_rows(d->head_dim));
-  LDM_REQUIRE(d->dpad == ((d->head_dim + 63) / 64) * 64 && d->seq_pad % 8 == 0 && d->seq_pad >= d->seq,
-              LDM_ERR_BAD_SHAPE, "ldm_flash_attn_fwd: dpad=%d seq_pad=%d inconsistent with head_dim=%d seq=%d", d->dpad,
-              d->seq_pad, d->head_dim, d->seq);
+  const int kv_seq = d->kv_seq > 0 ? d->kv_seq : d->seq;
+  LDM_REQUIRE(d->kv_seq >= 0 && d->dpad == ((d->head_dim + 63) / 64) * 64 && d->seq_pad % 8 == 0 && d->seq_pad >= kv_seq,
+              LDM_ERR_BAD_SHAPE, "ldm_flash_attn_fwd: dpad=%d seq_pad=%d inconsistent with head_dim=%d kv_seq=%d", d->dpad,
+              d->seq_pad, d->head_dim, kv_seq);
   cudaStream_t s = as_stream(stream);
   switch (d->head_dim) {
     case 40: {

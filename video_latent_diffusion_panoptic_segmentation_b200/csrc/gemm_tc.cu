@@ -184,10 +184,15 @@ extern "C" int ldm_gemm_bf16(const ldm_gemm_desc* d, ldm_stream_t stream) {
               block_n);
   if (flags & LDM_GEMM_GEGLU) LDM_REQUIRE(d->N % 32 == 0, LDM_ERR_BAD_SHAPE, "GEGLU needs N %% 32 == 0");
   if (flags & LDM_GEMM_QKV_SPLIT) {
-    LDM_REQUIRE(d->q && d->k && d->vt && d->heads > 0 && d->head_dim % 8 == 0 && d->N == 3 * d->heads * d->head_dim &&
-                    d->seq > 0 && d->seq_pad % 8 == 0 && d->dpad % 64 == 0 &&
+    const int Cqkv = d->heads * d->head_dim;
+    const int nparts = Cqkv > 0 ? d->N / Cqkv : 0;
+    const int part0 = d->qkv_part0;
+    LDM_REQUIRE(d->heads > 0 && d->head_dim % 8 == 0 && d->N == nparts * Cqkv && nparts >= 1 && part0 >= 0 &&
+                    part0 + nparts <= 3 && d->seq > 0 && d->seq_pad % 8 == 0 && d->dpad % 64 == 0 &&
                     (long long)d->B * d->H * d->W % d->seq == 0,
                 LDM_ERR_BAD_SHAPE, "ldm_gemm_bf16: bad QKV split geometry");
+    LDM_REQUIRE((part0 > 0 || d->q) && (part0 > 1 || part0 + nparts < 2 || d->k) && (part0 + nparts < 3 || d->vt),
+                LDM_ERR_BAD_ARG, "ldm_gemm_bf16: QKV split needs the q / k / vt buffers of the parts it writes");
   } else {
     LDM_REQUIRE(d->out != nullptr, LDM_ERR_BAD_ARG, "ldm_gemm_bf16: null out");
     LDM_REQUIRE(d->N % 8 == 0, LDM_ERR_ALIGNMENT, "ldm_gemm_bf16: N must be a multiple of 8 (got %d)", d->N);
@@ -227,6 +232,7 @@ extern "C" int ldm_gemm_bf16(const ldm_gemm_desc* d, ldm_stream_t stream) {
   p.seq = d->seq;
   p.seq_pad = d->seq_pad;
   p.vt_rows = d->vt_rows > 0 ? d->vt_rows : d->head_dim;
+  p.qkv_part0 = d->qkv_part0;
   if (flags & LDM_GEMM_QKV_SPLIT) {
     auto magic = [](long long dv) { return (unsigned long long)(((1ULL << 40) + (unsigned long long)dv - 1) / (unsigned long long)dv); };
     p.magic_seq = magic(d->seq);

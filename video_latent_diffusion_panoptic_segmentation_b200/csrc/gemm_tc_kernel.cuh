@@ -43,6 +43,7 @@ struct GemmParams {
   const float* ln_beta;
   float ln_eps;
   int heads, head_dim, dpad, seq, seq_pad, vt_rows;
+  int qkv_part0;    // QKV_SPLIT: first of the q|k|v parts the N columns hold (0: q.., 1: k.., 2: v only)
   unsigned long long magic_seq, magic_c, magic_d;  // ceil(2^40 / divisor): x / d == (x * magic) >> 40 for x * d < 2^40
   int n_store;      // OUT_NCHW_F32: leading output channels actually stored
   long long img_px; // pixels per image of the un-flattened problem (H*W)
@@ -503,8 +504,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             for (int g = 0; g < 4; ++g) {
               const int n = nc + g * 8;
               if (n >= p.N) break;
-              const int which = (int)(((unsigned long long)(unsigned)n * p.magic_c) >> 40);
-              const int cc = n - which * C;
+              const int part = (int)(((unsigned long long)(unsigned)n * p.magic_c) >> 40);
+              const int cc = n - part * C;
+              const int which = part + p.qkv_part0;
               const int head = (int)(((unsigned long long)(unsigned)cc * p.magic_d) >> 40);
               const int e = cc - head * p.head_dim;
               const long long bh = (long long)qkv_bi * p.heads + head;

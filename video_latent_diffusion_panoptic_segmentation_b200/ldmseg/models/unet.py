@@ -162,6 +162,21 @@ class UNet:
         self._packed = None
         self._plans = {}
 
+    def modify_encoder_hidden_state_proj(self, in_channels, out_channels):
+        """unet.py:122-123: a fresh nn.Linear in front of the cross-attention context (CLIP image features 1024 -> 768)."""
+        lin = torch.nn.Linear(in_channels, out_channels)
+        self._sd["encoder_hid_proj.weight"] = lin.weight.detach().clone()
+        self._sd["encoder_hid_proj.bias"] = lin.bias.detach().clone()
+        self.encoder_hid_proj = lin
+        self._packed, self._plans = None, {}
+
+    def define_learnable_embeddings(self, num_queries, dim):
+        """image_descriptors == 'learnable' (descriptors.py:89-91): an nn.Embedding whose weight is the context."""
+        emb = torch.nn.Embedding(num_queries, dim)
+        self._sd["object_queries.weight"] = emb.weight.detach().clone()
+        self.object_queries = emb
+        self._packed, self._plans = None, {}
+
     def freeze_layers(self, layers=("norm", "time_embedding")):
         return None  # inference-only mirror: nothing is trainable
 
@@ -180,10 +195,8 @@ class UNet:
     # ------------------------------------------------------------------ weight packing
     def _pack(self):
         sd, dev = self._sd, self.device
-        if not self._cross_attention_removed and any(".attn2." in k for k in sd):
-            raise NotImplementedError("cross-attention (image_descriptors != remove) is not built yet; call "
-                                      "remove_cross_attention() as tools/main_ldm.py:156-158 does")
         P = {}
+        P["cross"] = (not self._cross_attention_removed) and any(".attn2." in k for k in sd)
 
         def dv(t, dtype=f32):
             return t.to(dev, dtype).contiguous()
@@ -245,16 +258,31 @@ class UNet:
             perm = torch.cat([idx, idx + inner], dim=1).reshape(-1)  # 16 value rows, then their 16 gate rows
             P[tb + ".ff1"] = (dv(w1[perm], bf16), dv(b1[perm]))
             P[tb + ".ff2"] = lin(tb + ".ff.net.2")
+            if P["cross"]:  # BasicTransformerBlock.norm2 / attn2 against encoder_hidden_states
+                P[tb + ".norm2"] = norm(tb + ".norm2")
+                P[tb + ".q2"] = dv(sd[tb + ".attn2.to_q.weight"], bf16)
+                P[tb + ".kv2"] = dv(torch.cat([sd[tb + ".attn2.to_k.weight"], sd[tb + ".attn2.to_v.weight"]], 0), bf16)
+                P[tb + ".to_out2"] = lin(tb + ".attn2.to_out.0")
+        if P["cross"]:
+            P["ctx_dim"] = sd[attn_names[0] + ".transformer_blocks.0.attn2.to_k.weight"].shape[1]
+            if "encoder_hid_proj.weight" in sd:    # unet.py:122-123,319-320
+                P["hid_proj"] = lin("encoder_hid_proj")
+            if "object_queries.weight" in sd:      # unet.py:322-323 (image_descriptors == 'learnable')
+                P["object_queries"] = dv(sd["object_queries.weight"], bf16)
         for k in sd:
             if k.endswith("samplers.0.conv.weight"):
                 P[k[: -len(".weight")]] = conv3(k[: -len(".weight")])
         self._packed = P
 
     # ------------------------------------------------------------------ plan
-    def _build_plan(self, B, h, w, cin):
+    def _build_plan(self, B, h, w, cin, ctx_len=0):
         if self._packed is None:
             self._pack()
         P, cfg, dev = self._packed, self.config, self.device
+        cross = P["cross"]
+        if cross and ctx_len <= 0:
+            raise L.LdmError("this UNet keeps its cross-attention layers: pass encoder_hidden_states (or call "
+                             "define_learnable_embeddings / remove_cross_attention as tools/main_ldm.py does)")
         ch = list(cfg.block_out_channels)
         heads, groups, eps = cfg.attention_head_dim, cfg.norm_num_groups, cfg.norm_eps
         nres = cfg.layers_per_block
@@ -272,6 +300,16 @@ class UNet:
         st.emb_silu = torch.empty((temb_dim,), dtype=f32, device=dev)
         st.temb_bias = torch.empty((P["temb_total"],), dtype=f32, device=dev)
         qkv_cache = {}
+        ctx_plan = []  # launches that depend only on the context: run when it changes, not once per DDIM step
+        st.ctx_len, st.context_in, st.context = ctx_len, None, None
+        if cross:
+            in_dim = P["hid_proj"][0].shape[1] if "hid_proj" in P else P["ctx_dim"]
+            st.context_in = torch.zeros((B * ctx_len, in_dim), dtype=bf16, device=dev)
+            if "hid_proj" in P:
+                st.context = torch.empty((B * ctx_len, P["ctx_dim"]), dtype=bf16, device=dev)
+                ctx_plan.append((ops.gemm, (st.context_in, P["hid_proj"][0], st.context), dict(bias=P["hid_proj"][1])))
+            else:
+                st.context = st.context_in
 
         def add(fn, *a, **k):
             plan.append((fn, a, k))
@@ -331,6 +369,22 @@ class UNet:
             add(ops.gemm, t1, P[tb + ".to_out"][0], h2, bias=P[tb + ".to_out"][1], residual=hid)
             arena.release(t1)
             arena.release(hid)
+            if cross:
+                # attn2: q from the tokens, k / v from the context (projected once per context into per-layer buffers)
+                kv = ops.alloc_kv(B, heads, ctx_len, d, dev)
+                ctx_plan.append((ops.gemm, (st.context, P[tb + ".kv2"], None),
+                                 dict(flags=L.LDM_GEMM_QKV_SPLIT, qkv=dict(kv, part0=1))))
+                t1 = arena.alloc((M, C))
+                add(ops.layernorm, h2, *P[tb + ".norm2"], t1, 1e-5)
+                add(ops.gemm, t1, P[tb + ".q2"], None, flags=L.LDM_GEMM_QKV_SPLIT,
+                    qkv=dict(q=qkv["q"], heads=heads, head_dim=d, dpad=qkv["dpad"], seq=seq, seq_pad=qkv["seq_pad"]))
+                add(ops.flash_attn, qkv["q"], kv["k"], kv["vt"], t1, B=B, heads=heads, seq=seq, head_dim=d,
+                    dpad=kv["dpad"], seq_pad=kv["seq_pad"], scale=d ** -0.5, kv_seq=ctx_len)
+                h2b = arena.alloc((M, C))
+                add(ops.gemm, t1, P[tb + ".to_out2"][0], h2b, bias=P[tb + ".to_out2"][1], residual=h2)
+                arena.release(t1)
+                arena.release(h2)
+                h2 = h2b
             t2 = arena.alloc((M, C))
             add(ops.layernorm, h2, *P[tb + ".norm3"], t2, 1e-5)
             g = arena.alloc((M, 4 * C))
@@ -423,6 +477,10 @@ class UNet:
         add(ops.gemm, t, P["conv_out"][0], st.out, taps=9, bias=P["conv_out"][1], flags=L.LDM_GEMM_OUT_NCHW_F32,
             block_n=32, n_store=cfg.out_channels)
         st.plan, st.arena_bytes, st.graph = plan, arena.total, None
+        st.ctx_plan = ctx_plan
+        if cross and "object_queries" in P:  # the context is a parameter: project it now, once
+            st.context_in.view(B, ctx_len, -1).copy_(P["object_queries"].unsqueeze(0).expand(B, -1, -1))
+            self._run_ctx_plan(st)
         st.launches_per_forward = None
         return st
 
@@ -430,15 +488,38 @@ class UNet:
         for fn, a, k in st.plan:
             fn(*a, **k)
 
-    def _get_plan(self, B, h, w, cin, parts=None):
+    def _run_ctx_plan(self, st):
+        for fn, a, k in st.ctx_plan:
+            fn(*a, **k)
+
+    def set_context(self, st, encoder_hidden_states):
+        """encoder_hidden_states [B, L, dim] -> the plan's static context; (re)projects k / v of every attn2 layer
+        (and encoder_hid_proj, unet.py:319-320). The UNet graph reads those buffers, so one call serves all steps."""
+        B = st.sample.shape[0]
+        e = encoder_hidden_states
+        if e.dim() != 3 or e.shape[0] != B or e.shape[1] != st.ctx_len or e.shape[2] != st.context_in.shape[1]:
+            raise ValueError(f"encoder_hidden_states {tuple(e.shape)} does not match (B={B}, L={st.ctx_len}, "
+                             f"dim={st.context_in.shape[1]})")
+        st.context_in.view(B, st.ctx_len, -1).copy_(e)
+        self._run_ctx_plan(st)
+
+    def _get_plan(self, B, h, w, cin, parts=None, ctx_len=None):
         """parts: optional list of static f32 NCHW [B,4,h,w] buffers (x_t, rgb_latents[, condition]) that conv_in
-        reads directly -- the sampler's fused concat (trainers_ldm_cond.py:1134-1141)."""
-        key = (B, h, w, cin, None if parts is None else tuple(t.data_ptr() for t in parts))
+        reads directly -- the sampler's fused concat (trainers_ldm_cond.py:1134-1141). ctx_len: tokens of the
+        cross-attention context (default: the learnable object queries' count, or 0 without cross-attention)."""
+        if self._packed is None:
+            self._pack()
+        if ctx_len is None:
+            oq = self._packed.get("object_queries")
+            ctx_len = oq.shape[0] if oq is not None else 0
+        if not self._packed["cross"]:
+            ctx_len = 0
+        key = (B, h, w, cin, ctx_len, None if parts is None else tuple(t.data_ptr() for t in parts))
         st = self._plans.get(key)
         if st is None:
             if cin != self.conv_in.in_channels:
                 raise ValueError(f"input has {cin} channels, conv_in expects {self.conv_in.in_channels}")
-            st = self._build_plan(B, h, w, cin)
+            st = self._build_plan(B, h, w, cin, ctx_len)
             if parts is not None:
                 self.set_split_inputs(st, parts)
             self._plans[key] = st
@@ -504,16 +585,25 @@ class UNet:
     def forward(self, sample, timestep, encoder_hidden_states=None, class_labels=None, timestep_cond=None,
                 attention_mask=None, cross_attention_kwargs=None, down_block_additional_residuals=None,
                 mid_block_additional_residual=None, return_dict=True, timestep_img=None):
-        if encoder_hidden_states is not None:
-            raise NotImplementedError("encoder_hidden_states must be None: cross-attention is removed on this path")
-        if down_block_additional_residuals is not None or mid_block_additional_residual is not None:
-            raise NotImplementedError("additional residuals are not on the sampling path")
         if not sample.is_cuda:
             raise L.LdmError("UNet.forward needs CUDA tensors: there is no CPU fallback")
+        if self._packed is None:
+            self._pack()
+        cross, learnable = self._packed["cross"], "object_queries" in self._packed
+        if encoder_hidden_states is not None and not cross:
+            raise ValueError("encoder_hidden_states given but this UNet has no cross-attention layers "
+                             "(remove_cross_attention() was called, tools/main_ldm.py:156-158)")
+        if down_block_additional_residuals is not None or mid_block_additional_residual is not None:
+            raise NotImplementedError("additional residuals are not on the sampling path")
         B, cin, h, w = sample.shape
         if cin != self.conv_in.in_channels:
             raise ValueError(f"sample has {cin} channels, conv_in expects {self.conv_in.in_channels}")
-        st = self._get_plan(B, h, w, cin)
+        use_ehs = cross and not learnable  # unet.py:322-323: learnable object queries replace whatever was passed
+        if use_ehs and encoder_hidden_states is None:
+            raise ValueError("this UNet keeps its cross-attention layers: encoder_hidden_states is required")
+        st = self._get_plan(B, h, w, cin, ctx_len=encoder_hidden_states.shape[1] if use_ehs else None)
+        if use_ehs:
+            self.set_context(st, encoder_hidden_states)
         st.sample.copy_(sample)
         ts = timestep if torch.is_tensor(timestep) else torch.tensor(timestep)
         st.timestep.copy_(ts.reshape(-1)[:1].to(torch.int64))  # unet.py:302-303: one timestep expanded over B

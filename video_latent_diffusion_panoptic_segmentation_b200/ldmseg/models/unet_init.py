@@ -11,8 +11,9 @@ import torch
 
 
 def unet_param_shapes(block_out_channels=(320, 640, 1280, 1280), layers_per_block=2, in_channels=4, out_channels=4,
-                      attn_levels=(True, True, True, False), temb_mult=4):
-    """Ordered {key: shape} of diffusers' UNet2DConditionModel without attn2/norm2 (unet.py:83-105)."""
+                      attn_levels=(True, True, True, False), temb_mult=4, cross_attention_dim=None):
+    """Ordered {key: shape} of diffusers' UNet2DConditionModel; without attn2/norm2 (unet.py:83-105) unless
+    cross_attention_dim is given (768 in the SD-1.4 config)."""
     ch = list(block_out_channels)
     temb = ch[0] * temb_mult
     S = {}
@@ -45,6 +46,12 @@ def unet_param_shapes(block_out_channels=(320, 640, 1280, 1280), layers_per_bloc
         for p in ("to_q", "to_k", "to_v"):
             lin(f"{tb}.attn1.{p}", c, c, bias=False)
         lin(tb + ".attn1.to_out.0", c, c)
+        if cross_attention_dim:
+            norm(tb + ".norm2", c)
+            lin(tb + ".attn2.to_q", c, c, bias=False)
+            lin(tb + ".attn2.to_k", cross_attention_dim, c, bias=False)
+            lin(tb + ".attn2.to_v", cross_attention_dim, c, bias=False)
+            lin(tb + ".attn2.to_out.0", c, c)
         norm(tb + ".norm3", c)
         lin(tb + ".ff.net.0.proj", c, 8 * c)
         lin(tb + ".ff.net.2", 4 * c, c)

@@ -33,8 +33,9 @@ class TrainerDiffusion:
         self.vae_image, self.vae_semseg, self.unet_model = vae_image, vae_semseg, unet_model
         self.noise_scheduler = noise_scheduler
         if image_descriptor_model is not None or text_encoder is not None:
-            raise NotImplementedError("image descriptors / text encoders imply cross-attention, which is removed on "
-                                      "the default path (base.yaml:71); SURVEY section 8(f) rank 4")
+            raise NotImplementedError("CLIP image / text encoders are outside this path; the UNet's cross-attention "
+                                      "itself is built (UNet.forward(encoder_hidden_states=...), learnable object "
+                                      "queries): SURVEY section 8(f) rank 4")
         self.image_descriptor_model, self.textencoder, self.tokenizer = None, None, None
         ek = p.get("eval_kwargs", {})
         self.mask_th = ek.get("mask_th", 0.5)

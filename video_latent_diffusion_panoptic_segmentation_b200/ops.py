@@ -46,7 +46,8 @@ def gemm(a1, w, out=None, *, a2=None, taps=1, bias=None, rowbias=None, residual=
          qkv=None, ln=None, n_store=0):
     """out = epilogue(conv/gemm(a1 ++ a2, w)). a1/a2: [B,H,W,C] or [rows,C] bf16; w: [N, taps*(c1+c2)] bf16.
 
-    qkv = dict(q=, k=, vt=, heads=, head_dim=, dpad=, seq=, seq_pad=) for LDM_GEMM_QKV_SPLIT;
+    qkv = dict(q=, k=, vt=, heads=, head_dim=, dpad=, seq=, seq_pad=[, part0=]) for LDM_GEMM_QKV_SPLIT (part0 and the
+    number of C-wide column blocks of w select which of q / k / v are written: see ldm_gemm_desc.qkv_part0);
     ln = (gamma, beta, eps) for LDM_GEMM_CONVT_LN_SILU.
     """
     _chk(a1, bf16, "a1"); _chk(a2, bf16, "a2"); _chk(w, bf16, "w"); _chk(bias, f32, "bias")
@@ -68,11 +69,12 @@ def gemm(a1, w, out=None, *, a2=None, taps=1, bias=None, rowbias=None, residual=
         raise L.LdmError(f"gemm: weight K={w.shape[1]} != taps*(c1+c2)={taps * (d.c1 + d.c2)}")
     if flags & L.LDM_GEMM_QKV_SPLIT:
         for k_ in ("q", "k", "vt"):
-            _chk(qkv[k_], bf16, k_)
-        d.q, d.k, d.vt = _p(qkv["q"]), _p(qkv["k"]), _p(qkv["vt"])
+            _chk(qkv.get(k_), bf16, k_)
+        d.q, d.k, d.vt = _p(qkv.get("q")), _p(qkv.get("k")), _p(qkv.get("vt"))
         d.heads, d.head_dim, d.dpad = qkv["heads"], qkv["head_dim"], qkv["dpad"]
         d.seq, d.seq_pad = qkv["seq"], qkv["seq_pad"]
-        d.vt_rows = qkv["vt"].shape[1]
+        d.vt_rows = qkv["vt"].shape[1] if qkv.get("vt") is not None else 0
+        d.qkv_part0 = qkv.get("part0", 0)
     else:
         _chk(out, f32 if flags & (L.LDM_GEMM_OUT_F32 | L.LDM_GEMM_OUT_NCHW_F32) else bf16, "out")
         d.out = _p(out)
@@ -98,12 +100,26 @@ def alloc_qkv(B, heads, seq, d, device):
     return dict(q=q, k=k, vt=vt, heads=heads, head_dim=d, dpad=dpad, seq=seq, seq_pad=seq_pad)
 
 
-def flash_attn(q, k, vt, out, *, B, heads, seq, head_dim, dpad, seq_pad, scale):
+def alloc_kv(B, heads, kv_seq, d, device):
+    """Head-split key / value buffers of a cross-attention context of kv_seq tokens (LDM_GEMM_QKV_SPLIT with part0 = 1
+    writes them; flash_attn(kv_seq=) reads them): k [B*heads, kv_seq, dpad], vt [B*heads, vt_rows, seq_pad]."""
+    dpad, seq_pad = (d + 63) // 64 * 64, (kv_seq + 7) // 8 * 8
+    rows = (d + 15) // 16 * 16
+    k = torch.zeros((B * heads, kv_seq, dpad), dtype=bf16, device=device)
+    vt = torch.zeros((B * heads, rows, seq_pad), dtype=bf16, device=device)
+    if rows != d:
+        vt[:, d, :kv_seq] = 1.0
+    return dict(k=k, vt=vt, heads=heads, head_dim=d, dpad=dpad, seq=kv_seq, seq_pad=seq_pad)
+
+
+def flash_attn(q, k, vt, out, *, B, heads, seq, head_dim, dpad, seq_pad, scale, kv_seq=0):
+    """kv_seq > 0: cross-attention, k [B*heads, kv_seq, dpad], vt [B*heads, vt_rows, seq_pad >= kv_seq]."""
     for t, n in ((q, "q"), (k, "k"), (vt, "vt"), (out, "out")):
         _chk(t, bf16, n)
     d = L.AttnDesc()
     d.q, d.k, d.vt, d.out = _p(q), _p(k), _p(vt), _p(out)
     d.B, d.heads, d.seq, d.head_dim, d.dpad, d.seq_pad, d.scale = B, heads, seq, head_dim, dpad, seq_pad, scale
+    d.kv_seq = kv_seq
     d.vt_rows = vt.shape[1]
     L.check(L.lib().ldm_flash_attn_fwd(C.byref(d), _stream()), "ldm_flash_attn_fwd")
     return out

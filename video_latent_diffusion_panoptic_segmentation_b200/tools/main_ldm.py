@@ -79,10 +79,18 @@ def build_models(p, device, seed=0):
             latent_channels=vk["latent_channels"], num_upscalers=vk["num_upscalers"],
             upscale_channels=vk["upscale_channels"]))
     unet = UNet(device=device)
-    unet.load_state_dict(unet_init.random_unet_state_dict(seed=seed, in_channels=4))  # stands in for from_pretrained
-    if p["train_kwargs"].get("image_descriptors", "remove") != "remove":
-        raise NotImplementedError("image_descriptors != remove needs cross-attention (SURVEY section 8(f) rank 4)")
-    unet.remove_cross_attention()
+    desc = p["train_kwargs"].get("image_descriptors", "remove")
+    # stands in for from_pretrained (SD-1.4 has cross_attention_dim 768; without it the attn2 weights are not drawn)
+    unet.load_state_dict(unet_init.random_unet_state_dict(seed=seed, in_channels=4,
+                                                          cross_attention_dim=None if desc == "remove" else 768))
+    if desc == "remove":        # descriptors.py:93-95
+        unet.remove_cross_attention()
+    elif desc == "learnable":   # descriptors.py:89-91: 128 learnable object queries are the cross-attention context
+        torch.manual_seed(seed + 2)
+        unet.define_learnable_embeddings(128, 768)
+    else:
+        raise NotImplementedError(f"image_descriptors={desc!r} needs a CLIP text / vision encoder, which is outside "
+                                  "this path (SURVEY section 8(f) rank 4 covers the UNet's cross-attention itself)")
     torch.manual_seed(seed)
     unet.modify_encoder(**p["model_kwargs"])
     unet.freeze_layers(p["train_kwargs"].get("freeze_layers", []))
@@ -131,7 +139,8 @@ def main_worker(gpu, ngpus_per_node, cfg_dist, p, name="b200"):
     if p.get("load_path"):
         data = torch.load(p["load_path"], map_location="cpu")
         unet.load_state_dict(data["unet"])
-        unet.remove_cross_attention()
+        if p["train_kwargs"].get("image_descriptors", "remove") == "remove":
+            unet.remove_cross_attention()
         if "vae_semseg" in data:
             vae.load_state_dict({k.replace("module.", ""): v for k, v in data["vae_semseg"].items()})
     res = trainer.compute_metrics(["pq"], threshold_output=True, save_images=False, seed=42,
