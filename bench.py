@@ -6,7 +6,8 @@
         bench.py --gpus N --steps K --warmup W
 
 One "step" = one pass of the hot path over one batch of 8 synthetic 384x1248 frames per GPU (configs[1]):
-noise -> 50 x (UNet, DDIM update) -> seg-AE decode -> fused argmax/threshold ids -> merge -> PQ statistics.
+noise -> 50 x (UNet, DDIM update) -> seg-AE decode -> fused argmax/threshold ids -> merge -> PQ statistics -> DVPQ
+statistics over the clip formed by all ranks' frames (windows of 2 frames; halo all_gather + stats all_reduce).
 Rank 0 prints ONE JSON line (see DESIGN.md "Measurement" for every field).
 """
 import argparse
@@ -33,7 +34,8 @@ def config_dict(frames_per_gpu, ddim_steps, world):
     """`config` of the JSON line -- shared by both arms (the reference arm times a bounded sample of this workload)."""
     return {"workload": f"LDMSeg sampler, batch {frames_per_gpu} frames 384x1248 per GPU, DDIM {ddim_steps} steps, "
                         "random-init UNet (815M, SD-1.4 topology, self-attn only) + seg-AE, bf16 storage / fp32 "
-                        "accumulate, incl. AE decode, ids, merge, PQ stats",
+                        "accumulate, incl. AE decode, ids, merge, PQ stats and DVPQ stats (windows of 2 frames over the "
+                        "clip formed by all ranks' frames: halo all_gather + stats all_reduce)",
             "frames_per_gpu": frames_per_gpu, "ddim_steps": ddim_steps,
             "parallelism": f"frames sharded over {world} GPU(s)",
             "l2": "per-step working set (weights 1.6 GB + activations) exceeds the 126 MB L2"}
@@ -130,11 +132,17 @@ class CpuReference:
             _, cleaned, _ = self.LO.logits_to_panoptic(logits[0], 0.5, 512, 0.5, 127)
         ev = EO.CityscapesPQOracle()
         ev.add_image(cleaned, self.gt)
+        # one DVPQ window of 2 frames per frame, as in our arm (the clip's frames are this frame repeated)
+        void = cleaned < 0
+        pc = np.where(void, 19, cleaned % 19).astype(np.int32)
+        pi = np.where(void, 0, cleaned // 19).astype(np.int32)
+        gc, gi = self.gt.astype(np.int32), np.zeros_like(self.gt, dtype=np.int32)
+        EO.dvpq_window([pc, pc], [pi, pi], [gc, gc], [gi, gi])
         return time.perf_counter() - t0
 
     def describe(self, t_unet, t_tail, n):
         return (f"1 frame 384x1248 on {self.threads} host threads: {n} of {self.T} DDIM iterations timed (UNet fp32 + "
-                f"scheduler, {t_unet:.2f} s each) + seg-AE decode + ids/merge + PQ ({t_tail:.2f} s), "
+                f"scheduler, {t_unet:.2f} s each) + seg-AE decode + ids/merge + PQ + one DVPQ window ({t_tail:.2f} s), "
                 f"extrapolated to {self.T} iterations per frame; fp32 CPU port of the reference path (the reference's "
                 f"diffusers UNet is not installable here, the oracle restatement stands in)")
 
@@ -211,6 +219,18 @@ def run_ours(args):
     ids_host = torch.empty((B, H, W), dtype=torch.int32).pin_memory()
 
     evaluator = CityscapesPanopticEvaluator(device=dev)
+    from video_latent_diffusion_panoptic_segmentation_b200.eval import clip_dvpq as CD
+    gt_ins_dev = torch.zeros_like(gt_dev)
+
+    def dvpq_stats(cleaned, gt_cat):
+        """DVPQ over the clip formed by all ranks' frames (configs[2]): rank r holds frames [r*B, (r+1)*B); windows of
+        2 frames, the halo frame comes from the next rank (all_gather), the statistics are all-reduced / gathered.
+        The class-agnostic ids of the LDMSeg head are split into (cat, ins) = (id % 19, id // 19), void -> class 19: synthetic
+        glue of this benchmark (a few int32 element-wise torch ops), not part of the library."""
+        void = cleaned < 0
+        pc = torch.where(void, torch.full_like(cleaned, 19), cleaned % 19)  # class 19: outside the 19 evaluated classes
+        pi = torch.where(void, torch.zeros_like(cleaned), cleaned // 19)
+        return CD.dvpq_clip_sharded(pc, pi, gt_cat, gt_ins_dev, n_frames=world * B, eval_frames=2)
 
     def step(resident):
         evaluator.reset()
@@ -225,6 +245,7 @@ def run_ours(args):
         if world > 1:
             reduce_evaluator_(evaluator, dev)
         res = evaluator.evaluate()
+        res["dvpq"] = dvpq_stats(cleaned, gt)
         if not resident:
             ids_host.copy_(cleaned, non_blocking=True)  # the panoptic ids a caller reads back
             torch.cuda.current_stream().synchronize()
@@ -265,7 +286,7 @@ def run_ours(args):
 
     # where one step spends its time (one extra, untimed-for-the-metric step with CUDA events between the phases)
     def phases():
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
         evaluator.reset()
         ev[0].record()
         lat = tr.sample([""] * B, T, seed=None, rgb_latents=rgb_dev, scheduler=sched, noise=noise_host)
@@ -276,9 +297,11 @@ def run_ours(args):
             evaluator.add_image(cleaned[b], gt_dev[b])
         evaluator.evaluate()
         ev[3].record()
+        dvpq_stats(cleaned, gt_dev)
+        ev[4].record()
         torch.cuda.synchronize()
         return {"sampler_50xunet_ddim": ev[0].elapsed_time(ev[1]), "ae_decode_ids_merge": ev[1].elapsed_time(ev[2]),
-                "pq_evaluator": ev[2].elapsed_time(ev[3])}
+                "pq_evaluator": ev[2].elapsed_time(ev[3]), "dvpq_clip_k2": ev[3].elapsed_time(ev[4])}
 
     phase_ms = phases()
     hbm, tf_burst, tf_sus, which = peaks()
@@ -291,6 +314,9 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(ids_host.numel() * 4)},
             "gpu_launches": int(graph_launches + eager_launches),
             "clocks": clocks, "pq": {k: res[k] for k in ("pq", "tp", "fp", "fn")},
+            "dvpq": {"pq": float(res["dvpq"]["pq"]), "windows": int(res["dvpq"]["n_windows"]),
+                     "tp": int(res["dvpq"]["tp"].sum()), "fn": int(res["dvpq"]["fn"].sum()),
+                     "fp": int(res["dvpq"]["fp"].sum())},
             "phases_ms_per_step": {k: round(v, 2) for k, v in phase_ms.items()}}
 
     if rank == 0:

@@ -271,6 +271,12 @@ int ldm_pan_insert(const int32_t* sem, const int32_t* labels, int32_t target, in
 int ldm_id_mask(int32_t* x, const int32_t* a, int32_t va, const int32_t* b, int32_t vb, int32_t fill, int64_t n,
                 ldm_stream_t stream);
 
+/* pan[i] = cat[i] * max_ins + ins[i]: the panoptic id of eval/eval_dvpq.py:108-121 (`pan = cat * max_ins + ins` for the
+ * prediction and the ground truth of a window) on device-resident id maps. Values must fit int32 (cat <= 255,
+ * max_ins = 2^20 in the reference). */
+int ldm_pan_combine(const int32_t* cat, const int32_t* ins, int32_t max_ins, int32_t* pan, int64_t n,
+                    ldm_stream_t stream);
+
 /* Depth-aware masking of a DVPQ window (eval/eval_dvpq.py:123-145: `depth_mask = depth_gts > 0`, abs-rel error,
  * `pred_in_depth_mask[ignored_pred_mask] = 19 * max_ins`). For every pixel of the [H, Wd] depth maps with depth_gt > 0:
  *   rel = |depth_pred - depth_gt| / depth_gt in float64, with numpy's arithmetic of the PNG sample type -- elem_bits 8 / 16:

@@ -151,3 +151,79 @@ def test_stats_reduction_world_size_2_gloo():
         assert fnc == {3: 0, 7: 0, 11: 1}
         assert iouc[11] == 0.05 + 0.4
     assert res[0][1:] == res[1][1:]
+
+
+# ------------------------------------------------------------------------------------------- sharded clip DVPQ (8e)
+def _clip(n_frames, H=40, W=56, seed=3):
+    """Synthetic clip: per frame (pred_cat, pred_ins, gt_cat, gt_ins) int32 maps with drifting Voronoi tubes."""
+    from synth import synth_panoptic
+    rng = np.random.default_rng(seed)
+    _, cat0, ins0 = synth_panoptic(rng, H, W + 2 * n_frames, n_seeds=14)
+    out = []
+    for f in range(n_frames):
+        gc, gi = cat0[:, 2 * f:2 * f + W].copy(), ins0[:, 2 * f:2 * f + W].copy()
+        pc, pi = np.roll(gc, (1, 2), axis=(0, 1)).copy(), np.roll(gi, (1, 2), axis=(0, 1)).copy()
+        flip = rng.random((H, W)) < 0.04
+        pc[flip], pi[flip] = 5, 7
+        pc[pc == 255], pi[pc == 255] = 3, 1
+        out.append((pc, pi, gc, gi))
+    return [np.stack([fr[j] for fr in out]).astype(np.int32) for j in range(4)]
+
+
+def _oracle_eval_fn(pc, pi, gc, gi, dp, dg):
+    from oracle import eval_oracle as EO
+    k = pc.shape[0]
+    return EO.dvpq_window([pc[j].numpy() for j in range(k)], [pi[j].numpy() for j in range(k)],
+                          [gc[j].numpy() for j in range(k)], [gi[j].numpy() for j in range(k)])
+
+
+def _clip_worker(rank, world, port, n_frames, k, q):
+    import torch.distributed as dist
+    from video_latent_diffusion_panoptic_segmentation_b200.eval import clip_dvpq as CD
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    maps = _clip(n_frames)
+    lo, hi = CD.shard_range(n_frames, rank, world)
+    local = [torch.from_numpy(m[lo:hi]) for m in maps]
+    res = CD.dvpq_clip_sharded(*local, n_frames=n_frames, eval_frames=k, eval_fn=_oracle_eval_fn)
+    q.put((rank, res["pq"], res["iou"].tolist(), res["tp"].tolist(), res["fn"].tolist(), res["fp"].tolist(),
+           res["n_windows"]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_frames,k", [(2, 8, 2), (3, 7, 3), (4, 5, 3)])
+def test_clip_dvpq_sharded_gloo_matches_single_process(world, n_frames, k):
+    """frames sharded contiguously, the k-1 frame halo from the following shard(s) (a halo may span several
+    short or empty shards), windows evaluated by the owner of their first frame, integer counts all-reduced, float rows
+    gathered in window order: bit-identical to the reference's single-process aggregation (eval_dvpq.py:153-210)."""
+    from oracle import eval_oracle as EO
+    from video_latent_diffusion_panoptic_segmentation_b200.ldmseg.evaluations.new_eval import aggregate
+    maps = _clip(n_frames)
+    rows = [EO.dvpq_window(*[[m[i + j] for j in range(k)] for m in maps]) for i in range(n_frames - k + 1)]
+    want = aggregate(rows)
+    assert want["tp"].sum() > 0 and want["fp"].sum() + want["fn"].sum() > 0
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + 7 * world + n_frames) % 2000
+    procs = [ctx.Process(target=_clip_worker, args=(r, world, port, n_frames, k, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in res:
+        assert r[1] == want["pq"] and r[2] == want["iou"].tolist()  # bit-identical float64
+        assert r[3] == want["tp"].tolist() and r[4] == want["fn"].tolist() and r[5] == want["fp"].tolist()
+        assert r[6] == n_frames - k + 1
+
+
+def test_shard_range_covers_every_frame_once():
+    from video_latent_diffusion_panoptic_segmentation_b200.eval.clip_dvpq import shard_range
+    for n in (1, 5, 8, 1101):
+        for world in (1, 2, 3, 8):
+            seen = []
+            for r in range(world):
+                lo, hi = shard_range(n, r, world)
+                seen += list(range(lo, hi))
+            assert seen == list(range(n))

@@ -465,3 +465,40 @@ def test_resized_cropped_tail_vs_reference_chain(models):
         assert mism < 2e-3, f"image {b}: {mism:.4%} of the ids differ from the reference chain"
         mism_c = float((cleaned[0].cpu().numpy() != cl).mean())
         assert mism_c < 1e-2, f"image {b}: {mism_c:.4%} of the merged ids differ"
+
+
+def test_clip_dvpq_device_windows_match_reference_logic():
+    """SURVEY 8e / H9 on device-resident id maps: windows of k stacked frames through ldm_pan_combine + ldm_joint_hist
+    (+ ldm_depth_mask_pred) against the restated eval_dvpq.py window logic (width-concatenated numpy arrays), bit-exact
+    for the four per-class arrays; then the whole-clip aggregate for k = 1, 2, 3."""
+    from oracle import eval_oracle as EO
+    from test_host_cpu import _clip
+    from video_latent_diffusion_panoptic_segmentation_b200.eval import clip_dvpq as CD
+    from video_latent_diffusion_panoptic_segmentation_b200.ldmseg.evaluations.new_eval import aggregate
+    n_frames = 6
+    maps = _clip(n_frames, H=48, W=64, seed=11)
+    dev_maps = [torch.from_numpy(m).to(DEV) for m in maps]
+    rng = np.random.default_rng(5)
+    dg = rng.integers(0, 4000, size=maps[0].shape).astype(np.uint16)
+    dg[rng.random(dg.shape) < 0.2] = 0
+    dp = (dg.astype(np.float64) * rng.uniform(0.6, 1.5, size=dg.shape)).astype(np.uint16)
+    for k in (1, 2, 3):
+        rows = [EO.dvpq_window(*[[m[i + j] for j in range(k)] for m in maps]) for i in range(n_frames - k + 1)]
+        want = aggregate(rows)
+        got = CD.dvpq_clip_sharded(*dev_maps, n_frames=n_frames, eval_frames=k)
+        assert got["n_windows"] == n_frames - k + 1
+        for key in ("iou", "tp", "fn", "fp"):
+            assert np.array_equal(got[key], want[key]), (k, key)
+        assert got["pq"] == want["pq"] and got["pq_things"] == want["pq_things"]
+    # depth-aware windows (uint16 samples, wrap-around arithmetic of the reference)
+    k, th = 2, 0.25
+    rows = [EO.dvpq_window(*[[m[i + j] for j in range(k)] for m in maps],
+                           depth_pred=[dp[i + j] for j in range(k)], depth_gt=[dg[i + j] for j in range(k)],
+                           depth_thres=th) for i in range(n_frames - k + 1)]
+    want = aggregate(rows)
+    got = CD.dvpq_clip_sharded(*dev_maps, n_frames=n_frames, eval_frames=k,
+                               depth_pred=torch.from_numpy(dp.astype(np.int32)).to(DEV),
+                               depth_gt=torch.from_numpy(dg.astype(np.int32)).to(DEV), depth_thres=th, depth_bits=16)
+    for key in ("iou", "tp", "fn", "fp"):
+        assert np.array_equal(got[key], want[key]), ("depth", key)
+    assert abs(got["abs_rel"] - want["abs_rel"]) <= 1e-12 * abs(want["abs_rel"])

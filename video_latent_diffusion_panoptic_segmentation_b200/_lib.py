@@ -87,6 +87,7 @@ SIGNATURES = {
     "ldm_ccl_label4": (C.c_int, [c_vp, c_i32, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
     "ldm_joint_hist": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i32, c_vp, c_vp]),
     "ldm_pan_insert": (C.c_int, [c_vp, c_vp, c_i32, c_i32, c_vp, c_i64, c_vp]),
+    "ldm_pan_combine": (C.c_int, [c_vp, c_vp, c_i32, c_vp, c_i64, c_vp]),
     "ldm_id_mask": (C.c_int, [c_vp, c_vp, c_i32, c_vp, c_i32, c_i32, c_i64, c_vp]),
     "ldm_depth_mask_pred": (C.c_int, [c_vp, c_i32, c_vp, c_vp, c_i32, c_i32, c_i32, C.c_double, c_i32, c_vp, c_vp, c_i32,
                                       c_vp]),

@@ -69,7 +69,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   uint64_t* p_full = s_full + 2;         // [NQ]
   uint64_t* o_full = p_full + 2;         // [NQ]
   uint64_t* s_free = o_full + 2;         // [NQ]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
+  uint64_t* o_done = s_free + 2;         // [NQ] completes ONCE, when the last block's PV MMAs have landed (see the final wait)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
 
   // warp-uniform by construction, so that the control warps' loops run with uniform control flow (see gemm_tc.cu)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -87,6 +88,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       mbar_init(&s_full[g], 1);
       mbar_init(&p_full[g], 128);
       mbar_init(&o_full[g], 1);
+      mbar_init(&o_done[g], 1);
       mbar_init(&s_free[g], 128);
     }
     for (int s = 0; s < STAGES; ++s) {
@@ -172,6 +174,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             umma_bf16_ts(d_tmem, pa + kk * 8, db, idesc_o, blk > 0 || kk != 0);
           }
           umma_commit(&o_full[g]);
+          if (blk == nblk - 1) umma_commit(&o_done[g]);
         }
         __syncwarp();
       };
@@ -325,7 +328,11 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       mbar_arrive(&p_full[g]);
       TRACE(4, j);
     }
-    mbar_wait(&o_full[g], (nblk - 1) & 1);
+    // NOT o_full with the parity of the last block: a softmax thread never waits for a PV MMA inside the loop, so here
+    // it can be TWO commits ahead of the tensor pipe (s_full of block j only implies PV of block j-2), and a parity wait
+    // cannot tell "phase nblk-3 complete" from "phase nblk-1 complete" -- a fast warp then read O without the last two
+    // blocks (seen as a run-to-run difference of one warp's rows). o_done has a single phase.
+    mbar_wait(&o_done[g], 0);
     tc_fence_after();
     float o_acc[Cfg::kDN];
     {

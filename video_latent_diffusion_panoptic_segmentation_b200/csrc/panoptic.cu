@@ -429,6 +429,11 @@ __global__ void pan_insert_kernel(const int32_t* __restrict__ sem, const int32_t
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     if (sem[i] == target) pan[i] = target * max_ins + labels[i];
 }
+__global__ void pan_combine_kernel(const int32_t* __restrict__ cat, const int32_t* __restrict__ ins, int max_ins,
+                                   int32_t* __restrict__ pan, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    pan[i] = cat[i] * max_ins + ins[i];
+}
 __global__ void id_mask_kernel(int32_t* x, const int32_t* a, int va,
                                const int32_t* b, int vb, int fill, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -579,6 +584,15 @@ extern "C" int ldm_pan_insert(const int32_t* sem, const int32_t* labels, int32_t
   pan_insert_kernel<<<grid1d(n, 256), 256, 0, as_stream(stream)>>>(sem, labels, target, max_ins, pan, n);
   count_launch();
   return check_launch("pan_insert_kernel");
+}
+
+extern "C" int ldm_pan_combine(const int32_t* cat, const int32_t* ins, int32_t max_ins, int32_t* pan, int64_t n,
+                               ldm_stream_t stream) {
+  using namespace ldm_host;
+  LDM_REQUIRE(cat && ins && pan && n > 0 && max_ins > 0, LDM_ERR_BAD_ARG, "ldm_pan_combine: bad arg");
+  pan_combine_kernel<<<grid1d(n, 256), 256, 0, as_stream(stream)>>>(cat, ins, max_ins, pan, n);
+  count_launch();
+  return check_launch("pan_combine_kernel");
 }
 
 // Depth-aware masking of DVPQ (eval/eval_dvpq.py:123-145). One thread per depth pixel; the per-CTA (sum, count) of the

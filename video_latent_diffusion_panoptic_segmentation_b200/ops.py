@@ -327,6 +327,16 @@ def joint_hist(a, b, capacity=1 << 14):
     return av[order], bv[order], c[order]
 
 
+def pan_combine(cat, ins, max_ins, pan=None):
+    """pan = cat * max_ins + ins on int32 device maps (eval_dvpq.py:108-121)."""
+    _chk(cat, i32, "cat"); _chk(ins, i32, "ins")
+    if pan is None:
+        pan = torch.empty_like(cat)
+    _chk(pan, i32, "pan")
+    L.check(L.lib().ldm_pan_combine(_p(cat), _p(ins), max_ins, _p(pan), cat.numel(), _stream()), "ldm_pan_combine")
+    return pan
+
+
 def pan_insert(sem, labels, target, max_ins, pan):
     _chk(sem, i32, "sem"); _chk(labels, i32, "labels"); _chk(pan, i32, "pan")
     L.check(L.lib().ldm_pan_insert(_p(sem), _p(labels), target, max_ins, _p(pan), sem.numel(), _stream()),
