@@ -304,6 +304,28 @@ def run_ours(args):
                 "pq_evaluator": ev[2].elapsed_time(ev[3]), "dvpq_clip_k2": ev[3].elapsed_time(ev[4])}
 
     phase_ms = phases()
+
+    def rgb_vae_encode_ms():
+        """The step in front of the metric's timed region (excluded from the metric by 8d): B frames
+        of 384x1248 through the RGB VAE encoder (random-init SD-1.4 VAE), CUDA events, reported for context only."""
+        from video_latent_diffusion_panoptic_segmentation_b200.ldmseg.models import GeneralVAEImage, unet_init
+        vim = GeneralVAEImage.from_pretrained(state_dict=unet_init.random_vae_image_state_dict(seed=2), device=dev)
+        img = torch.rand((B, 3, H, W), device=dev)
+        for _ in range(2):
+            vim.encode_moments(img, scale=2.0, shift=-1.0)
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            vim.encode_moments(img, scale=2.0, shift=-1.0)
+        b_.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b_) / 3
+
+    try:
+        vae_ms = rgb_vae_encode_ms() if rank == 0 else None
+    except Exception as e:  # context only: never take the measurement down
+        vae_ms = f"failed: {e!r}"
+    torch.cuda.empty_cache()
     hbm, tf_burst, tf_sus, which = peaks()
     line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -317,7 +339,8 @@ def run_ours(args):
             "dvpq": {"pq": float(res["dvpq"]["pq"]), "windows": int(res["dvpq"]["n_windows"]),
                      "tp": int(res["dvpq"]["tp"].sum()), "fn": int(res["dvpq"]["fn"].sum()),
                      "fp": int(res["dvpq"]["fp"].sum())},
-            "phases_ms_per_step": {k: round(v, 2) for k, v in phase_ms.items()}}
+            "phases_ms_per_step": {k: round(v, 2) for k, v in phase_ms.items()},
+            "rgb_vae_encode_ms_per_batch": vae_ms}
 
     if rank == 0:
         # roofline of the dominant kernel (gemm_tc_kernel: linear / conv1x1 / implicit conv3x3), measured live with
@@ -334,9 +357,10 @@ def run_ours(args):
         gm = by.get("gemm", {"ms": 1e-9, "flops": 0, "n": 1})
         ach = gm["flops"] / (gm["ms"] / 1e3) / 1e12
         traffic = None  # DRAM bytes per launch of the contraction kernel, from the committed ncu capture of one forward
-        tpath = os.path.join(ROOT, "profiles", "r01g_unet_forward_traffic.json")
-        if os.path.exists(tpath):
-            tj = json.load(open(tpath))
+        import glob
+        tpaths = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_unet_forward_traffic.json")))  # latest round's capture
+        if tpaths:
+            tj = json.load(open(tpaths[-1]))
             if "gemm_tc_kernel" in tj:
                 traffic = tj["gemm_tc_kernel"]["dram_bytes_per_launch"]
         line["roofline"] = {"bound": "tensor", "kernel": "gemm_tc_kernel", "achieved": ach, "peak": tf_sus,

@@ -101,6 +101,17 @@ def test_modify_encoder_matches_oracle():
     assert tuple(m.config.block_out_channels) == (64, 128, 256, 256)
 
 
+def test_vae_image_param_shapes_match_oracle_module():
+    from oracle import vae_image_oracle as VO
+    net = VO.VAEImageOracle()
+    want = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    got = unet_init.vae_image_param_shapes()
+    assert got == want and sum(int(np.prod(v)) for v in got.values()) == 34163664
+    with_cross = unet_init.unet_param_shapes(block_out_channels=(64, 128, 256, 256), cross_attention_dim=768)
+    ref = UO.UNetOracle(block_out_channels=(64, 128, 256, 256), cross_attention_dim=768)
+    assert with_cross == {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+
+
 def test_unet_forward_without_gpu_fails_loudly():
     cfg = dict(block_out_channels=(64, 128, 256, 256))
     m = UNet(device="cpu", **cfg)

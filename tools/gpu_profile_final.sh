@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-end evidence: launch list of the bench command, per-launch DRAM traffic of one UNet forward, ncu --set full of the top kernels.
 set -u
-TAG=${1:-r01g}
+TAG=${1:-r01h}
 mkdir -p gpurun_out
 BENCH="python bench.py --steps 1 --warmup 3 --no-cpu-baseline"
 $BENCH > gpurun_out/${TAG}_bench_plain.log 2>&1 && \
@@ -15,3 +15,7 @@ PK="python tools/profile_kernels.py --iters 1 --only attn_L0,gemm1x1_res_L0,gemm
 $PK > gpurun_out/pk_plain.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:'flash_attn|gemm_tc|gn_|layernorm' -o gpurun_out/${TAG}_top_kernels $PK > gpurun_out/ncu_full.log 2>&1
 echo "ncu full rc=$?"
+# context numbers outside the metric: the configs[4] frame size (768x2496) and the RGB VAE encoder in front of the sampler
+timeout 600 python tools/time_unet_k2.py 2 > gpurun_out/${TAG}_unet_k2.json 2> gpurun_out/k2.err; echo "k2 rc=$?"
+timeout 300 python tools/time_vae_image.py > gpurun_out/${TAG}_vae_image.json 2> gpurun_out/vae.err; echo "vae rc=$?"
+timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/${TAG}_bench_full.log 2> gpurun_out/${TAG}_bench_full.err; echo "bench rc=$?"

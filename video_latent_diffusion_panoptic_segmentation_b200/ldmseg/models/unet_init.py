@@ -107,6 +107,50 @@ def seg_decoder_param_shapes(out_channels=128, int_channels=256, latent_channels
     return S
 
 
+def vae_image_param_shapes(in_channels=3, latent_channels=4, block_out_channels=(128, 256, 512, 512),
+                           layers_per_block=2, **unused):
+    """encoder.* / quant_conv.* keys of diffusers' AutoencoderKL (SD-1.4 vae/config.json) -- the half of
+    GeneralVAEImage that tools/main_ldm.py:138-140 keeps."""
+    S = {}
+
+    def conv(name, cin, cout, k):
+        S[name + ".weight"], S[name + ".bias"] = (cout, cin, k, k), (cout,)
+
+    def lin(name, cin, cout):
+        S[name + ".weight"], S[name + ".bias"] = (cout, cin), (cout,)
+
+    def norm(name, c):
+        S[name + ".weight"], S[name + ".bias"] = (c,), (c,)
+
+    def resnet(name, cin, cout):
+        norm(name + ".norm1", cin)
+        conv(name + ".conv1", cin, cout, 3)
+        norm(name + ".norm2", cout)
+        conv(name + ".conv2", cout, cout, 3)
+        if cin != cout:
+            conv(name + ".conv_shortcut", cin, cout, 1)
+
+    boc = list(block_out_channels)
+    conv("encoder.conv_in", in_channels, boc[0], 3)
+    c = boc[0]
+    for i, co in enumerate(boc):
+        for j in range(layers_per_block):
+            resnet(f"encoder.down_blocks.{i}.resnets.{j}", c if j == 0 else co, co)
+        if i < len(boc) - 1:
+            conv(f"encoder.down_blocks.{i}.downsamplers.0.conv", co, co, 3)
+        c = co
+    resnet("encoder.mid_block.resnets.0", c, c)
+    resnet("encoder.mid_block.resnets.1", c, c)
+    a = "encoder.mid_block.attentions.0"
+    norm(a + ".group_norm", c)
+    for n in ("to_q", "to_k", "to_v", "to_out.0"):
+        lin(f"{a}.{n}", c, c)
+    norm("encoder.conv_norm_out", c)
+    conv("encoder.conv_out", c, 2 * latent_channels, 3)
+    conv("quant_conv", 2 * latent_channels, 2 * latent_channels, 1)
+    return S
+
+
 def random_state_dict(shapes, seed=0, transposed_conv_keys=()):
     g = torch.Generator().manual_seed(seed)
     sd = {}
@@ -134,3 +178,7 @@ def random_seg_decoder_state_dict(seed=1, **cfg):
     n_up = cfg.get("num_upscalers", 2)
     tkeys = tuple(f"decoder.{2 + 3 * i}" for i in range(n_up))
     return random_state_dict(shapes, seed, transposed_conv_keys=tkeys)
+
+
+def random_vae_image_state_dict(seed=2, **cfg):
+    return random_state_dict(vae_image_param_shapes(**cfg), seed)
