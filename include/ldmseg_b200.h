@@ -35,7 +35,7 @@ enum ldm_status {
   LDM_ERR_DRIVER = -6
 };
 
-int ldm_abi_version(void);
+int ldm_abi_version(void); /* 2 since ldm_gemm_desc.qkv_part0 / ldm_attn_desc.kv_seq were added */
 const char* ldm_last_error(void);
 /* 0 when the current device is compute capability 10.0 (B200); LDM_ERR_ARCH otherwise. */
 int ldm_check_device(void);
@@ -195,6 +195,13 @@ int ldm_conv_out(const void* x, const float* w, const float* bias, float* out, i
  * prev_sample / pred_x0 may be NULL.  */
 int ldm_ddim_step(const float* eps, const float* sample, const float* coef, const int32_t* t_index,
                   float* prev_sample, float* pred_x0, int64_t n, ldm_stream_t stream);
+
+/* The same with classifier-free guidance in front (trainers_ldm_cond.py:1147-1149, `noise_pred_uncond + guidance_scale *
+ * (noise_pred_text - noise_pred_uncond)`, fp32, the reference's three roundings): eps_uncond / eps_text are the two
+ * halves of the doubled batch's UNet output; eps_text == NULL is ldm_ddim_step. */
+int ldm_ddim_step_cfg(const float* eps_uncond, const float* eps_text, float guidance_scale, const float* sample,
+                      const float* coef, const int32_t* t_index, float* prev_sample, float* pred_x0, int64_t n,
+                      ldm_stream_t stream);
 
 /* Layout helpers (NHWC bf16). */
 int ldm_upsample_nearest(const void* x, void* out, int32_t B, int32_t h, int32_t w, int32_t C, int32_t oh,

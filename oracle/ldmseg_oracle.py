@@ -138,8 +138,10 @@ def build_seg_decoder(seed=0, **kw):
 # ------------------------------------------------------------------------------------------------ sampler
 @torch.no_grad()
 def sample(unet, scheduler, rgb_latents, num_inference_steps=50, seed=None, self_condition=False,
-           return_all_latents=False, noise=None):
-    """trainers_ldm_cond.py:1048-1173 with image_descriptors=remove (no guidance, multiplier 1).
+           return_all_latents=False, noise=None, context=None, uncond_context=None, guidance_scale=7.5):
+    """trainers_ldm_cond.py:1048-1173. Default: image_descriptors=remove (no guidance, multiplier 1). With `context`
+    [B,L,dim] the UNet gets encoder_hidden_states; with `uncond_context` too, the batch is doubled [uncond | text]
+    and the prediction is uncond + guidance_scale * (text - uncond) (:1110-1122,1129,1147-1149).
     Noise is (B,4,h,w) from rgb_latents.shape[-2:], drawn from a CPU generator as in :1091-1095."""
     scheduler.set_timesteps_inference(num_inference_steps)
     B, _, h, w = rgb_latents.shape
@@ -151,8 +153,15 @@ def sample(unet, scheduler, rgb_latents, num_inference_steps=50, seed=None, self
     steps = list(scheduler.timesteps)
     all_latents = []
     for i, t in enumerate(steps):
-        parts = [latents, rgb_latents] + ([condition] if self_condition else [])
-        eps = unet(torch.cat(parts, dim=1).float(), t, encoder_hidden_states=None)
+        if uncond_context is not None:
+            assert not self_condition
+            inp = torch.cat([torch.cat([latents] * 2), torch.cat([rgb_latents] * 2)], dim=1).float()
+            eps2 = unet(inp, t, encoder_hidden_states=torch.cat([uncond_context, context]).float())
+            eps_uncond, eps_text = eps2.chunk(2)
+            eps = eps_uncond + guidance_scale * (eps_text - eps_uncond)
+        else:
+            parts = [latents, rgb_latents] + ([condition] if self_condition else [])
+            eps = unet(torch.cat(parts, dim=1).float(), t, encoder_hidden_states=context)
         prev, x0 = scheduler.step(eps, t, latents)
         if self_condition:
             condition = x0

@@ -316,6 +316,68 @@ def test_unet_cross_attention_vs_oracle():
     assert _rel(lat, ref) < 8e-2, _rel(lat, ref)
 
 
+class _ToyTokenizer:
+    """Stands in for CLIPTokenizer (a third-party model the reference loads, descriptors.py:99-101): same call contract."""
+    model_max_length = 12
+
+    def __call__(self, texts, padding="max_length", max_length=None, truncation=True, return_tensors="pt"):
+        from types import SimpleNamespace
+        L_ = max_length or self.model_max_length
+        ids = torch.zeros((len(texts), L_), dtype=torch.long)
+        for i, t in enumerate(texts):
+            codes = [1 + (ord(c) % 60) for c in t][:L_]
+            ids[i, :len(codes)] = torch.tensor(codes, dtype=torch.long)
+        return SimpleNamespace(input_ids=ids)
+
+
+class _ToyTextEncoder(torch.nn.Module):
+    """Stands in for CLIPTextModel: input_ids -> (last_hidden_state [B, L, 768],)."""
+
+    def __init__(self):
+        super().__init__()
+        torch.manual_seed(12)
+        self.emb = torch.nn.Embedding(64, 768)
+        self.pos = torch.nn.Parameter(0.1 * torch.randn(12, 768))
+
+    def forward(self, input_ids):
+        return (self.emb(input_ids) + self.pos[None, :input_ids.shape[1]],)
+
+
+def test_sampler_classifier_free_guidance_vs_oracle():
+    """H1 with a text encoder (trainers_ldm_cond.py:1110-1122,1126-1129,1147-1149): doubled batch [uncond | text],
+    encoder_hidden_states through the kept cross-attention, guidance fused into the DDIM kernel."""
+    from oracle import ldmseg_oracle as LO
+    from oracle import unet_oracle as UO
+    from video_latent_diffusion_panoptic_segmentation_b200.ldmseg.models import UNet
+    from video_latent_diffusion_panoptic_segmentation_b200.ldmseg.schedulers import DDIMNoiseScheduler
+    from video_latent_diffusion_panoptic_segmentation_b200.ldmseg.trainers import TrainerDiffusion
+    o_unet = UO.build_unet(seed=8, cross_attention_dim=768)
+    unet = UNet(device=DEV)
+    unet.load_state_dict(o_unet.state_dict())
+    o_unet = o_unet.to(DEV)
+    tok, enc = _ToyTokenizer(), _ToyTextEncoder().to(DEV).eval()
+    B, h, w, T, g = 2, 16, 24, 3, 4.0
+    prompts = ["a car on the road", "two pedestrians"]
+    rgb = (0.18215 * torch.randn((B, 4, h, w), generator=torch.Generator().manual_seed(1234))).to(DEV)
+    tr = TrainerDiffusion(p={}, unet_model=unet, tokenizer=tok, text_encoder=enc,
+                          noise_scheduler=DDIMNoiseScheduler(**SCHED_KW), args={"gpu": 0})
+    lat = tr.sample(prompts, num_inference_steps=T, guidance_scale=g, seed=42, rgb_latents=rgb)
+    with torch.no_grad():
+        ctx = enc(tok(prompts).input_ids.to(DEV))[0]
+        unc = enc(tok([""] * B).input_ids.to(DEV))[0]
+    ref = LO.sample(o_unet, LO.DDIMOracle(), rgb, num_inference_steps=T, seed=42, context=ctx, uncond_context=unc,
+                    guidance_scale=g)
+    ref1 = LO.sample(o_unet, LO.DDIMOracle(), rgb, num_inference_steps=T, seed=42, context=ctx, uncond_context=unc,
+                     guidance_scale=1.0)
+    assert lat.shape == ref.shape == (B, 4, h, w)
+    assert _rel(lat, ref) < 8e-2, _rel(lat, ref)
+    assert _rel(ref1, ref) > 2 * _rel(lat, ref)  # the guidance scale matters more than the error
+    # a UNet whose cross-attention was removed ignores the descriptors, as the reference's does (attn2 is None)
+    unet.remove_cross_attention()
+    lat0 = tr.sample(prompts, num_inference_steps=T, guidance_scale=g, seed=42, rgb_latents=rgb)
+    assert lat0.shape == (B, 4, h, w) and torch.isfinite(lat0).all() and not torch.equal(lat0, lat)
+
+
 def test_tail_ids_bit_exact_given_identical_logits(models):
     """H6/H7: feed the SAME fp32 logits to the CUDA tail and to the restated reference tail."""
     from oracle import ldmseg_oracle as LO

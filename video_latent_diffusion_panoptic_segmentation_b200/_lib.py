@@ -19,6 +19,7 @@ LDM_GEMM_CONVT_LN_SILU = 1 << 4
 LDM_GEMM_OUT_NCHW_F32 = 1 << 5
 
 HASH_EMPTY = 0x8000000000000000
+ABI_VERSION = 2  # must equal ldm_abi_version() of the built library (descriptor struct layouts)
 
 
 class GemmDesc(C.Structure):
@@ -74,6 +75,7 @@ SIGNATURES = {
     "ldm_resize_bilinear_planar": (C.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "ldm_conv_out": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "ldm_ddim_step": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "ldm_ddim_step_cfg": (C.c_int, [c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "ldm_upsample_nearest": (C.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "ldm_im2col3x3_s2": (C.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "ldm_logits_to_ids": (C.c_int, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_i32, c_vp]),
@@ -114,6 +116,9 @@ def load():
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
+        if lib.ldm_abi_version() != ABI_VERSION:
+            raise LdmError(f"{LIB_PATH} has ABI version {lib.ldm_abi_version()}, this binding expects {ABI_VERSION}: "
+                           "rebuild it (python -m video_latent_diffusion_panoptic_segmentation_b200.build)")
         _lib = lib
     return _lib
 

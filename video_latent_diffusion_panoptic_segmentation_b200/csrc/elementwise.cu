@@ -10,9 +10,11 @@ using namespace ldm;
 // Explicit round-to-nearest mul/sub/div/add intrinsics keep the reference's op order (no FMA contraction) so the
 // fp32 result is bit-identical to torch eager on the CPU.
 // `prev` / `x0out` may alias `sample` (in-place update by the sampler loop): no __restrict__ on those.
-__global__ void ddim_step_kernel(const float* __restrict__ eps, const float* sample,
-                                 const float* __restrict__ coef, const int32_t* __restrict__ t_index,
-                                 float* prev, float* x0out, long long n) {
+// With `eps_text` the noise prediction is first combined as classifier-free guidance does (trainers_ldm_cond.py:1147-1149):
+// eps = eps_uncond + g * (eps_text - eps_uncond), three roundings in the reference's order.
+__global__ void ddim_step_kernel(const float* __restrict__ eps, const float* __restrict__ eps_text, float guidance,
+                                 const float* sample, const float* __restrict__ coef,
+                                 const int32_t* __restrict__ t_index, float* prev, float* x0out, long long n) {
   const int ti = t_index ? *t_index : 0;
   const float s1m_at = coef[ti * 4 + 0];   // sqrt(1 - alpha_t)
   const float s_at = coef[ti * 4 + 1];     // sqrt(alpha_t)
@@ -22,7 +24,13 @@ __global__ void ddim_step_kernel(const float* __restrict__ eps, const float* sam
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
     const float4 e = __ldg(reinterpret_cast<const float4*>(eps) + i);
     const float4 x = reinterpret_cast<const float4*>(sample)[i];
-    const float ev[4] = {e.x, e.y, e.z, e.w};
+    float ev[4] = {e.x, e.y, e.z, e.w};
+    if (eps_text) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(eps_text) + i);
+      const float tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ev[j] = __fadd_rn(ev[j], __fmul_rn(guidance, __fsub_rn(tv[j], ev[j])));
+    }
     const float xv[4] = {x.x, x.y, x.z, x.w};
     float p0[4], pv[4];
 #pragma unroll
@@ -36,8 +44,10 @@ __global__ void ddim_step_kernel(const float* __restrict__ eps, const float* sam
   // tail
   for (long long i = nv * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
-    const float p0 = __fdiv_rn(__fsub_rn(sample[i], __fmul_rn(s1m_at, eps[i])), s_at);
-    if (prev) prev[i] = __fadd_rn(__fmul_rn(s_ap, p0), __fmul_rn(s1m_ap, eps[i]));
+    float e = eps[i];
+    if (eps_text) e = __fadd_rn(e, __fmul_rn(guidance, __fsub_rn(eps_text[i], e)));
+    const float p0 = __fdiv_rn(__fsub_rn(sample[i], __fmul_rn(s1m_at, e)), s_at);
+    if (prev) prev[i] = __fadd_rn(__fmul_rn(s_ap, p0), __fmul_rn(s1m_ap, e));
     if (x0out) x0out[i] = p0;
   }
 }
@@ -248,13 +258,20 @@ int grid_for(long long work_items, int threads) {
 
 extern "C" int ldm_ddim_step(const float* eps, const float* sample, const float* coef, const int32_t* t_index,
                              float* prev_sample, float* pred_x0, int64_t n, ldm_stream_t stream) {
+  return ldm_ddim_step_cfg(eps, nullptr, 0.f, sample, coef, t_index, prev_sample, pred_x0, n, stream);
+}
+
+extern "C" int ldm_ddim_step_cfg(const float* eps_uncond, const float* eps_text, float guidance_scale,
+                                 const float* sample, const float* coef, const int32_t* t_index, float* prev_sample,
+                                 float* pred_x0, int64_t n, ldm_stream_t stream) {
   using namespace ldm_host;
-  LDM_REQUIRE(eps && sample && coef, LDM_ERR_BAD_ARG, "ldm_ddim_step: null arg");
+  LDM_REQUIRE(eps_uncond && sample && coef, LDM_ERR_BAD_ARG, "ldm_ddim_step: null arg");
   LDM_REQUIRE(n > 0, LDM_ERR_BAD_SHAPE, "ldm_ddim_step: n=%lld", (long long)n);
-  LDM_REQUIRE(((uintptr_t)eps | (uintptr_t)sample | (uintptr_t)prev_sample | (uintptr_t)pred_x0) % 16 == 0,
+  LDM_REQUIRE(((uintptr_t)eps_uncond | (uintptr_t)eps_text | (uintptr_t)sample | (uintptr_t)prev_sample |
+               (uintptr_t)pred_x0) % 16 == 0,
               LDM_ERR_ALIGNMENT, "ldm_ddim_step: pointers must be 16-byte aligned");
-  ddim_step_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, as_stream(stream)>>>(eps, sample, coef, t_index, prev_sample,
-                                                                            pred_x0, n);
+  ddim_step_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, as_stream(stream)>>>(eps_uncond, eps_text, guidance_scale, sample,
+                                                                            coef, t_index, prev_sample, pred_x0, n);
   count_launch();
   return check_launch("ddim_step_kernel");
 }

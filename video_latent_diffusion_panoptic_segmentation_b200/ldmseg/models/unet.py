@@ -177,6 +177,10 @@ class UNet:
         self.object_queries = emb
         self._packed, self._plans = None, {}
 
+    def has_cross_attention(self):
+        """True when the transformer blocks keep norm2 / attn2 (SD weights loaded and remove_cross_attention() not called)."""
+        return (not self._cross_attention_removed) and any(".attn2." in k for k in (self._sd or {}))
+
     def freeze_layers(self, layers=("norm", "time_embedding")):
         return None  # inference-only mirror: nothing is trainable
 

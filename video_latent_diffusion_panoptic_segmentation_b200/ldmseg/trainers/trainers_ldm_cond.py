@@ -32,11 +32,9 @@ class TrainerDiffusion:
         self.args = args or {"gpu": torch.cuda.current_device() if torch.cuda.is_available() else 0}
         self.vae_image, self.vae_semseg, self.unet_model = vae_image, vae_semseg, unet_model
         self.noise_scheduler = noise_scheduler
-        if image_descriptor_model is not None or text_encoder is not None:
-            raise NotImplementedError("CLIP image / text encoders are outside this path; the UNet's cross-attention "
-                                      "itself is built (UNet.forward(encoder_hidden_states=...), learnable object "
-                                      "queries): SURVEY section 8(f) rank 4")
-        self.image_descriptor_model, self.textencoder, self.tokenizer = None, None, None
+        # CLIP image / text encoders are third-party models (transformers); when given they are called as the reference
+        # calls them (:1102-1122) and only produce the UNet's encoder_hidden_states
+        self.image_descriptor_model, self.textencoder, self.tokenizer = image_descriptor_model, text_encoder, tokenizer
         ek = p.get("eval_kwargs", {})
         self.mask_th = ek.get("mask_th", 0.5)
         self.count_th = ek.get("count_th", 512)
@@ -93,21 +91,57 @@ class TrainerDiffusion:
         return latents * scaling_factor, latents_mean * scaling_factor
 
     # ------------------------------------------------------------------ sample (:1048-1173)
-    def _loop_state(self, B, h, w):
-        """Static buffers + UNet plan for the DDIM loop at this shape (built once, reused for every batch)."""
-        key = (B, h, w, self.self_condition)
+    def _loop_state(self, B, h, w, multiplier=1, ctx_len=None):
+        """Static buffers + UNet plan for the DDIM loop at this shape (built once, reused for every batch). With
+        classifier-free guidance (multiplier 2) the UNet runs on the doubled batch [uncond | text] (:1129,1126)."""
+        key = (B, h, w, self.self_condition, multiplier, ctx_len)
         st = self._loop.get(key)
         if st is None:
-            dev = self.device
-            st = {"latents": torch.empty((B, 4, h, w), dtype=f32, device=dev),
-                  "rgb": torch.empty((B, 4, h, w), dtype=f32, device=dev)}
+            dev, n = self.device, B * multiplier
+            st = {"latents": torch.empty((n, 4, h, w), dtype=f32, device=dev),
+                  "rgb": torch.empty((n, 4, h, w), dtype=f32, device=dev)}
             parts = [st["latents"], st["rgb"]]
             if self.self_condition:
-                st["cond"] = torch.zeros((B, 4, h, w), dtype=f32, device=dev)
+                st["cond"] = torch.zeros((n, 4, h, w), dtype=f32, device=dev)
                 parts.append(st["cond"])
-            st["plan"] = self.unet_model._get_plan(B, h, w, 4 * len(parts), parts=parts)
+            st["plan"] = self.unet_model._get_plan(n, h, w, 4 * len(parts), parts=parts, ctx_len=ctx_len)
             self._loop[key] = st
         return st
+
+    def norm_resize_images(self, x):
+        """:665-677: what the CLIP / DINO descriptor models expect (input of a third-party model: plain torch)."""
+        import torch.nn.functional as F
+        dev = x.device
+        mean_in = torch.tensor([0.485, 0.456, 0.406], device=dev).view(1, 3, 1, 1)
+        std_in = torch.tensor([0.229, 0.224, 0.225], device=dev).view(1, 3, 1, 1)
+        identifier = self.image_descriptor_model.__class__.__name__.lower()
+        if "clip" in identifier:
+            x = F.interpolate(x, size=(224, 224), mode="bilinear", align_corners=False)
+            mean = torch.tensor([0.48145466, 0.4578275, 0.40821073], device=dev).view(1, 3, 1, 1)
+            std = torch.tensor([0.26862954, 0.26130258, 0.27577711], device=dev).view(1, 3, 1, 1)
+            return (x - mean) / std
+        if "dino" in identifier:
+            x = F.interpolate(x, size=(518, 518), mode="bilinear", align_corners=False)
+        return (x - mean_in) / std_in
+
+    def _descriptors(self, prompts, rgb_images, batch_size):
+        """:1100-1122 -> (encoder_hidden_states of the conditional half, of the unconditional half or None).
+        Image descriptors: the reference concatenates the SAME descriptors twice, so both halves of its doubled batch
+        are identical and `uncond + g * (text - uncond)` is `uncond` bit for bit: one half is computed here."""
+        ctx, uncond = None, None
+        if self.image_descriptor_model is not None:
+            assert rgb_images is not None
+            d = self.image_descriptor_model(self.norm_resize_images(rgb_images).to(self.weight_dtype))["last_feat"]
+            ctx = d.view(d.shape[0], d.shape[1], -1).permute(0, 2, 1).to(torch.float)
+        if self.textencoder is not None:
+            dev = self.device
+            ti = self.tokenizer(prompts, padding="max_length", max_length=self.tokenizer.model_max_length,
+                                truncation=True, return_tensors="pt")
+            ctx = self.textencoder(ti.input_ids.to(device=dev))[0].to(torch.float)
+            ui = self.tokenizer([""] * batch_size, padding="max_length", max_length=ti.input_ids.shape[-1],
+                                return_tensors="pt")
+            uncond = self.textencoder(ui.input_ids.to(device=dev))[0].to(torch.float)
+        return ctx, uncond
 
     @torch.no_grad()
     def sample(self, prompts: List[str], num_inference_steps: int = 50, guidance_scale: float = 7.5,
@@ -130,33 +164,50 @@ class TrainerDiffusion:
             noise = torch.randn((batch_size, 4, h, w), generator=rng_generator)  # CPU generator, as :1091-1094
         if repeat_noise:
             noise = noise[0:1].repeat(batch_size, 1, 1, 1)
-        st = self._loop_state(batch_size, h, w)
-        latents, plan = st["latents"], st["plan"]
+        unet = self.unet_model
+        ctx, uncond = self._descriptors(prompts, rgb_images, batch_size)
+        if ctx is not None and not unet.has_cross_attention():
+            ctx = uncond = None  # attn2 is None in every block: the reference's UNet ignores encoder_hidden_states too
+        multiplier = 2 if uncond is not None else 1
+        if multiplier > 1 and self.self_condition:
+            raise NotImplementedError("self_condition with a text encoder: the reference concatenates a doubled batch "
+                                      "with an undoubled condition (:1134-1136,1152-1153) and fails")
+        B = batch_size
+        st = self._loop_state(B, h, w, multiplier, ctx_len=None if ctx is None else ctx.shape[1])
+        lat_all, plan = st["latents"], st["plan"]
+        latents = lat_all[:B]
         latents.copy_(noise.to(dev, non_blocking=True))           # H2D (:1095)
         if scheduler.init_noise_sigma != 1.0:
             latents.mul_(scheduler.init_noise_sigma)
         original_noise = latents.clone() if repeat_noise else None
-        st["rgb"].copy_(rgb_latents.to(dev, f32))
+        st["rgb"][:B].copy_(rgb_latents.to(dev, f32))
+        if multiplier > 1:
+            st["rgb"][B:].copy_(st["rgb"][:B])                    # torch.cat([rgb_latents] * multiplier) (:1126)
         if self.self_condition:
             st["cond"].zero_()
+        if ctx is not None:  # k / v of every attn2 layer are projected once here, not once per step
+            unet.set_context(plan, ctx if uncond is None else torch.cat([uncond, ctx]))   # (:1120)
         timesteps = scheduler.timesteps.to(dev)
         coef = scheduler.coef_table(dev)
-        unet = self.unet_model
         all_latents = []
         n = timesteps.numel()
         for i in range(n):
             t = timesteps[i:i + 1]
             plan.timestep.copy_(t)                                  # device-side timestep: no host sync in the loop
+            if multiplier > 1:
+                lat_all[B:].copy_(latents)                          # torch.cat([latents] * multiplier) (:1129)
             if plan.graph is not None:
                 plan.graph.replay()                                 # UNet (:1143-1144), concat fused into conv_in
             else:
                 unet._run_plan(plan)
             t_index = t.view(torch.int32)[:1]
             last = i == n - 1
-            # DDIM update (:1152-1162): prev_sample, or pred_original_sample on the last step, written in place
-            ops.ddim_step(plan.out, latents, coef, t_index,
+            # guidance (:1147-1149) + DDIM update (:1152-1162) in one launch: prev_sample, or pred_original_sample on
+            # the last step, written in place
+            ops.ddim_step(plan.out[:B], latents, coef, t_index,
                           prev_sample=None if last else latents,
-                          pred_x0=latents if last else (st["cond"] if self.self_condition else None))
+                          pred_x0=latents if last else (st["cond"] if self.self_condition else None),
+                          eps_text=plan.out[B:] if multiplier > 1 else None, guidance_scale=guidance_scale)
             if return_all_latents:
                 all_latents.append(latents.clone())
         if return_all_latents:
