@@ -46,7 +46,7 @@ constexpr int kVAtomBytes = kDN * 128;             // 48 rows x 64 keys
 constexpr int kStageBytes = kKBytes + 2 * kVAtomBytes;  // 24 KB
 constexpr int kMergeStride = 43;   // floats per row in the merge buffer (m, l, 40 x O; odd stride: no bank conflicts)
 constexpr int kMergeBytes = 2 * 128 * kMergeStride * 4;
-constexpr int kSmem = 2 * kQBytes + kStages * kStageBytes + kMergeBytes + 1024 + 256;
+constexpr int kSmem = 2 * kQBytes + kStages * kStageBytes + kMergeBytes + 1024 + 512;
 constexpr int kThreads = 128 + 2 * 256;
 constexpr int kGroupStride = 256;  // TMEM columns
 constexpr int kRing = kBKV + kBKV / 2;
@@ -68,8 +68,8 @@ flash_attn40_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* kv_full = q_full + 2;       // [kStages]
   uint64_t* kv_empty = kv_full + 8;     // [kStages]
   uint64_t* s_full = kv_empty + 8;      // [2]
-  uint64_t* p_full = s_full + 2;        // [2]
-  uint64_t* o_full = p_full + 2;        // [2]
+  uint64_t* p_full = s_full + 2;        // [2][2]: one barrier per (group, block parity), see the MMA warp's wait
+  uint64_t* o_full = p_full + 4;        // [2]
   uint64_t* s_free = o_full + 2;        // [2]
   uint64_t* o_done = s_free + 2;        // [2] completes ONCE, when the last block's PV MMAs have landed (see the final wait)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
@@ -87,7 +87,8 @@ flash_attn40_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     for (int g = 0; g < 2; ++g) {
       mbar_init(&q_full[g], 1);
       mbar_init(&s_full[g], 1);
-      mbar_init(&p_full[g], 256);
+      mbar_init(&p_full[2 * g], 256);
+      mbar_init(&p_full[2 * g + 1], 256);
       mbar_init(&o_full[g], 1);
       mbar_init(&o_done[g], 1);
       mbar_init(&s_free[g], 256);
@@ -191,7 +192,11 @@ flash_attn40_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           }
         }
         for (int g = 0; g < 2; ++g) {
-          mbar_wait(&p_full[g], j & 1);
+          // Two barriers per group, alternating with the block parity. With one, a group whose softmax threads finish
+          // blocks j AND j + 1 (S of j + 1 is issued above, before this wait) while this warp is still held up by the
+          // other group's s_free would complete two phases before the wait looks: a parity wait then never returns.
+          // Arrivals for block j + 2 need S of j + 2, which is only issued after this wait has returned.
+          mbar_wait(&p_full[2 * g + (j & 1)], (j >> 1) & 1);
           tc_fence_after();
           TRACE(4 + g, j);
           issue_o(g, stage, j);
@@ -313,7 +318,7 @@ flash_attn40_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       TRACE(3, j);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&p_full[g]);
+      mbar_arrive(&p_full[2 * g + (j & 1)]);
       TRACE(4, j);
     }
     // NOT o_full with the parity of the last block: a softmax thread never waits for a PV MMA inside the loop, so here

@@ -42,7 +42,7 @@ struct AttnCfg {
   static constexpr int kVBytes = kVAtoms * kDN * 128;
   static constexpr int kVBytesPad = ((kVBytes + 1023) / 1024) * 1024;
   static constexpr int kStageBytes = kKBytes + kVBytesPad;
-  static constexpr int kSmem = NQ * kQBytes + STAGES * kStageBytes + 1024 + 256;
+  static constexpr int kSmem = NQ * kQBytes + STAGES * kStageBytes + 1024 + 512;
   static constexpr int kThreads = 128 + 128 * NQ;  // warpgroup 0: producer, MMA issuer (+2 idle warps); then NQ softmax warpgroups
   static constexpr int kTmemGroupStride = 256;
   static constexpr int kRing = BKV + BKV / 2;          // S / P ring of one group (columns)
@@ -66,8 +66,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   uint64_t* kv_full = q_full + 2;        // [STAGES]
   uint64_t* kv_empty = kv_full + 8;      // [STAGES]
   uint64_t* s_full = kv_empty + 8;       // [NQ]
-  uint64_t* p_full = s_full + 2;         // [NQ]
-  uint64_t* o_full = p_full + 2;         // [NQ]
+  uint64_t* p_full = s_full + 2;         // [NQ][2]: one barrier per (group, block parity), see the MMA warp's wait
+  uint64_t* o_full = p_full + 4;         // [NQ]
   uint64_t* s_free = o_full + 2;         // [NQ]
   uint64_t* o_done = s_free + 2;         // [NQ] completes ONCE, when the last block's PV MMAs have landed (see the final wait)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
@@ -86,7 +86,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     for (int g = 0; g < NQ; ++g) {
       mbar_init(&q_full[g], 1);
       mbar_init(&s_full[g], 1);
-      mbar_init(&p_full[g], 128);
+      mbar_init(&p_full[2 * g], 128);
+      mbar_init(&p_full[2 * g + 1], 128);
       mbar_init(&o_full[g], 1);
       mbar_init(&o_done[g], 1);
       mbar_init(&s_free[g], 128);
@@ -197,7 +198,11 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           }
         }
         for (int g = 0; g < NQ; ++g) {
-          mbar_wait(&p_full[g], j & 1);
+          // Two barriers per group, alternating with the block parity. With one, a group whose softmax threads finish
+          // blocks j AND j + 1 (S of j + 1 is issued above, before this wait) while this warp is still held up by the
+          // other group's s_free would complete two phases before the wait looks: a parity wait then never returns.
+          // Arrivals for block j + 2 need S of j + 2, which is only issued after this wait has returned.
+          mbar_wait(&p_full[2 * g + (j & 1)], (j >> 1) & 1);
           tc_fence_after();
           TRACE(4 + g, j);
           issue_o(g, stage, j);
@@ -325,7 +330,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       TRACE(3, j);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&p_full[g]);
+      mbar_arrive(&p_full[2 * g + (j & 1)]);
       TRACE(4, j);
     }
     // NOT o_full with the parity of the last block: a softmax thread never waits for a PV MMA inside the loop, so here
