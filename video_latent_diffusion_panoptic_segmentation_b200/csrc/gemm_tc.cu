@@ -178,7 +178,20 @@ extern "C" int ldm_gemm_bf16(const ldm_gemm_desc* d, ldm_stream_t stream) {
                        (d->block_n <= 0 || (pair_override() == 1 && d->block_n >= 64 && d->block_n % 32 == 0));
   bool pair = pair_ok && cost2 < cost1 && kblocks_total >= 32;  // the pair's hand-offs only pay on long main loops
   if (pair_override() >= 0) pair = pair_ok && pair_override() != 0;  // LDM_GEMM_PAIR=-1: model decides
-  int block_n = d->block_n > 0 ? d->block_n : (pair ? bn2 : bn1);
+  // QKV head split: with block_n = 160 (the only multiple of the 32-column TMEM chunk that 40-, 80- and 160-wide heads
+  // all divide) every tile holds whole heads of one part, and the q / k tiles can leave through TMA stores
+  // (LDM_GEMM_QKV_TMA=0: the row-per-thread stores, A/B timing)
+  static const bool qkv_tma_enabled = [] { const char* e = getenv("LDM_GEMM_QKV_TMA"); return e ? atoi(e) != 0 : true; }();
+  bool qkv_tma = false;
+  if ((flags & LDM_GEMM_QKV_SPLIT) && qkv_tma_enabled && d->block_n <= 0 && !d->bias && !d->rowbias && d->head_dim > 0 &&
+      160 % d->head_dim == 0 && (d->heads * d->head_dim) % 160 == 0 && p.H == 1 && p.bw == kBlockM && p.bh == 1 &&
+      d->dpad == ((d->head_dim + 63) / 64) * 64 && d->seq >= kBlockM && kblocks_total <= 6) {
+    // only where the epilogue, not the main loop, bounds the tile (K <= 384: the 48x156 level). Measured: 105 -> 73 us
+    // there, but 46 -> 50 us at K = 640, where block_n = 256 has the cheaper main loop per column.
+    qkv_tma = true;
+    pair = false;
+  }
+  int block_n = d->block_n > 0 ? d->block_n : (qkv_tma ? 160 : (pair ? bn2 : bn1));
   if ((flags & LDM_GEMM_GEGLU) && d->block_n <= 0 && block_n < 128) block_n = 128;  // staged GEGLU blocks span 128 columns
   LDM_REQUIRE(block_n % 32 == 0 && block_n >= 32 && block_n <= 256, LDM_ERR_BAD_ARG, "ldm_gemm_bf16: block_n=%d",
               block_n);
@@ -215,7 +228,7 @@ extern "C" int ldm_gemm_bf16(const ldm_gemm_desc* d, ldm_stream_t stream) {
   const int n_out = (flags & LDM_GEMM_GEGLU) ? d->N / 2 : d->N;
   const bool staged = !(flags & (LDM_GEMM_OUT_F32 | LDM_GEMM_OUT_NCHW_F32 | LDM_GEMM_QKV_SPLIT | LDM_GEMM_CONVT_LN_SILU)) &&
                       n_out >= 64 && n_out % 8 == 0 && block_n >= ((flags & LDM_GEMM_GEGLU) ? 128 : 64) && staged_enabled();
-  p.flags = flags | debug_flags() | (staged ? kStagedStore : 0);
+  p.flags = flags | debug_flags() | (staged ? kStagedStore : 0) | (qkv_tma ? kQkvStaged : 0);
   p.bias = d->bias;
   p.rowbias = d->rowbias;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(d->residual);
@@ -298,6 +311,22 @@ extern "C" int ldm_gemm_bf16(const ldm_gemm_desc* d, ldm_stream_t stream) {
     const uint32_t box[4] = {64, (uint32_t)p.bw, (uint32_t)p.bh, 1};
     int rc = make_tmap(&tmR, d->residual, 4, dims, str, box, 2, true);
     if (rc) return rc;
+  }
+
+  if (qkv_tma) {
+    // tmO / tmR (unused by this epilogue otherwise) become the q / k maps: {dpad, seq, heads, images}, box 64 x 128 tokens
+    const uint64_t nimg = (uint64_t)((long long)d->B * d->H * d->W / d->seq);
+    const uint64_t dims[4] = {(uint64_t)d->dpad, (uint64_t)d->seq, (uint64_t)d->heads, nimg};
+    const uint64_t str[3] = {(uint64_t)d->dpad * 2, (uint64_t)d->dpad * 2 * d->seq, (uint64_t)d->dpad * 2 * d->seq * d->heads};
+    const uint32_t box[4] = {64, (uint32_t)kBlockM, 1, 1};
+    if (d->q) {
+      int rc = make_tmap(&tmO, d->q, 4, dims, str, box, 2, true);
+      if (rc) return rc;
+    }
+    if (d->k) {
+      int rc = make_tmap(&tmR, d->k, 4, dims, str, box, 2, true);
+      if (rc) return rc;
+    }
   }
 
   const int smem_bytes = p.stages * p.stage_bytes + kEpiStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;

@@ -17,6 +17,7 @@ constexpr int kSmemBudget = 227 * 1024;
 constexpr int kEpiStageBytes = 2 * 16384 + 1024;  // epilogue output staging for the TMA-store path + per-half bias slice
 // Diagnostic switches (env LDM_GEMM_DEBUG, never set by the product): isolate the two halves of the main loop.
 constexpr int kStagedStore = 1 << 20; // internal: epilogue writes the output through shared memory + TMA store
+constexpr int kQkvStaged = 1 << 21;   // internal (QKV_SPLIT): q / k tiles are whole heads and leave through TMA stores
 constexpr int kDbgNoTma = 1 << 29;  // producer signals the stages without loading them
 constexpr int kDbgNoMma = 1 << 30;
 constexpr int kDbgNoFence = 1 << 27; // skip tcgen05.fence::after_thread_sync after the full-barrier wait
@@ -455,8 +456,66 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           sb ^= 1;
         }
       } else {
+        bool qkv_done = false;
+        if constexpr (kEpi == kEpiQkv) {
+          // q / k tiles through shared memory + TMA stores. block_n is a multiple of head_dim and divides C here, so
+          // the tile holds whole heads of ONE part. Per head and 64-column block of its padded row (head_dim data
+          // columns, then zeros up to dpad) the eight warps stage a [128 tokens x 64] swizzled block and one thread
+          // stores it into q / k [B*heads, seq, dpad] (map {dpad, seq, heads, B}). Full 128-byte lines instead of the
+          // row-per-thread 16-byte stores (26.7 sectors per request, epilogue 3.5x longer than the K = 320 main loop).
+          const int C = p.heads * p.head_dim;
+          const int part_in = n0 / C;
+          const int which_t = part_in + p.qkv_part0;
+          const long long grow0 = (long long)m_tile * kBlockM;  // flattened rows: bh == 1, bw == kBlockM
+          const int bi0 = (int)(((unsigned long long)grow0 * p.magic_seq) >> 40);
+          const int s0 = (int)(grow0 - (long long)bi0 * p.seq);
+          const int nimg = (int)(((long long)p.W * p.H * p.B) / p.seq);
+          // (a tile whose 128 rows run into the next image keeps the row-per-thread stores below: one tile per image)
+          if ((p.flags & kQkvStaged) && which_t < 2 && (s0 + kBlockM <= p.seq || bi0 + 1 >= nimg)) {
+            const int head0 = (n0 - part_in * C) / p.head_dim;
+            const int heads_in_tile = p.block_n / p.head_dim;
+            const int blocks_per_head = p.dpad >> 6;
+            for (int hd = 0; hd < heads_in_tile; ++hd) {
+              for (int kb = 0; kb < blocks_per_head; ++kb) {
+                uint8_t* sbuf = epi_smem + sb * 16384;
+                if (epi_leader) bulk_wait_read1();  // the store that last used this buffer has been read
+                named_bar_sync(1, 32 * kEpiWarps);
+                const int cbase = hd * p.head_dim + kb * 64 + half * 32;  // accumulator column of this thread's chunk
+                int ng = ((hd + 1) * p.head_dim - cbase) >> 3;             // 8-column groups that hold data (warp-uniform)
+                ng = ng < 0 ? 0 : (ng > 4 ? 4 : ng);
+                uint32_t v[32];
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                  if (g < ng) tmem_ld8(t_addr + cbase + g * 8, v + g * 8);
+                tmem_ld_wait();
+                uint8_t* rowp = sbuf + r * 128;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                  uint4 u = make_uint4(0, 0, 0, 0);
+                  if (g < ng) {
+                    u.x = pack_bf16(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1]));
+                    u.y = pack_bf16(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3]));
+                    u.z = pack_bf16(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5]));
+                    u.w = pack_bf16(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7]));
+                  }
+                  *reinterpret_cast<uint4*>(rowp + (((half * 4 + g) ^ (r & 7)) << 4)) = u;
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(1, 32 * kEpiWarps);
+                if (epi_leader) {  // rows past the end of the last image are clipped by the TMA unit
+                  if (which_t == 0) tma_store_4d(&tmO, sbuf, kb * 64, s0, head0 + hd, bi0);
+                  else tma_store_4d(&tmR, sbuf, kb * 64, s0, head0 + hd, bi0);
+                  bulk_commit();
+                }
+                sb ^= 1;
+              }
+            }
+            qkv_done = true;
+          }
+        }
 #pragma unroll
         for (int ci = 0; ci < 4; ++ci) {
+          if (qkv_done) break;
           const int c = (2 * ci + half) * 32;
           if (c >= p.block_n) break;
           uint32_t v[32];
