@@ -177,7 +177,7 @@ def run_reference(args):
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": ref.threads, "kind": "port",
                              "sample": ref.describe(t_unet, t_tail, len(times))},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------- our arm
@@ -427,13 +427,28 @@ def run_ours(args):
             except Exception as e:  # the checker must not take the measurement down
                 line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
                                         "sample": f"failed: {e!r}"}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's original stdout; everything else that writes to fd 1 (the NCCL version
+    banner at N > 1, library prints) has been moved to stderr by main()."""
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
