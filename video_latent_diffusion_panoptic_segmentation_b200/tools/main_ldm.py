@@ -18,7 +18,7 @@ import numpy as np
 import torch
 import yaml
 
-from ..ldmseg.models import GeneralVAESeg, UNet
+from ..ldmseg.models import GeneralVAEImage, GeneralVAESeg, UNet
 from ..ldmseg.models import unet_init
 from ..ldmseg.schedulers import DDIMNoiseScheduler
 from ..ldmseg.trainers import TrainerDiffusion
@@ -47,7 +47,9 @@ BASE = {
     "num_classes": 128,
     "ignore_label": 127,
     # synthetic validation set (no dataset on disk): frames of `synthetic.size`, `synthetic.frames` of them
-    "synthetic": dict(frames=8, size=[384, 1248], batch_size=8, seed=1234),
+    # from_images: the loader yields RGB frames in [0, 1] and the RGB VAE encoder produces the latents (main_ldm.py:138-140,
+    # trainers_ldm_cond.py:1234-1239) instead of handing the latents over directly
+    "synthetic": dict(frames=8, size=[384, 1248], batch_size=8, seed=1234, from_images=False),
 }
 DIST = {"world_size": 1, "rank": 0, "dist_url": "tcp://127.0.0.1:54288", "dist_backend": "nccl",
         "multiprocessing_distributed": False}
@@ -98,6 +100,13 @@ def build_models(p, device, seed=0):
     return vae, unet, sched
 
 
+def build_vae_image(p, device, seed=0):
+    """main_ldm.py:138-140: the RGB VAE (decoder dropped); random-init SD-1.4 VAE encoder without a checkpoint."""
+    vim = GeneralVAEImage.from_pretrained(state_dict=unet_init.random_vae_image_state_dict(seed=seed + 3), device=device)
+    vim.set_scaling_factor(p["image_scaling_factor"])
+    return vim
+
+
 def synthetic_batches(p, rank=0, world=1):
     """Synthetic validation shard of this rank: random RGB latents (N(0,1)*0.18215) + Voronoi ground truth."""
     sy = p["synthetic"]
@@ -107,10 +116,14 @@ def synthetic_batches(p, rank=0, world=1):
     for i in range(0, len(frames), sy["batch_size"]):
         idx = frames[i:i + sy["batch_size"]]
         g = torch.Generator().manual_seed(sy["seed"] + i + 1000 * rank)
-        rgb = p["image_scaling_factor"] * torch.randn((len(idx), 4, H // 8, W // 8), generator=g)
         gt = np.stack([_voronoi_semantic(rng, H, W) for _ in idx])
-        yield {"rgb_latents": rgb, "semseg": torch.from_numpy(gt), "mask": torch.ones((len(idx), H, W), dtype=torch.bool),
-               "meta": [{"im_size": (H, W), "image_id": int(j)} for j in idx]}
+        batch = {"semseg": torch.from_numpy(gt), "mask": torch.ones((len(idx), H, W), dtype=torch.bool),
+                 "meta": [{"im_size": (H, W), "image_id": int(j)} for j in idx]}
+        if sy.get("from_images", False):
+            batch["image"] = torch.rand((len(idx), 3, H, W), generator=g)
+        else:
+            batch["rgb_latents"] = p["image_scaling_factor"] * torch.randn((len(idx), 4, H // 8, W // 8), generator=g)
+        yield batch
 
 
 def _voronoi_semantic(rng, H, W, n_seeds=40, n_cls=19):
@@ -135,12 +148,16 @@ def main_worker(gpu, ngpus_per_node, cfg_dist, p, name="b200"):
         raise NotImplementedError("only base.eval_only=True (sampling + PQ) is built; training is out of scope")
     device = torch.device("cuda", gpu)
     vae, unet, sched = build_models(p, device)
-    trainer = TrainerDiffusion(p=p, vae_semseg=vae, unet_model=unet, noise_scheduler=sched, args={"gpu": gpu})
+    vae_image = build_vae_image(p, device) if p["synthetic"].get("from_images", False) else None
+    trainer = TrainerDiffusion(p=p, vae_image=vae_image, vae_semseg=vae, unet_model=unet, noise_scheduler=sched,
+                               args={"gpu": gpu})
     if p.get("load_path"):
         data = torch.load(p["load_path"], map_location="cpu")
         unet.load_state_dict(data["unet"])
         if p["train_kwargs"].get("image_descriptors", "remove") == "remove":
             unet.remove_cross_attention()
+        if "vae_image" in data and vae_image is not None:
+            vae_image.load_state_dict(data["vae_image"])
         if "vae_semseg" in data:
             vae.load_state_dict({k.replace("module.", ""): v for k, v in data["vae_semseg"].items()})
     res = trainer.compute_metrics(["pq"], threshold_output=True, save_images=False, seed=42,
