@@ -544,6 +544,13 @@ def check_joint_hist():
     uk, uc = np.unique(key, return_counts=True)
     got = av * (1 << 31) + bv
     assert np.array_equal(got, uk) and np.array_equal(c, uc), "joint_hist mismatch"
+    # default (small) table: two overflow retries for these 54 150 pairs; and a frame-like case that fits at once
+    av2, bv2, c2 = ops.joint_hist(torch.from_numpy(a).to(DEV), torch.from_numpy(b).to(DEV))
+    assert np.array_equal(av2, av) and np.array_equal(bv2, bv) and np.array_equal(c2, c), "joint_hist retry mismatch"
+    a3, b3 = (a // (1 << 20)).astype(np.int32), (b // (1 << 20)).astype(np.int32)
+    av3, bv3, c3 = ops.joint_hist(torch.from_numpy(a3).to(DEV), torch.from_numpy(b3).to(DEV))
+    uk3, uc3 = np.unique(a3.astype(np.int64) * (1 << 31) + b3.astype(np.int64), return_counts=True)
+    assert np.array_equal(av3 * (1 << 31) + bv3, uk3) and np.array_equal(c3, uc3), "joint_hist (small table) mismatch"
     return {"name": "joint_hist", "pairs": int(len(uk))}
 
 

@@ -305,9 +305,11 @@ def ccl_label4(sem, target):
     return labels, ncomp
 
 
-def joint_hist(a, b, capacity=1 << 14):
+def joint_hist(a, b, capacity=1 << 10):
     """Counts of distinct (a[i], b[i]) pairs. Returns (a_ids, b_ids, counts) as int64 numpy arrays sorted by
-    (a, b) -- i.e. the np.unique(a*offset+b, return_counts=True) of the reference in ascending key order."""
+    (a, b) -- i.e. the np.unique(a*offset+b, return_counts=True) of the reference in ascending key order.
+    The table starts small (a frame has a few hundred distinct id pairs; the whole table is read back: 12 KB at 1 024
+    slots) and is retried 16x larger when it fills up."""
     import numpy as np
     _chk(a, i32, "a"); _chk(b, i32, "b")
     keys = torch.empty(capacity, dtype=torch.int64, device=a.device)
