@@ -13,6 +13,10 @@ What it restates
     ``cross_attention_dim=768`` the blocks keep norm2 / attn2 against ``encoder_hidden_states`` (unet.py:319-323:
     ``encoder_hid_proj``, learnable ``object_queries``).
 
+One independent known answer pins the SHAPES of this restatement: with cross_attention_dim=768 and in_channels=4 it has
+exactly the published 859 520 964 parameters of Stable Diffusion 1.x's UNet (tests/test_host_cpu.py); the arithmetic
+itself stays unpinned:
+
 PARITY UNPINNED at the diffusers boundary: the reference holds no test, golden vector or fixture for the UNet and
 diffusers cannot be imported here, so nothing independent pins this restatement (DESIGN.md says the same).
 Two documented generalisations: noise/latents may be non-square, and Upsample2D uses the

@@ -101,6 +101,17 @@ def test_modify_encoder_matches_oracle():
     assert tuple(m.config.block_out_channels) == (64, 128, 256, 256)
 
 
+def test_unet_parameter_count_matches_published_sd14():
+    """Known answer that pins the restated architecture's shapes: Stable Diffusion 1.x's UNet2DConditionModel has
+    859 520 964 parameters (the published "860M UNet"); without attn2 / norm2 (unet.py:83-105) 815 533 444 remain."""
+    full = unet_init.unet_param_shapes(cross_attention_dim=768)
+    assert sum(int(np.prod(v)) for v in full.values()) == 859520964
+    removed = unet_init.unet_param_shapes()
+    assert sum(int(np.prod(v)) for v in removed.values()) == 815533444
+    ref = UO.UNetOracle(in_channels=4)
+    assert sum(p.numel() for p in ref.parameters()) == 815533444
+
+
 def test_vae_image_param_shapes_match_oracle_module():
     from oracle import vae_image_oracle as VO
     net = VO.VAEImageOracle()
