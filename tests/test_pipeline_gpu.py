@@ -343,9 +343,25 @@ class _ToyTextEncoder(torch.nn.Module):
         return (self.emb(input_ids) + self.pos[None, :input_ids.shape[1]],)
 
 
-def test_sampler_classifier_free_guidance_vs_oracle():
+def _clip_text_model():
+    """The class the reference loads (descriptors.py:100: transformers.CLIPTextModel), SD-1.4's text-encoder geometry
+    (768 wide, 77 positions, 49 408 tokens) with two layers, random-init (no checkpoint offline)."""
+    from transformers import CLIPTextConfig, CLIPTextModel
+    torch.manual_seed(13)
+    cfg = CLIPTextConfig(hidden_size=768, intermediate_size=3072, num_attention_heads=12, num_hidden_layers=2,
+                         max_position_embeddings=77, vocab_size=49408)
+    return CLIPTextModel(cfg)
+
+
+class _ClipLengthTokenizer(_ToyTokenizer):
+    model_max_length = 77
+
+
+@pytest.mark.parametrize("encoder", ["toy", "transformers_clip"])
+def test_sampler_classifier_free_guidance_vs_oracle(encoder):
     """H1 with a text encoder (trainers_ldm_cond.py:1110-1122,1126-1129,1147-1149): doubled batch [uncond | text],
-    encoder_hidden_states through the kept cross-attention, guidance fused into the DDIM kernel."""
+    encoder_hidden_states through the kept cross-attention, guidance fused into the DDIM kernel. Once with a toy
+    encoder, once with transformers' CLIPTextModel (the reference's class) and its 77-token context."""
     from oracle import ldmseg_oracle as LO
     from oracle import unet_oracle as UO
     from video_latent_diffusion_panoptic_segmentation_b200.ldmseg.models import UNet
@@ -355,7 +371,10 @@ def test_sampler_classifier_free_guidance_vs_oracle():
     unet = UNet(device=DEV)
     unet.load_state_dict(o_unet.state_dict())
     o_unet = o_unet.to(DEV)
-    tok, enc = _ToyTokenizer(), _ToyTextEncoder().to(DEV).eval()
+    if encoder == "toy":
+        tok, enc = _ToyTokenizer(), _ToyTextEncoder().to(DEV).eval()
+    else:
+        tok, enc = _ClipLengthTokenizer(), _clip_text_model().to(DEV).eval()
     B, h, w, T, g = 2, 16, 24, 3, 4.0
     prompts = ["a car on the road", "two pedestrians"]
     rgb = (0.18215 * torch.randn((B, 4, h, w), generator=torch.Generator().manual_seed(1234))).to(DEV)
