@@ -397,6 +397,54 @@ def test_sampler_classifier_free_guidance_vs_oracle(encoder):
     assert lat0.shape == (B, 4, h, w) and torch.isfinite(lat0).all() and not torch.equal(lat0, lat)
 
 
+def test_sampler_clip_image_descriptors_vs_oracle():
+    """image_descriptors == 'clip_image' (descriptors.py:15-31,67-71; trainers_ldm_cond.py:1102-1109,665-677):
+    transformers' CLIPVisionModel (ViT-L/14 geometry, two layers, random init) -> 257 x 1024 descriptors ->
+    encoder_hid_proj 1024 -> 768 -> cross-attention. The reference doubles the batch with the SAME descriptors in both
+    halves; the mirror computes one half (uncond + g * (text - uncond) == uncond)."""
+    from transformers import CLIPVisionConfig, CLIPVisionModel
+    from oracle import ldmseg_oracle as LO
+    from oracle import unet_oracle as UO
+    from video_latent_diffusion_panoptic_segmentation_b200.ldmseg.models import UNet
+    from video_latent_diffusion_panoptic_segmentation_b200.ldmseg.schedulers import DDIMNoiseScheduler
+    from video_latent_diffusion_panoptic_segmentation_b200.ldmseg.trainers import TrainerDiffusion
+
+    class MyCLIPVisionModel(torch.nn.Module):  # the reference's wrapper (descriptors.py:15-31), by composition
+        def __init__(self, cfg):
+            super().__init__()
+            self.clip = CLIPVisionModel(cfg)
+
+        def forward(self, pixel_values=None, **kw):
+            out = self.clip.vision_model(pixel_values=pixel_values)
+            return {"last_feat": out.last_hidden_state.permute(0, 2, 1)}
+
+    torch.manual_seed(14)
+    vis = MyCLIPVisionModel(CLIPVisionConfig(hidden_size=1024, intermediate_size=4096, num_attention_heads=16,
+                                             num_hidden_layers=2, image_size=224, patch_size=14)).to(DEV).eval()
+    o_unet = UO.build_unet(seed=9, cross_attention_dim=768)
+    torch.manual_seed(15)
+    o_unet.modify_encoder_hidden_state_proj(1024, 768)          # descriptors.py:71
+    unet = UNet(device=DEV)
+    unet.load_state_dict(o_unet.state_dict())
+    o_unet = o_unet.to(DEV)
+    B, h, w, T = 2, 16, 24, 2
+    images = torch.rand((B, 3, 8 * h, 8 * w), generator=torch.Generator().manual_seed(3)).to(DEV)
+    rgb = (0.18215 * torch.randn((B, 4, h, w), generator=torch.Generator().manual_seed(1234))).to(DEV)
+    tr = TrainerDiffusion(p={}, unet_model=unet, image_descriptor_model=vis,
+                          noise_scheduler=DDIMNoiseScheduler(**SCHED_KW), args={"gpu": 0})
+    lat = tr.sample([""] * B, num_inference_steps=T, guidance_scale=7.5, seed=42, rgb_latents=rgb, rgb_images=images)
+    with torch.no_grad():
+        x = F.interpolate(images, size=(224, 224), mode="bilinear", align_corners=False)
+        mean = torch.tensor([0.48145466, 0.4578275, 0.40821073], device=DEV).view(1, 3, 1, 1)
+        std = torch.tensor([0.26862954, 0.26130258, 0.27577711], device=DEV).view(1, 3, 1, 1)
+        d = vis((x - mean) / std)["last_feat"]
+        desc = d.view(d.shape[0], d.shape[1], -1).permute(0, 2, 1).float()
+    assert desc.shape == (B, 257, 1024)
+    ref = LO.sample(o_unet, LO.DDIMOracle(), rgb, num_inference_steps=T, seed=42, context=desc, uncond_context=desc,
+                    guidance_scale=7.5)   # the reference's doubled batch with identical halves
+    assert _rel(lat, ref) < 8e-2, _rel(lat, ref)
+
+
 def test_tail_ids_bit_exact_given_identical_logits(models):
     """H6/H7: feed the SAME fp32 logits to the CUDA tail and to the restated reference tail."""
     from oracle import ldmseg_oracle as LO
