@@ -139,3 +139,21 @@ def test_seg_encoder_bit_exact_with_reference():
     assert np.array_equal(m.numpy(), z["moments"])
     assert np.array_equal(mean.numpy(), z["mode"]) and np.array_equal(std.numpy(), z["std"])
     assert np.array_equal(fwd.numpy(), z["forward"])
+
+
+def test_evaluator_edge_cases_match_reference():
+    """tests/golden/edge_cases.json (real reference outputs, make_golden_edge_cases.py): identical maps, a prediction
+    that matches nothing, all-void ground truth, a single pixel, > 1 000 distinct id pairs, IoU exactly 0.5 (strict >),
+    an all-void prediction, all-ignore ground truth, 512 single-pixel components, a thing split in two."""
+    from synth import edge_cases_city, edge_cases_vpq
+    edge = json.load(open(os.path.join(G, "edge_cases.json")))
+    for name, (pred, gt) in edge_cases_vpq().items():
+        for a, b in zip(EO.vpq_stats(pred, gt), edge["vpq"][name]):
+            assert a.tolist() == b, name
+    for name, (pred, gt) in edge_cases_city().items():
+        ev = EO.CityscapesPQOracle()
+        ev.add_image(pred, gt)
+        res, want = ev.evaluate(), edge["city"][name]
+        assert (ev.TP, ev.FP, ev.FN, ev.iou_sum) == (want["tp"], want["fp"], want["fn"], want["iou_sum"]), name
+        assert (res["pq"], res["sq"], res["rq"]) == (want["pq"], want["sq"], want["rq"]), name
+        assert {str(c): {k: v for k, v in m.items()} for c, m in res["per_class"].items()} == want["per_class"], name

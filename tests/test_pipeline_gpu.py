@@ -523,6 +523,28 @@ def test_cityscapes_evaluator_matches_reference_golden():
     assert {str(c): m for c, m in res["per_class"].items()} == want["per_class"]
 
 
+@pytest.mark.parametrize("which", ["vpq", "city"])
+def test_evaluator_edge_cases_match_reference_golden(which):
+    """tests/golden/edge_cases.json holds the REAL reference's outputs on the edge inputs of tests/synth.py (identical
+    maps, nothing matches, all-void / all-ignore ground truth, all-void prediction, one pixel, > 1 000 distinct id
+    pairs -- the joint-histogram table has to grow --, IoU exactly 0.5, 512 one-pixel components, a split thing)."""
+    from synth import edge_cases_city, edge_cases_vpq
+    from video_latent_diffusion_panoptic_segmentation_b200.ldmseg.evaluations import CityscapesPanopticEvaluator, vpq_eval
+    edge = json.load(open(os.path.join(G, "edge_cases.json")))
+    if which == "vpq":
+        for name, (pred, gt) in edge_cases_vpq().items():
+            for a, b in zip(vpq_eval([pred, gt]), edge["vpq"][name]):
+                assert a.tolist() == b, name
+    else:
+        for name, (pred, gt) in edge_cases_city().items():
+            ev = CityscapesPanopticEvaluator(thing_ids={11, 12, 13, 14, 15, 16, 17, 18}, device=DEV)
+            ev.add_image(pred, gt)
+            res, want = ev.evaluate(), edge["city"][name]
+            assert (ev.TP, ev.FP, ev.FN, ev.iou_sum) == (want["tp"], want["fp"], want["fn"], want["iou_sum"]), name
+            assert (res["pq"], res["sq"], res["rq"]) == (want["pq"], want["sq"], want["rq"]), name
+            assert {str(c): m for c, m in res["per_class"].items()} == want["per_class"], name
+
+
 def test_compute_pq_end_to_end(models):
     """compute_metrics(['pq']) on synthetic batches; the PQ is re-derived by the oracle evaluator from the ids the
     CUDA path produced (bit-exact statistics), and the ids from the oracle tail on the oracle decoder's logits agree
