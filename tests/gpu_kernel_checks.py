@@ -494,6 +494,34 @@ def check_logits_to_ids(up=2):
     return info
 
 
+def check_segment_filter_boundaries():
+    """Merge filter (trainers_ldm_cond.py:1303-1325) at its decision boundaries, on constructed per-class counts:
+    count == count_th is kept and count_th - 1 dropped (`count < count_th`), count / over == overlap_th exactly is kept
+    and just below dropped (`< overlap_th`, float64 as numpy), over == 0 (numpy: x / 0 = inf) is kept, the ignore
+    label and labels outside [0, C) are dropped."""
+    C, count_th, overlap_th, ignore = 16, 100, 0.5, 15
+    #            class: 0    1    2    3     4    5    6       7
+    count = np.array([100,  99, 200, 200,  300, 500, 100,      0] + [0] * 7 + [400], np.int32)
+    over = np.array([100, 100, 400, 401,    0, 100, 201,     50] + [0] * 7 + [400], np.int32)
+    keep_ref = []
+    for c in range(C):
+        k = not (count[c] < count_th or c == ignore)
+        if k and count[c] > 0:
+            with np.errstate(divide="ignore"):
+                if np.float64(count[c]) / np.float64(over[c]) < overlap_th:
+                    k = False
+        keep_ref.append(k and count[c] > 0)
+    assert keep_ref[:8] == [True, False, True, False, True, True, False, False] and not keep_ref[15]
+    ids = torch.from_numpy(np.concatenate([np.arange(-2, C + 2), np.arange(C)]).astype(np.int32)).view(1, -1).to(DEV)
+    counts = torch.from_numpy(np.stack([count, over])[None]).contiguous().to(DEV)
+    cleaned = _empty_like(ids)
+    ops.segment_filter(ids, counts, cleaned, count_th=count_th, overlap_th=overlap_th, ignore_label=ignore)
+    idn = ids.cpu().numpy()[0]
+    want = np.array([i if (0 <= i < C and keep_ref[i]) else -1 for i in idn], np.int32)
+    assert np.array_equal(cleaned.cpu().numpy()[0], want), (cleaned.cpu().numpy()[0].tolist(), want.tolist())
+    return {"name": "segment_filter boundaries", "kept": int(sum(keep_ref))}
+
+
 def check_bitmap():
     B, n, H, W = 2, 16, 24, 78
     rng = np.random.default_rng(0)
@@ -607,6 +635,7 @@ CHECKS = {
     "cross_attn_160_kv16": lambda: check_cross_attention(2, 8, 160, 120, 16, 64),
     "logits_to_ids_up2": check_logits_to_ids,
     "logits_to_ids_up1": lambda: check_logits_to_ids(1),
+    "segment_filter_boundaries": check_segment_filter_boundaries,
     "bitmap": check_bitmap,
     "ccl": check_ccl,
     "joint_hist": check_joint_hist,
