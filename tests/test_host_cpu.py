@@ -249,3 +249,64 @@ def test_shard_range_covers_every_frame_once():
                 lo, hi = shard_range(n, r, world)
                 seen += list(range(lo, hi))
             assert seen == list(range(n))
+
+
+# ------------------------------------------------------------------------------------------- host logic of the 8f rows
+def test_vae_image_state_dict_key_translation_and_guards():
+    """GeneralVAEImage.load_state_dict: decoder / post_quant_conv keys are dropped (main_ldm.py:139), the pre-0.15
+    diffusers AttentionBlock names map onto to_q / to_k / to_v / to_out.0; compute without a GPU fails loudly."""
+    from oracle import vae_image_oracle as VO
+    from video_latent_diffusion_panoptic_segmentation_b200.ldmseg.models import GeneralVAEImage
+    sd = VO.VAEImageOracle(block_out_channels=(64, 64, 128, 128)).state_dict()
+    old = {}
+    for k, v in sd.items():
+        for new_name, old_name in (("to_q", "query"), ("to_k", "key"), ("to_v", "value"), ("to_out.0", "proj_attn")):
+            if f".attentions.0.{new_name}." in k:
+                k = k.replace(f".{new_name}.", f".{old_name}.")
+        old[k] = v
+    old["decoder.conv_in.weight"] = torch.zeros(1)
+    old["post_quant_conv.weight"] = torch.zeros(1)
+    m = GeneralVAEImage(device="cpu", block_out_channels=(64, 64, 128, 128))
+    m.load_state_dict(old)
+    assert sorted(m.state_dict()) == sorted(sd)
+    m.set_scaling_factor(0.5)
+    assert m.scaling_factor == 0.5
+    with pytest.raises(L.LdmError):
+        m.encode(torch.zeros(1, 3, 64, 64))
+    with pytest.raises(NotImplementedError):
+        GeneralVAEImage(device="cpu", block_out_channels=(32, 64))
+
+
+def test_trainer_descriptor_branches_on_cpu():
+    """TrainerDiffusion._descriptors (trainers_ldm_cond.py:1100-1122): text encoder -> (text, uncond) contexts of the
+    tokenizer's max length; image descriptor model -> one context, [B, C, n] -> [B, n, C]; p_get mirrors rgb_size."""
+    from types import SimpleNamespace
+    from video_latent_diffusion_panoptic_segmentation_b200.ldmseg.trainers import TrainerDiffusion
+    from video_latent_diffusion_panoptic_segmentation_b200.ldmseg.trainers.trainers_ldm_cond import p_get
+
+    class Tok:
+        model_max_length = 6
+
+        def __call__(self, texts, padding=None, max_length=None, truncation=True, return_tensors="pt"):
+            ids = torch.zeros((len(texts), max_length), dtype=torch.long)
+            for i, t in enumerate(texts):
+                ids[i, :min(len(t), max_length)] = 1
+            return SimpleNamespace(input_ids=ids)
+
+    class Enc(torch.nn.Module):
+        def forward(self, ids):
+            return (torch.nn.functional.one_hot(ids, 4).float(),)
+
+    class ToyClipVision(torch.nn.Module):
+        def forward(self, x):
+            assert x.shape[-2:] == (224, 224)  # norm_resize_images: 'clip' in the class name
+            return {"last_feat": torch.ones((x.shape[0], 5, 7))}
+
+    tr = TrainerDiffusion(p={}, tokenizer=Tok(), text_encoder=Enc(), args={"gpu": "cpu"})
+    ctx, unc = tr._descriptors(["ab", "abcd"], None, 2)
+    assert ctx.shape == unc.shape == (2, 6, 4) and unc[..., 0].all() and not torch.equal(ctx, unc)
+    tr = TrainerDiffusion(p={}, image_descriptor_model=ToyClipVision(), args={"gpu": "cpu"})
+    ctx, unc = tr._descriptors([""], torch.rand(1, 3, 32, 48), 1)
+    assert ctx.shape == (1, 7, 5) and unc is None
+    assert p_get({"transformation_kwargs": {"size_rgb": 192}}, "rgb_size") == (192, 192)
+    assert p_get({"rgb_size": (384, 1248)}, "rgb_size") == (384, 1248) and p_get({}, "rgb_size") is None
