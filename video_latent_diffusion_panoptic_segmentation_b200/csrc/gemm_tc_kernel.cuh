@@ -512,6 +512,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             }
             qkv_done = true;
           }
+          if ((p.flags & kQkvStaged) && !qkv_done) {
+            // This tile takes the direct path, whose V^T transpose scratch (sT below) lies inside staging buffer 0: a
+            // TMA store of the previous (q / k) tile may still be reading that buffer. Wait for the reads, all warps.
+            if (epi_leader) bulk_wait_read0();
+            named_bar_sync(1, 32 * kEpiWarps);
+          }
         }
 #pragma unroll
         for (int ci = 0; ci < 4; ++ci) {
