@@ -101,27 +101,28 @@ def reduce_rows(rows, n_windows, device=None):
     world = dist.get_world_size()
     dev = torch.device(device) if (device is not None and dist.get_backend() == "nccl") else torch.device("cpu")
     width = 4 * NUM_CAT + 1
-    cap = torch.tensor([len(rows)], dtype=torch.int64, device=dev)
-    dist.all_reduce(cap, op=dist.ReduceOp.MAX)
-    cap = max(1, int(cap.item()))
-    local = torch.zeros((cap, width), dtype=torch.float64, device=dev)
-    counts = torch.zeros((3, NUM_CAT), dtype=torch.int64, device=dev)
-    for i, r in enumerate(rows):
-        flat = np.concatenate([np.asarray(r[0], np.float64), np.asarray(r[1], np.float64), np.asarray(r[2], np.float64),
-                               np.asarray(r[3], np.float64), np.asarray([r[4]], np.float64)])
-        local[i] = torch.from_numpy(flat).to(dev)
-        for j in range(3):
-            counts[j] += torch.from_numpy(np.asarray(r[1 + j]).astype(np.int64)).to(dev)
     n_local = torch.tensor([len(rows)], dtype=torch.int64, device=dev)
-    dist.all_reduce(counts, op=dist.ReduceOp.SUM)                       # exact integer statistics
     ns = [torch.zeros_like(n_local) for _ in range(world)]
-    dist.all_gather(ns, n_local)
+    dist.all_gather(ns, n_local)                                        # windows per rank (also sizes the row buffer)
+    ns = [int(t.item()) for t in ns]
+    cap = max(1, max(ns))
+    local_h = np.zeros((cap, width), dtype=np.float64)   # assembled on the host, one transfer each
+    counts_h = np.zeros((3, NUM_CAT), dtype=np.int64)
+    for i, r in enumerate(rows):
+        local_h[i] = np.concatenate([np.asarray(r[0], np.float64), np.asarray(r[1], np.float64),
+                                     np.asarray(r[2], np.float64), np.asarray(r[3], np.float64),
+                                     np.asarray([r[4]], np.float64)])
+        for j in range(3):
+            counts_h[j] += np.asarray(r[1 + j]).astype(np.int64)
+    local = torch.from_numpy(local_h).to(dev)
+    counts = torch.from_numpy(counts_h).to(dev)
+    dist.all_reduce(counts, op=dist.ReduceOp.SUM)                       # exact integer statistics
     gathered = [torch.zeros_like(local) for _ in range(world)]
     dist.all_gather(gathered, local)                                    # float rows, added in window order below
     all_rows = []
     for r in range(world):                                              # contiguous shards: rank order == window order
         g = gathered[r].cpu().numpy()
-        for i in range(int(ns[r].item())):
+        for i in range(ns[r]):
             all_rows.append((g[i, 0:20], g[i, 20:40], g[i, 40:60], g[i, 60:80], g[i, 80]))
     if len(all_rows) != n_windows:
         raise RuntimeError(f"reduce_rows: gathered {len(all_rows)} windows, expected {n_windows}")
