@@ -323,6 +323,9 @@ class TrainerDiffusion:
             if "rgb_latents" in data:
                 rgb_latents = data["rgb_latents"].to(self.device)
             else:  # :1234-1239: frames go through the RGB VAE encoder first
+                if self.vae_image is None or "image" not in data:
+                    raise L.LdmError("compute_pq: the batch has no 'rgb_latents'; pass 'image' batches and a vae_image "
+                                     "(GeneralVAEImage) to the trainer")
                 rgb_latents, _ = self.encode_inputs(data["image"].to(self.device), encode_func=self.vae_image.encode,
                                                     scaling_factor=self.vae_image.scaling_factor,
                                                     resize=p_get(self.p, "rgb_size"))
