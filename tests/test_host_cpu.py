@@ -310,3 +310,24 @@ def test_trainer_descriptor_branches_on_cpu():
     assert ctx.shape == (1, 7, 5) and unc is None
     assert p_get({"transformation_kwargs": {"size_rgb": 192}}, "rgb_size") == (192, 192)
     assert p_get({"rgb_size": (384, 1248)}, "rgb_size") == (384, 1248) and p_get({}, "rgb_size") is None
+
+
+def test_scheduler_training_helpers_match_reference_fixture():
+    """add_noise / remove_noise (ddim_scheduler.py:155-216) and compute_loss_weights (:97-117) of the mirror against
+    vectors of the REAL reference scheduler (tests/golden/make_golden_scheduler_extra.py): bit-exact, on the CPU (these
+    helpers are plain tensor math, not kernels). The reference's 'inverse_log_snr' mode raises; no vector for it."""
+    z = np.load(os.path.join(G, "scheduler_extra.npz"))
+    s = DDIMNoiseScheduler(**SCHED_KW)
+    x0, noise, t = torch.from_numpy(z["x0"]), torch.from_numpy(z["noise"]), torch.from_numpy(z["t"])
+    assert torch.equal(s.add_noise(x0, noise.clone(), t), torch.from_numpy(z["noisy"]))
+    assert torch.equal(s.add_noise(x0, noise.clone(), t, scale=0.5), torch.from_numpy(z["noisy_scaled"]))
+    assert torch.equal(s.remove_noise(torch.from_numpy(z["noisy"]), noise, t), torch.from_numpy(z["rec"]))
+    assert torch.equal(s.remove_noise(torch.from_numpy(z["noisy_scaled"]), noise, t, scale=0.5),
+                       torch.from_numpy(z["rec_scaled"]))
+    assert float(s.init_noise_sigma) == float(z["init_noise_sigma"])
+    assert float(s.final_alpha_cumprod) == float(z["final_alpha_cumprod"])
+    for mode in ("none", "max_clamp_snr", "fixed", "linear"):
+        kw = dict(SCHED_KW)
+        kw["weight"] = mode
+        w = DDIMNoiseScheduler(**kw, max_snr=5.0).weights
+        assert np.array_equal(np.asarray(w, dtype=np.float64), z[f"weights_{mode}"]), mode
