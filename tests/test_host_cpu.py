@@ -331,3 +331,22 @@ def test_scheduler_training_helpers_match_reference_fixture():
         kw["weight"] = mode
         w = DDIMNoiseScheduler(**kw, max_snr=5.0).weights
         assert np.array_equal(np.asarray(w, dtype=np.float64), z[f"weights_{mode}"]), mode
+
+
+def test_posterior_matches_reference_fixture():
+    """DiagonalGaussianDistribution mirror (vae.py:371-425) against vectors of the REAL reference class for every act_fn
+    and clamp_output: mean, logvar (clamped at -30 / 20), std, var, kl, get_range and a seeded sample, bit-exact."""
+    from video_latent_diffusion_panoptic_segmentation_b200.ldmseg.models.vae import DiagonalGaussianDistribution
+    z = np.load(os.path.join(G, "posterior.npz"))
+    params = torch.from_numpy(z["params"])
+    for act in ("none", "sigmoid", "tanh", "clip"):
+        for clamp in (False, True):
+            d = DiagonalGaussianDistribution(params.clone(), clamp_output=clamp, act_fn=act)
+            k = f"{act}_{int(clamp)}"
+            for name, got in (("mean", d.mean), ("logvar", d.logvar), ("std", d.std), ("var", d.var), ("kl", d.kl())):
+                assert np.array_equal(got.numpy(), z[f"{k}_{name}"]), (k, name)
+            assert np.array_equal(d.sample(generator=torch.Generator().manual_seed(5)).numpy(), z[k + "_sample"]), k
+            r = d.get_range()
+            assert [float(r.min), float(r.max)] == z[k + "_range"].tolist() and torch.equal(d.mode(), d.mean)
+    with pytest.raises(NotImplementedError):
+        DiagonalGaussianDistribution(params, act_fn="relu")

@@ -35,6 +35,12 @@ class VAEOutput(U.OutputDict):
     posterior: object
 
 
+class RangeDict(U.OutputDict):
+    """vae.py:22-24"""
+    min: torch.Tensor
+    max: torch.Tensor
+
+
 class DiagonalGaussianDistribution:
     """vae.py:371-425 (mean | logvar halves of the encoder's moments; clamp, activation, mode / sample / kl)."""
 
@@ -71,6 +77,13 @@ class DiagonalGaussianDistribution:
 
     def kl(self):
         return 0.5 * torch.sum(torch.pow(self.mean, 2) + self.var - 1.0 - self.logvar, dim=[1, 2, 3])
+
+    def get_range(self):
+        return RangeDict(min=self.mean.min(), max=self.mean.max())
+
+    def __str__(self) -> str:
+        return (f"DiagonalGaussianDistribution(mean={self.mean}, var={self.var}, "
+                f"clamp_output={self.clamp_output}, act_fn={self.act_fn})")
 
 
 def _pad64(c):
