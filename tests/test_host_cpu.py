@@ -350,3 +350,25 @@ def test_posterior_matches_reference_fixture():
             assert [float(r.min), float(r.max)] == z[k + "_range"].tolist() and torch.equal(d.mode(), d.mean)
     with pytest.raises(NotImplementedError):
         DiagonalGaussianDistribution(params, act_fn="relu")
+
+
+def test_output_dict_types_keep_items_and_attributes_in_sync():
+    """T1 (ldmseg/utils/utils.py:26-31 and its subclasses unet.py:20-21, ddim_scheduler.py:21-23, vae.py:22-33):
+    OrderedDict subclasses whose __setitem__ mirrors keys to attributes; construction by keyword goes through it."""
+    from collections import OrderedDict
+    from video_latent_diffusion_panoptic_segmentation_b200.ldmseg.models.unet import UNetOutput
+    from video_latent_diffusion_panoptic_segmentation_b200.ldmseg.models.vae import EncoderOutput, RangeDict, VAEOutput
+    from video_latent_diffusion_panoptic_segmentation_b200.ldmseg.schedulers.ddim_scheduler import DDIMNoiseSchedulerOutput
+    from video_latent_diffusion_panoptic_segmentation_b200.ldmseg.utils import OutputDict
+    t = torch.arange(3.0)
+    o = UNetOutput(sample=t)
+    assert isinstance(o, OutputDict) and isinstance(o, OrderedDict) and o.sample is t and o["sample"] is t
+    o["extra"] = 5
+    assert o.extra == 5 and list(o.keys()) == ["sample", "extra"]
+    s = DDIMNoiseSchedulerOutput(prev_sample=t, pred_original_sample=t + 1)
+    assert s.prev_sample is t and torch.equal(s["pred_original_sample"], t + 1)
+    assert tuple(s.values())[0] is t  # positional unpacking order = insertion order, as callers rely on
+    assert EncoderOutput(latent_dist="d").latent_dist == "d"
+    v = VAEOutput(sample=t, posterior=None)
+    assert v.sample is t and v["posterior"] is None
+    assert RangeDict(min=t.min(), max=t.max()).max == 2.0
