@@ -36,3 +36,28 @@ def test_struct_sizes_match_header_layout():
     assert C.sizeof(L.GemmDesc) == 12 * 8 + 4 + 14 * 4 + 0 or C.sizeof(L.GemmDesc) % 8 == 0
     assert C.sizeof(L.AttnDesc) == 4 * 8 + 6 * 4 + 4 + 4 + 4 + 4  # kv_seq + tail padding to 8 bytes
     assert C.sizeof(L.GroupNormDesc) == 6 * 8 + 5 * 4 + 4 + 4 + 4
+
+
+def test_ctypes_signatures_have_the_declared_arity():
+    """Every prototype of include/ldmseg_b200.h against the ctypes argtypes of _lib.py: same number of parameters, and
+    pointer / integer / floating parameters in the same positions (catches a binding that drifted from the header)."""
+    import ctypes as C
+    src = open(os.path.join(ROOT, "include", "ldmseg_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = re.findall(r"\b(?:int|size_t|long long|const char\*)\s+(ldm_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", src)
+    assert len(protos) == len(L.SIGNATURES)
+    for name, params in protos:
+        params = [p.strip() for p in params.split(",")] if params.strip() not in ("", "void") else []
+        argtypes = L.SIGNATURES[name][1]
+        assert len(params) == len(argtypes), f"{name}: header has {len(params)} parameters, ctypes {len(argtypes)}"
+        for prm, ct in zip(params, argtypes):
+            is_ptr = "*" in prm or prm.startswith("ldm_stream_t")
+            if is_ptr:
+                assert ct is C.c_void_p or isinstance(ct, type) and issubclass(ct, C._Pointer), (name, prm, ct)
+            elif prm.startswith(("float", "double")):
+                assert ct in (C.c_float, C.c_double), (name, prm, ct)
+                assert (ct is C.c_double) == prm.startswith("double"), (name, prm, ct)
+            else:
+                assert ct in (C.c_int, C.c_int32, C.c_int64, C.c_longlong), (name, prm, ct)
+                if prm.startswith("int64_t"):
+                    assert C.sizeof(ct) == 8, (name, prm, ct)
