@@ -61,3 +61,23 @@ def test_ctypes_signatures_have_the_declared_arity():
                 assert ct in (C.c_int, C.c_int32, C.c_int64, C.c_longlong), (name, prm, ct)
                 if prm.startswith("int64_t"):
                     assert C.sizeof(ct) == 8, (name, prm, ct)
+
+
+def test_descriptor_structs_list_the_header_fields_in_order():
+    """ldm_gemm_desc / ldm_attn_desc / ldm_groupnorm_desc: field names and order of the ctypes Structures equal the
+    header's (a reordered or missing field would silently shift every later one)."""
+    src = open(os.path.join(ROOT, "include", "ldmseg_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    for cname, ctype in (("ldm_gemm_desc", L.GemmDesc), ("ldm_attn_desc", L.AttnDesc),
+                         ("ldm_groupnorm_desc", L.GroupNormDesc)):
+        body = re.search(r"typedef struct " + cname + r"\s*\{(.*?)\}\s*" + cname + r"\s*;", src, flags=re.S).group(1)
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            # "const void* a1" / "int32_t B, H, W" / "float ln_eps": the identifiers after the type
+            first, *rest = decl.split(",")
+            names.append(re.findall(r"[A-Za-z_][A-Za-z0-9_]*", first)[-1])
+            names += [r.strip().lstrip("*") for r in rest]
+        assert names == [f[0] for f in ctype._fields_], (cname, names)
