@@ -81,3 +81,32 @@ def test_descriptor_structs_list_the_header_fields_in_order():
             names.append(re.findall(r"[A-Za-z_][A-Za-z0-9_]*", first)[-1])
             names += [r.strip().lstrip("*") for r in rest]
         assert names == [f[0] for f in ctype._fields_], (cname, names)
+
+
+def test_header_compiles_as_c_and_struct_offsets_match_ctypes(tmp_path):
+    """include/ldmseg_b200.h is plain C (gcc -std=c99 -pedantic-errors) and the offsets / sizes the C compiler gives the
+    three descriptor structs are the ones ctypes uses."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        import pytest
+        pytest.skip("no gcc")
+    structs = (("ldm_gemm_desc", L.GemmDesc), ("ldm_attn_desc", L.AttnDesc), ("ldm_groupnorm_desc", L.GroupNormDesc))
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "ldmseg_b200.h"', "int main(void) {"]
+    for cname, ctype in structs:
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for f in ctype._fields_:
+            lines.append(f'  printf("{cname}.{f[0]} %zu\\n", offsetof({cname}, {f[0]}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines) + "\n")
+    exe = tmp_path / "abi"
+    subprocess.run([gcc, "-std=c99", "-pedantic-errors", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    str(src), "-o", str(exe)], check=True, capture_output=True, text=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, ctype in structs:
+        assert int(out[cname]) == C.sizeof(ctype), cname
+        for f in ctype._fields_:
+            assert int(out[f"{cname}.{f[0]}"]) == getattr(ctype, f[0]).offset, (cname, f[0])
