@@ -138,7 +138,7 @@ def build_seg_decoder(seed=0, **kw):
 # ------------------------------------------------------------------------------------------------ sampler
 @torch.no_grad()
 def sample(unet, scheduler, rgb_latents, num_inference_steps=50, seed=None, self_condition=False,
-           return_all_latents=False, noise=None, context=None, uncond_context=None, guidance_scale=7.5):
+           return_all_latents=False, noise=None, context=None, uncond_context=None, guidance_scale=7.5, trace=None):
     """trainers_ldm_cond.py:1048-1173. Default: image_descriptors=remove (no guidance, multiplier 1). With `context`
     [B,L,dim] the UNet gets encoder_hidden_states; with `uncond_context` too, the batch is doubled [uncond | text]
     and the prediction is uncond + guidance_scale * (text - uncond) (:1110-1122,1129,1147-1149).
@@ -162,6 +162,8 @@ def sample(unet, scheduler, rgb_latents, num_inference_steps=50, seed=None, self
         else:
             parts = [latents, rgb_latents] + ([condition] if self_condition else [])
             eps = unet(torch.cat(parts, dim=1).float(), t, encoder_hidden_states=context)
+        if trace is not None:  # (x_t, epsilon) of every step, for the per-step error curves of the parity tests
+            trace.append((latents.clone(), eps.clone()))
         prev, x0 = scheduler.step(eps, t, latents)
         if self_condition:
             condition = x0
@@ -198,6 +200,22 @@ def logits_to_panoptic(logits, mask_th=0.5, count_th=512, overlap_th=0.5, ignore
                 continue
         kept.append(int(label))
     return pred, cleaned, kept
+
+
+@torch.no_grad()
+def pipeline(unet, vae, rgb_latents, num_inference_steps, seed, mask_th=0.5, count_th=512, overlap_th=0.5,
+             ignore_label=127, scheduler=None, trace=None):
+    """The whole reference path for one batch (trainers_ldm_cond.py:1222-1325 with identity resizes): sample ->
+    decode_latents -> per image argmax / threshold / merge. Returns dict(latents, ids, cleaned) with int64 [B,H,W] maps."""
+    scheduler = scheduler or DDIMOracle()
+    latents = sample(unet, scheduler, rgb_latents, num_inference_steps=num_inference_steps, seed=seed, trace=trace)
+    logits = decode_latents(vae, latents)
+    ids, cleaned = [], []
+    for b in range(logits.shape[0]):
+        p, c, _ = logits_to_panoptic(logits[b], mask_th, count_th, overlap_th, ignore_label)
+        ids.append(p)
+        cleaned.append(c)
+    return {"latents": latents, "ids": np.stack(ids), "cleaned": np.stack(cleaned)}
 
 
 # ------------------------------------------------------------------------------------------------ bit codec

@@ -33,6 +33,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+USE_SDPA = False  # module switch, set by bench.py's torch_gpu_baseline leg
+
 SD14 = dict(
     in_channels=4, out_channels=4, block_out_channels=(320, 640, 1280, 1280), layers_per_block=2, heads=8,
     norm_groups=32, norm_eps=1e-5, attn_levels=(True, True, True, False), temb_mult=4,
@@ -103,8 +105,11 @@ class SelfAttn(nn.Module):
             return t.view(b, t.shape[1], self.heads, d).transpose(1, 2)
 
         q, k, v = split(self.to_q(x)), split(self.to_k(ctx)), split(self.to_v(ctx))
-        w = torch.softmax((q @ k.transpose(-1, -2)) * (d ** -0.5), dim=-1)
-        o = (w @ v).transpose(1, 2).reshape(b, n, c)
+        if USE_SDPA:  # the same arithmetic through torch's fused kernel (what current diffusers calls): bench.py's
+            o = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(b, n, c)  # GPU-library baseline leg only
+        else:
+            w = torch.softmax((q @ k.transpose(-1, -2)) * (d ** -0.5), dim=-1)
+            o = (w @ v).transpose(1, 2).reshape(b, n, c)
         return self.to_out[0](o)
 
 

@@ -15,6 +15,9 @@ def pytest_configure(config):
 
 def pytest_collection_modifyitems(config, items):
     import torch
+    # the oracle is the reference's fp32 path: no TF32 in its matmuls / cuDNN convolutions (base.yaml: allow_tf32 False)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
     if torch.cuda.is_available():
         return
     skip = pytest.mark.skip(reason="no CUDA device in this container")

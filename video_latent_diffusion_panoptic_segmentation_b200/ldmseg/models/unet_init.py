@@ -182,3 +182,88 @@ def random_seg_decoder_state_dict(seed=1, **cfg):
 
 def random_vae_image_state_dict(seed=2, **cfg):
     return random_state_dict(vae_image_param_shapes(**cfg), seed)
+
+
+# ------------------------------------------------------------------------------------------------ "trained-like" recipe
+# Plain random init makes the whole tail degenerate: the UNet's epsilon (std 0.3) is a 2 % correction of a final latent
+# that is 15 x the initial noise, the decoder's softmax never reaches mask_th, every pixel becomes void and PQ / DVPQ
+# are 0 = 0. A trained LDMSeg model differs in four ways, and the recipe restores exactly those on top of the random
+# weights (no layer is bypassed or shrunk; every kernel runs on the same dense shapes):
+#   1. the prediction, not the initial noise, determines the final latent     -> conv_out weight and bias x conv_out_gain
+#   2. the prediction follows the image                                       -> init_mode_image='copy' (a reference
+#      mode, ldmseg/models/unet.py:178-233) and image latents that are piecewise constant over drifting Voronoi cells
+#      (ldmseg/data/synthetic.py)
+#   3. the decoder is smooth: its two ConvTranspose2d(2, 2) layers do not invent a different class for each of the 16
+#      sub-pixel positions of a latent pixel                                   -> the four taps of every channel pair
+#      are equal (tap (0, 0) of the random draw): up-sampling + channel mix
+#   4. the classifier head is fitted to its input: a random 256 -> 128 projection slices the features along directions
+#      in which they hardly vary, so the two best classes are within 1 % of each other on a few percent of the pixels
+#      and the id map is speckle. One-shot stand-in for training the head (fit_seg_head): the last conv becomes a
+#      nearest-centroid classifier over k-means centroids of the features of ONE teacher frame (3x3 box filter on all
+#      nine taps, classes beyond the centroids switched off by their bias) -- coherent segments that persist from
+#      frame to frame, margins like a trained model's.
+TRAINED_LIKE = dict(conv_out_gain=32.0, rgb_amplitude=300.0, regions=40, drift=0.5,
+                    head_centroids=48, head_gain=40.0, head_offset=0.5, head_iters=15, head_stride=7)
+TRAINED_LIKE_MODEL_KWARGS = dict(in_channels=8, init_mode_seg="copy", init_mode_image="copy", cond_channels=0)
+
+
+def trained_like_unet_(sd, conv_out_gain=TRAINED_LIKE["conv_out_gain"]):
+    """In place on a UNet state dict (diffusers key names): epsilon x conv_out_gain."""
+    sd["conv_out.weight"] = sd["conv_out.weight"] * conv_out_gain
+    sd["conv_out.bias"] = sd["conv_out.bias"] * conv_out_gain
+    return sd
+
+
+def _decoder_conv_indices(sd):
+    return sorted(int(k.split(".")[1]) for k in sd if k.startswith("decoder.") and k.endswith(".weight")
+                  and sd[k].dim() == 4)
+
+
+def trained_like_seg_decoder_(sd):
+    """In place on a seg-AE state dict: the ConvTranspose2d layers ([cin, cout, 2, 2]) get four equal taps."""
+    for i in _decoder_conv_indices(sd)[1:-1]:
+        wt = sd[f"decoder.{i}.weight"]
+        sd[f"decoder.{i}.weight"] = wt[:, :, :1, :1].expand_as(wt).clone()
+    return sd
+
+
+@torch.no_grad()
+def fit_seg_head(features, out_channels=128, centroids=TRAINED_LIKE["head_centroids"], gain=TRAINED_LIKE["head_gain"],
+                 offset=TRAINED_LIKE["head_offset"], iters=TRAINED_LIKE["head_iters"], stride=TRAINED_LIKE["head_stride"]):
+    """features: [1, C, H, W] f32, the input of the decoder's last conv (GroupNorm + SiLU output) for one teacher
+    frame. Returns (weight [out, C, 3, 3], bias [out]) on the CPU:
+        logit_c(x) = g * ( p_c . (box3x3(f)(x) - mu) - |p_c|^2 / 2 - offset * mean|p|^2 ),    g = gain / mean|p|^2
+    with p_c the k-means centroids (Lloyd, `iters` rounds, started from evenly spaced samples: deterministic) of the
+    centred, box-filtered features sampled every `stride`-th pixel. argmax_c is the nearest centroid; the winner's
+    logit is positive and the others mostly negative, which the merge's sigmoid-overlap test (trainers_ldm_cond.py:
+    1316-1321) needs; classes >= centroids get bias -1e4."""
+    import torch.nn.functional as F
+    f = features.float()
+    C = f.shape[1]
+    fb = F.avg_pool2d(f[:1], 3, 1, 1, count_include_pad=True)      # = conv with w / 9 on all nine taps, zero padding
+    X = fb[0].permute(1, 2, 0).reshape(-1, C)[::stride]
+    mu = X.mean(0)
+    Xc = X - mu
+    P = Xc[torch.linspace(0, Xc.shape[0] - 1, centroids, device=Xc.device).long()].clone()
+    for _ in range(iters):
+        d = (Xc * Xc).sum(1, keepdim=True) - 2.0 * Xc @ P.T + (P * P).sum(1)[None]
+        a = d.argmin(1)
+        for k in range(centroids):
+            m = a == k
+            if bool(m.any()):
+                P[k] = Xc[m].mean(0)
+    n2 = (P * P).sum(1)
+    g = gain / float(n2.mean())
+    weight = torch.zeros((out_channels, C, 3, 3), dtype=torch.float32)
+    bias = torch.full((out_channels,), -1.0e4, dtype=torch.float32)
+    weight[:centroids] = (g * P / 9.0).cpu()[:, :, None, None].expand(centroids, C, 3, 3)
+    bias[:centroids] = (g * (-(P @ mu) - 0.5 * n2 - offset * n2.mean())).cpu()
+    return weight, bias
+
+
+def set_seg_head_(sd, weight, bias):
+    """In place: the last decoder conv of a seg-AE state dict := (weight, bias)."""
+    last = _decoder_conv_indices(sd)[-1]
+    assert sd[f"decoder.{last}.weight"].shape == weight.shape, (sd[f"decoder.{last}.weight"].shape, weight.shape)
+    sd[f"decoder.{last}.weight"], sd[f"decoder.{last}.bias"] = weight.clone(), bias.clone()
+    return sd

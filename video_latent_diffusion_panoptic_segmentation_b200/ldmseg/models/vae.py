@@ -193,6 +193,13 @@ class GeneralVAESeg:
         return logits
 
     @torch.no_grad()
+    def decode_features(self, z, scale=1.0):
+        """The input of the decoder's last conv (GroupNorm + SiLU output, vae.py:163-164) as f32 NCHW [B, dim, 4h, 4w]:
+        what unet_init.fit_seg_head fits the synthetic classifier head to (not on the sampling path)."""
+        self.decode_nhwc(z, scale)
+        return self._bufs[(z.shape[0], z.shape[2], z.shape[3])]["gn"].float().permute(0, 3, 1, 2).contiguous()
+
+    @torch.no_grad()
     def decode(self, z, interpolate=True):
         """vae.py:268-272 -> NCHW fp32 [B, out, f*4h, f*4w] (f = interpolation_factor if interpolate else 1)."""
         logits = self.decode_nhwc(z)

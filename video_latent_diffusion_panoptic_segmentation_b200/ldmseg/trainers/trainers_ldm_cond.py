@@ -82,6 +82,9 @@ class TrainerDiffusion:
         latents = latent_dist.sample() if sample_posterior else latents_mean.clone()
         if resize is not None:
             ls = self.latent_size
+            if ls is None:
+                raise L.LdmError("encode_inputs: resize is set but the trainer has no latent_size (p['latent_size']); "
+                                 "pass resize=None to keep the encoder's own latent size")
             size = (int(ls), int(ls)) if isinstance(ls, int) else tuple(int(v) for v in ls)
             if tuple(latents.shape[-2:]) != size:
                 def rs(t):
@@ -333,12 +336,16 @@ class TrainerDiffusion:
             gt_semseg = ([g.to(self.device) for g in gt_semseg] if isinstance(gt_semseg, (list, tuple))
                          else gt_semseg.to(self.device))
             B = rgb_latents.shape[0]
-            latents = self.sample([""] * B, num_inference_steps, guidance_scale, seed, rgb_latents=rgb_latents,
-                                  scheduler=scheduler, disable_progress_bar=True)
+            rgb_images = data["image"].to(self.device) if "image" in data else None
+            prompts = list(data["text"]) if "text" in data else [""] * B     # :1241-1252: text= and rgb_images=
+            latents = self.sample(prompts, num_inference_steps, guidance_scale, seed, rgb_latents=rgb_latents,
+                                  scheduler=scheduler, disable_progress_bar=True, rgb_images=rgb_images)
             f = self.vae_semseg.downsample_factor
             dec_size = (rgb_latents.shape[-2] * f, rgb_latents.shape[-1] * f)
             masks = data["mask"].to(self.device) if "mask" in data else None
-            rgb_size = tuple(masks.shape[-2:]) if masks is not None else dec_size
+            # :1264-1269: the logits are resized to the size of the RGB input
+            rgb_size = (tuple(rgb_images.shape[-2:]) if rgb_images is not None
+                        else tuple(masks.shape[-2:]) if masks is not None else dec_size)
             im_sizes = [tuple(m["im_size"]) for m in data["meta"]] if "meta" in data else [rgb_size] * B
             identity = (rgb_size == dec_size and all(tuple(sz) == rgb_size for sz in im_sizes)
                         and (masks is None or bool(masks.to(torch.bool).all())))

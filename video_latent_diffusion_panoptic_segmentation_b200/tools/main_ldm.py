@@ -7,17 +7,22 @@
 Same config key names as tools/configs/base/base.yaml (``vae_model_kwargs``, ``model_kwargs``,
 ``noise_scheduler_kwargs``, ``sampling_kwargs``, ``eval_kwargs``) and the same ``main_worker(gpu, ngpus_per_node,
 cfg_dist, p, name)`` signature (:73-79). Hydra is not available here, so dotted ``a.b.c=value`` overrides are parsed
-directly (YAML scalars). Training (everything outside ``eval_only``) is out of scope. Datasets on disk are out of
-scope too: without ``load_path`` the models are random-init and the validation loader is synthetic.
+directly (YAML scalars); ``--config-dir <reference>/tools/configs`` reads the reference's own YAML tree
+(base/base.yaml overlaid with datasets/cityscapes.yaml, as main_ldm.py:41 does) instead of the built-in defaults.
+Training (everything outside ``eval_only``) is out of scope. Datasets on disk are out of scope too: without
+``load_path`` the models are random-init (+ the "trained-like" recipe of unet_init.py) and the validation loader is
+synthetic.
 """
 import copy
 import os
+import re
 import sys
 
 import numpy as np
 import torch
 import yaml
 
+from ..ldmseg.data import synthetic as SY
 from ..ldmseg.models import GeneralVAEImage, GeneralVAESeg, UNet
 from ..ldmseg.models import unet_init
 from ..ldmseg.schedulers import DDIMNoiseScheduler
@@ -49,10 +54,47 @@ BASE = {
     # synthetic validation set (no dataset on disk): frames of `synthetic.size`, `synthetic.frames` of them
     # from_images: the loader yields RGB frames in [0, 1] and the RGB VAE encoder produces the latents (main_ldm.py:138-140,
     # trainers_ldm_cond.py:1234-1239) instead of handing the latents over directly
-    "synthetic": dict(frames=8, size=[384, 1248], batch_size=8, seed=1234, from_images=False),
+    # recipe: "trained_like" (unet_init.TRAINED_LIKE: the tail is not degenerate, segments survive the merge and the
+    # ground truth is derived from a teacher prediction) or "random" (plain torch-default init: every pixel ends up void)
+    "synthetic": dict(frames=8, size=[384, 1248], batch_size=8, seed=1234, from_images=False, recipe="trained_like"),
 }
+# the keys of BASE that exist in the reference's YAML tree (tests/test_host_cpu.py checks them against the parsed files)
+YAML_KEYS = ("eval_only", "load_path", "image_scaling_factor", "vae_model_kwargs", "model_kwargs",
+             "noise_scheduler_kwargs", "sampling_kwargs", "eval_kwargs", "num_classes", "ignore_label")
+TRAIN_KWARGS_KEYS = ("image_descriptors", "self_condition", "weight_dtype", "fp16", "freeze_layers")
 DIST = {"world_size": 1, "rank": 0, "dist_url": "tcp://127.0.0.1:54288", "dist_backend": "nccl",
         "multiprocessing_distributed": False}
+
+
+def load_reference_config(config_dir):
+    """The reference's config tree as main_ldm.py:31-41 assembles it: ``base/base.yaml`` overlaid with
+    ``datasets/cityscapes.yaml`` (``cfg_base | cfg_dataset``) and ``distributed/local.yaml``. base.yaml:177-178 reads
+    ``train_db_name:cityscapes`` / ``val_db_name:cityscapes`` without the space YAML requires after a key (PyYAML
+    rejects the file as it stands); those two lines are repaired before parsing, nothing else is touched.
+    Returns (p, cfg_dist)."""
+    def read(rel):
+        with open(os.path.join(config_dir, rel)) as f:
+            text = re.sub(r"(?m)^(\w+):(?=\S)", r"\1: ", f.read())
+        return yaml.safe_load(text) or {}
+    base, dataset = read("base/base.yaml"), read("datasets/cityscapes.yaml")
+    p = dict(base)
+    p.update(dataset)
+    dist_path = os.path.join(config_dir, "distributed", "local.yaml")
+    cfg_dist = read("distributed/local.yaml") if os.path.exists(dist_path) else dict(DIST)
+    return p, cfg_dist
+
+
+def from_reference_config(config_dir):
+    """BASE with every key the sampling path reads replaced by the reference YAML's value (+ the synthetic section)."""
+    ref, cfg_dist = load_reference_config(config_dir)
+    p = copy.deepcopy(BASE)
+    for k in YAML_KEYS:
+        if k in ref:
+            p[k] = copy.deepcopy(ref[k])
+    p["train_kwargs"] = dict(ref.get("train_kwargs", BASE["train_kwargs"]))
+    if "transformation_kwargs" in ref:
+        p["transformation_kwargs"] = copy.deepcopy(ref["transformation_kwargs"])
+    return p, cfg_dist
 
 
 def apply_overrides(cfg, overrides):
@@ -71,20 +113,33 @@ def apply_overrides(cfg, overrides):
     return cfg
 
 
+def recipe_of(p):
+    return p.get("synthetic", {}).get("recipe", "random")
+
+
 def build_models(p, device, seed=0):
-    """main_ldm.py:138-176: seg-AE, UNet (+ remove_cross_attention, modify_encoder), scheduler."""
+    """main_ldm.py:138-176: seg-AE, UNet (+ remove_cross_attention, modify_encoder), scheduler. Without checkpoints the
+    weights are random (torch defaults); with ``synthetic.recipe == "trained_like"`` the gains / smoothing of
+    unet_init.TRAINED_LIKE are applied on top (the classifier head is fitted later, see fit_trained_like_head)."""
+    trained_like = recipe_of(p) == "trained_like"
     vae = GeneralVAESeg(**{k: v for k, v in p["vae_model_kwargs"].items()}, device=device)
     if p["vae_model_kwargs"].get("pretrained_path") is None:
         vk = p["vae_model_kwargs"]
-        vae.load_state_dict(unet_init.random_seg_decoder_state_dict(
+        vsd = unet_init.random_seg_decoder_state_dict(
             seed=seed + 1, out_channels=vk["out_channels"], int_channels=vk["int_channels"],
             latent_channels=vk["latent_channels"], num_upscalers=vk["num_upscalers"],
-            upscale_channels=vk["upscale_channels"]))
+            upscale_channels=vk["upscale_channels"])
+        if trained_like:
+            unet_init.trained_like_seg_decoder_(vsd)
+        vae.load_state_dict(vsd)
     unet = UNet(device=device)
     desc = p["train_kwargs"].get("image_descriptors", "remove")
     # stands in for from_pretrained (SD-1.4 has cross_attention_dim 768; without it the attn2 weights are not drawn)
-    unet.load_state_dict(unet_init.random_unet_state_dict(seed=seed, in_channels=4,
-                                                          cross_attention_dim=None if desc == "remove" else 768))
+    usd = unet_init.random_unet_state_dict(seed=seed, in_channels=4,
+                                           cross_attention_dim=None if desc == "remove" else 768)
+    if trained_like:
+        unet_init.trained_like_unet_(usd)
+    unet.load_state_dict(usd)
     if desc == "remove":        # descriptors.py:93-95
         unet.remove_cross_attention()
     elif desc == "learnable":   # descriptors.py:89-91: 128 learnable object queries are the cross-attention context
@@ -94,10 +149,28 @@ def build_models(p, device, seed=0):
         raise NotImplementedError(f"image_descriptors={desc!r} needs a CLIP text / vision encoder, which is outside "
                                   "this path (SURVEY section 8(f) rank 4 covers the UNet's cross-attention itself)")
     torch.manual_seed(seed)
-    unet.modify_encoder(**p["model_kwargs"])
+    mk = dict(p["model_kwargs"])
+    if trained_like:  # the prediction follows the image (a trained model's image weights are not zero)
+        mk["init_mode_image"] = unet_init.TRAINED_LIKE_MODEL_KWARGS["init_mode_image"]
+    unet.modify_encoder(**mk)
     unet.freeze_layers(p["train_kwargs"].get("freeze_layers", []))
     sched = DDIMNoiseScheduler(**p["noise_scheduler_kwargs"], device=device)
     return vae, unet, sched
+
+
+@torch.no_grad()
+def fit_trained_like_head(trainer, latent_hw, num_inference_steps, seed=42, data_seed=1234):
+    """Step 4 of the trained-like recipe: sample global frame 0 of the synthetic clip alone (batch 1: the same launch
+    shapes, hence the same head, on every rank and at every world size), take the decoder features in front of the last
+    conv and fit the nearest-centroid head to them. Returns the teacher latents."""
+    vae = trainer.vae_semseg
+    h, w = latent_hw
+    rgb0 = SY.trained_like_rgb_latents(1, h, w, seed=data_seed).to(trainer.device)
+    lat = trainer.sample([""], num_inference_steps, seed=seed, rgb_latents=rgb0)
+    feats = vae.decode_features(lat, scale=1.0 / vae.scaling_factor)
+    weight, bias = unet_init.fit_seg_head(feats, out_channels=vae.out_channels)
+    vae.load_state_dict(unet_init.set_seg_head_(vae.state_dict(), weight, bias))
+    return lat
 
 
 def build_vae_image(p, device, seed=0):
@@ -108,11 +181,16 @@ def build_vae_image(p, device, seed=0):
 
 
 def synthetic_batches(p, rank=0, world=1):
-    """Synthetic validation shard of this rank: random RGB latents (N(0,1)*0.18215) + Voronoi ground truth."""
+    """Synthetic validation shard of this rank (frames rank, rank + world, ... as a DistributedSampler deals them,
+    trainers_ldm_cond.py:246-247). Latents handed over directly: the drifting-cell clip of ldmseg/data/synthetic.py
+    (recipe "trained_like") or N(0,1) * 0.18215 ("random"); from_images: RGB frames in [0, 1] for the VAE encoder.
+    The ground truth is a Voronoi map here; main_worker replaces it by one derived from a teacher prediction when the
+    recipe is "trained_like" (a Voronoi map never matches a prediction: TP = 0)."""
     sy = p["synthetic"]
     H, W = sy["size"]
     frames = list(range(sy["frames"]))[rank::world]
     rng = np.random.default_rng(7)
+    trained_like = recipe_of(p) == "trained_like" and not sy.get("from_images", False)
     for i in range(0, len(frames), sy["batch_size"]):
         idx = frames[i:i + sy["batch_size"]]
         g = torch.Generator().manual_seed(sy["seed"] + i + 1000 * rank)
@@ -121,6 +199,9 @@ def synthetic_batches(p, rank=0, world=1):
                  "meta": [{"im_size": (H, W), "image_id": int(j)} for j in idx]}
         if sy.get("from_images", False):
             batch["image"] = torch.rand((len(idx), 3, H, W), generator=g)
+        elif trained_like:
+            batch["rgb_latents"] = torch.cat([SY.trained_like_rgb_latents(1, H // 8, W // 8, seed=sy["seed"],
+                                                                          first_frame=int(j)) for j in idx])
         else:
             batch["rgb_latents"] = p["image_scaling_factor"] * torch.randn((len(idx), 4, H // 8, W // 8), generator=g)
         yield batch
@@ -160,9 +241,18 @@ def main_worker(gpu, ngpus_per_node, cfg_dist, p, name="b200"):
             vae_image.load_state_dict(data["vae_image"])
         if "vae_semseg" in data:
             vae.load_state_dict({k.replace("module.", ""): v for k, v in data["vae_semseg"].items()})
+    T = p["sampling_kwargs"]["num_inference_steps"]
+    batches = list(synthetic_batches(p, rank, world))
+    if recipe_of(p) == "trained_like" and not p.get("load_path") and not p["synthetic"].get("from_images", False):
+        H, W = p["synthetic"]["size"]
+        fit_trained_like_head(trainer, (H // 8, W // 8), T, seed=42, data_seed=p["synthetic"]["seed"])
+        for data in batches:   # teacher pass: the ground truth is a coarse, partly mislabelled copy of the prediction
+            lat = trainer.sample([""] * data["rgb_latents"].shape[0], T, seed=42,
+                                 rgb_latents=data["rgb_latents"].to(device))
+            _, cleaned, _ = trainer.panoptic_ids(lat)
+            data["semseg"] = SY.teacher_ground_truth(cleaned).cpu()
     res = trainer.compute_metrics(["pq"], threshold_output=True, save_images=False, seed=42,
-                                  dataloader=list(synthetic_batches(p, rank, world)),
-                                  num_inference_steps=p["sampling_kwargs"]["num_inference_steps"])
+                                  dataloader=batches, num_inference_steps=T)
     if world > 1:
         torch.distributed.barrier()
     if is_main_process():
@@ -172,9 +262,17 @@ def main_worker(gpu, ngpus_per_node, cfg_dist, p, name="b200"):
 
 def main(argv=None):
     argv = list(sys.argv[1:] if argv is None else argv)
-    p = apply_overrides(copy.deepcopy(BASE), argv)
+    cfg_dist = dict(DIST)
+    if "--config-dir" in argv:
+        i = argv.index("--config-dir")
+        p, cfg_dist = from_reference_config(argv[i + 1])
+        p["eval_only"] = True  # the only branch built here (base.yaml:8 defaults to training)
+        del argv[i:i + 2]
+    else:
+        p = copy.deepcopy(BASE)
+    p = apply_overrides(p, argv)
     gpu = int(os.environ.get("LOCAL_RANK", 0))
-    return main_worker(gpu, torch.cuda.device_count(), dict(DIST), p)
+    return main_worker(gpu, torch.cuda.device_count(), cfg_dist, p)
 
 
 if __name__ == "__main__":
