@@ -296,8 +296,7 @@ class Workload:
             lat = self.tr.sample([""] * (b - a), self.T, seed=None, rgb_latents=rgb, scheduler=self.sched, noise=noise)
             _, cleaned, _ = self.tr.panoptic_ids(lat)
             self.cleaned[a:b] = cleaned
-            for i in range(b - a):
-                self.evaluator.add_image(cleaned[i], gt[i])
+            self.evaluator.add_images(cleaned, gt)    # one labelling + one histogram launch + one D2H per batch
             if not resident:
                 self.ids_host[a:b].copy_(cleaned, non_blocking=True)   # the panoptic ids a caller reads back
         if world > 1:
@@ -411,8 +410,7 @@ def extras(line, wl, plan, args, env):
         ev[1].record()
         _, cleaned, _ = wl.tr.panoptic_ids(lat)
         ev[2].record()
-        for i in range(b - a):
-            wl.evaluator.add_image(cleaned[i], wl.gt_dev[a + i])
+        wl.evaluator.add_images(cleaned, wl.gt_dev[a:b])
         wl.evaluator.evaluate()
         ev[3].record()
         pc, pi = wl.SY.split_cat_ins(cleaned)

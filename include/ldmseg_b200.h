@@ -270,6 +270,25 @@ int ldm_ccl_label4(const int32_t* sem, int32_t target, int32_t* labels, int32_t*
 int ldm_joint_hist(const int32_t* a, const int32_t* b, int64_t n, unsigned long long* keys, int32_t* counts,
                    int32_t capacity, int32_t* overflow, ldm_stream_t stream);
 
+/* Batched front half of CityscapesPanopticEvaluator.add_image (cityscapes_pap_eval.py:66-110) for B images in ONE
+ * sequence of launches: pred_seg int32 [B,H,W] (-1 = void -> ignore_label), gt_sem int32 [B,H,W] ->
+ *   gt_pan  : thing pixels -> sem * max_ins + component (4-connected, scipy numbering per class), ignore_label -> -1
+ *   pred_pan: ignore_label -> 0, thing pixels -> label * max_ins + component, then -1 where gt or pred is ignore_label
+ * thing_slots: int8 [2][256] in device memory, row 0 for the prediction, row 1 for the ground truth: slot index
+ * (0 .. n_things-1) of a thing label, -1 otherwise (labels outside [0, 256) are never things). n_things <= 32.
+ * scratch: ldm_city_pan_scratch_bytes(B,H,W,n_things) bytes. */
+size_t ldm_city_pan_scratch_bytes(int32_t B, int32_t H, int32_t W, int32_t n_things);
+int ldm_city_pan_maps(const int32_t* pred_seg, const int32_t* gt_sem, int32_t* pred_pan, int32_t* gt_pan,
+                      const int8_t* thing_slots, int32_t n_things, int32_t ignore_label, int32_t max_ins,
+                      int32_t* scratch, int32_t B, int32_t H, int32_t W, ldm_stream_t stream);
+/* n_tables joint histograms in one launch (all images of a batch, or all sliding windows of eval/eval_dvpq.py:153-184):
+ * table t counts the pairs (a[t*stride + j], b[t*stride + j]), j < n_per_table (windows of k frames over frame-major
+ * maps: stride = H*W, n_per_table = k*H*W), into keys/counts[t*capacity ...] laid out as in ldm_joint_hist;
+ * overflow[t] is set when table t filled up. */
+int ldm_joint_hist_batch(const int32_t* a, const int32_t* b, int64_t n_per_table, int64_t stride, int32_t n_tables,
+                         unsigned long long* keys, int32_t* counts, int32_t capacity, int32_t* overflow,
+                         ldm_stream_t stream);
+
 /* id-map helpers of CityscapesPanopticEvaluator.add_image (cityscapes_pap_eval.py:66-110):
  *   ldm_pan_insert: pan[i] = target*max_ins + labels[i] where sem[i] == target   (thing -> sem*max_ins + instance)
  *   ldm_id_mask   : x[i] = fill where a[i] == va or (b != NULL and b[i] == vb)     (ignore regions -> -1)        */

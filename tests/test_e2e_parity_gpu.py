@@ -7,9 +7,9 @@ Weights: random init + the "trained-like" recipe (ldmseg/models/unet_init.py) so
 ground truth is a coarse, partly mislabelled copy of the ORACLE's prediction (ldmseg/data/synthetic.py), so TP, FP and
 FN all occur. Stated tolerances:
   |PQ_cuda - PQ_oracle|, |DVPQ_cuda - DVPQ_oracle| (k = 1, 2)  <= 0.1 point          (north_star)
-  share of pixels whose merged id differs                       <= 2 %
-  latents after every DDIM step: relative L2 <= 3e-2, max-abs <= 0.1 * max|ref|     (trajectory, errors accumulate)
-  UNet epsilon on the oracle's own x_t at every step: relative L2 <= 3e-2            (teacher-forced, no accumulation)
+  share of pixels whose merged id differs                       <= 1 %               (measured: 0.4 %)
+  latents after every DDIM step: relative L2 <= 1.5e-2, max-abs <= 2e-2 * max|ref|  (trajectory; measured 5e-3, flat)
+  UNet epsilon on the oracle's own x_t at every step: relative L2 <= 1.5e-2          (teacher-forced; measured 6e-3)
 The per-step curves go to gpurun_out/ (copied to profiles/ by hand after a GPU run).
 """
 import json
@@ -75,7 +75,7 @@ def world():
     return dict(o_unet=o_unet, unet=unet, fitted=fitted, trainer=trainer, hw=(h, w))
 
 
-@pytest.mark.parametrize("T,B", [(10, 2), (50, 1)])
+@pytest.mark.parametrize("T,B", [(10, 8), (50, 8)])
 def test_full_pipeline_pq_dvpq_vs_oracle(world, T, B):
     from oracle import eval_oracle as EO
     from oracle import ldmseg_oracle as LO
@@ -100,7 +100,6 @@ def test_full_pipeline_pq_dvpq_vs_oracle(world, T, B):
 
     # ---- per-step error curves
     curve = []
-    sched_ts = list(LO.DDIMOracle().timesteps)
     o_sched = LO.DDIMOracle()
     o_sched.set_timesteps_inference(T)
     for i, t in enumerate(o_sched.timesteps):
@@ -112,9 +111,10 @@ def test_full_pipeline_pq_dvpq_vs_oracle(world, T, B):
                       "latents_max_abs_over_max_ref": ((lat_steps[i] - nxt).abs().max() / nxt.abs().max()).item(),
                       "eps_rel_l2_teacher_forced": _rel(eps_cuda, eps_ref),
                       "eps_max_abs_over_max_ref": ((eps_cuda - eps_ref).abs().max() / eps_ref.abs().max()).item()})
+    checks = []   # (ok, message): evaluated after the report has been written, so a failing run still leaves its numbers
     for c in curve:
-        assert c["latents_rel_l2"] <= 3e-2 and c["latents_max_abs_over_max_ref"] <= 0.1, c
-        assert c["eps_rel_l2_teacher_forced"] <= 3e-2, c
+        checks.append((c["latents_rel_l2"] <= 1.5e-2 and c["latents_max_abs_over_max_ref"] <= 2e-2, f"latents {c}"))
+        checks.append((c["eps_rel_l2_teacher_forced"] <= 1.5e-2, f"eps {c}"))
 
     # ---- ids
     cl_cuda = cleaned.cpu().numpy().astype(np.int64)
@@ -122,8 +122,8 @@ def test_full_pipeline_pq_dvpq_vs_oracle(world, T, B):
     diff_share = float((cl_cuda != cl_ref).mean())
     kept_ref = [len(np.unique(c[c >= 0])) for c in cl_ref]
     kept_cuda = [len(np.unique(c[c >= 0])) for c in cl_cuda]
-    assert min(kept_ref) >= 10 and min(kept_cuda) >= 10, (kept_ref, kept_cuda)   # not degenerate
-    assert diff_share <= 0.02, diff_share
+    checks.append((min(kept_ref) >= 10 and min(kept_cuda) >= 10, f"degenerate: {kept_ref} {kept_cuda}"))
+    checks.append((diff_share <= 0.01, f"share of different merged ids {diff_share}"))
 
     # ---- PQ: oracle evaluator on the oracle ids vs CUDA evaluator on the CUDA ids, same ground truth
     gt = teacher_ground_truth(torch.from_numpy(cl_ref))
@@ -131,10 +131,10 @@ def test_full_pipeline_pq_dvpq_vs_oracle(world, T, B):
     ev_c = CityscapesPanopticEvaluator(thing_ids={11, 12, 13, 14, 15, 16, 17, 18}, device=DEV)
     for b in range(B):
         ev_o.add_image(cl_ref[b].copy(), gt[b].numpy())
-        ev_c.add_image(cleaned[b], gt[b].to(DEV))
+    ev_c.add_images(cleaned, gt.to(DEV))
     pq_o, pq_c = ev_o.evaluate(), ev_c.evaluate()
-    assert pq_o["tp"] > 0 and pq_o["fp"] > 0 and pq_o["fn"] > 0, pq_o
-    assert abs(pq_o["pq"] - pq_c["pq"]) <= 0.1, (pq_o["pq"], pq_c["pq"])
+    checks.append((pq_o["tp"] > 0 and pq_o["fp"] > 0 and pq_o["fn"] > 0, f"PQ statistics degenerate: {pq_o}"))
+    checks.append((abs(pq_o["pq"] - pq_c["pq"]) <= 0.1, f"PQ oracle {pq_o['pq']} vs cuda {pq_c['pq']}"))
 
     # ---- DVPQ over the batch as a clip, windows of 1 and 2 frames
     gc, gi = split_cat_ins(gt.to(torch.int32), ignore=0)
@@ -149,8 +149,8 @@ def test_full_pipeline_pq_dvpq_vs_oracle(world, T, B):
                 for i in range(B - k + 1)]
         want = EO.dvpq_aggregate(rows)
         got = CD.dvpq_clip_sharded(pc_c, pi_c, gc.to(DEV), gi.to(DEV), n_frames=B, eval_frames=k)
-        assert want["tp"].sum() > 0
-        assert abs(want["pq"] - got["pq"]) <= 0.1, (k, want["pq"], got["pq"])
+        checks.append((want["tp"].sum() > 0, f"DVPQ k={k} has no TP"))
+        checks.append((abs(want["pq"] - got["pq"]) <= 0.1, f"DVPQ k={k}: oracle {want['pq']} vs cuda {got['pq']}"))
         dvpq[k] = {"oracle": float(want["pq"]), "cuda": float(got["pq"]),
                    "oracle_tp_fn_fp": [int(want[x].sum()) for x in ("tp", "fn", "fp")],
                    "cuda_tp_fn_fp": [int(got[x].sum()) for x in ("tp", "fn", "fp")]}
@@ -167,3 +167,5 @@ def test_full_pipeline_pq_dvpq_vs_oracle(world, T, B):
         with open(os.path.join(out, f"e2e_parity_48x156_T{T}_B{B}.json"), "w") as f:
             json.dump(report, f, indent=1)
     print(json.dumps({k_: v for k_, v in report.items() if k_ != "per_step"}))
+    failed = [msg for ok, msg in checks if not ok]
+    assert not failed, failed

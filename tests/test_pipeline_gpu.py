@@ -673,3 +673,63 @@ def test_main_ldm_entry_point(variant):
     assert res["tp"] + res["fn"] > 0  # the synthetic ground truth has segments
     res2 = main_ldm.main_worker(0, 1, dict(main_ldm.DIST), p)
     assert (res2["tp"], res2["fp"], res2["fn"], res2["iou_sum"]) == (res["tp"], res["fp"], res["fn"], res["iou_sum"])
+
+
+def test_batched_evaluator_equals_stepwise_and_oracle():
+    """ldm_city_pan_maps + ldm_joint_hist_batch (one labelling over all thing classes of all images, one histogram launch,
+    one D2H) against the step-by-step form (ldm_ccl_label4 per class ...) and the oracle evaluator: pan maps bit-identical,
+    statistics bit-identical. Inputs: the seeded city cases, the edge cases, and a speckled 8-image batch in which every
+    thing class has hundreds of components (several per warp / per 1024-pixel block, all slots of the rank kernel)."""
+    from oracle import eval_oracle as EO
+    from synth import city_case, edge_cases_city
+    from video_latent_diffusion_panoptic_segmentation_b200 import ops
+    from video_latent_diffusion_panoptic_segmentation_b200.ldmseg.evaluations import CityscapesPanopticEvaluator
+    things = {11, 12, 13, 14, 15, 16, 17, 18}
+    cases = [city_case(s, 96, 160) for s in (3, 4, 5, 6)] + list(edge_cases_city().values())
+    rng = np.random.default_rng(77)
+    speck_pred = rng.integers(-1, 24, size=(8, 120, 200)).astype(np.int64)
+    speck_gt = np.where(rng.random((8, 120, 200)) < 0.5, speck_pred, rng.integers(0, 24, size=(8, 120, 200)))
+    coarse = np.kron(rng.integers(0, 20, size=(8, 15, 25)), np.ones((8, 8), dtype=np.int64))
+    speck_pred[:, :, 96:] = coarse[:, :, 96:]             # half speckle, half 8x8 blocks
+    for pred, gt in cases + [(speck_pred, speck_gt)]:
+        pred3, gt3 = (pred[None], gt[None]) if pred.ndim == 2 else (pred, gt)
+        ev_b = CityscapesPanopticEvaluator(thing_ids=things, device=DEV)
+        ev_s = CityscapesPanopticEvaluator(thing_ids=things, device=DEV)
+        ev_o = EO.CityscapesPQOracle()
+        pt = torch.from_numpy(pred3.astype(np.int32)).to(DEV)
+        gtt = torch.from_numpy(gt3.astype(np.int32)).to(DEV)
+        slots, n_things = ev_b._thing_slots()
+        pp, gp = ops.city_pan_maps(pt, gtt, slots, n_things, 0, 1 << 20)
+        for b in range(pred3.shape[0]):
+            pp_s, gp_s = ev_s.panoptic_maps(pred3[b], gt3[b])
+            assert torch.equal(pp[b], pp_s) and torch.equal(gp[b], gp_s)
+            ev_s.add_image_stepwise(pred3[b], gt3[b])
+            if b < 2:   # (the oracle paints one boolean mask per component: two images of the speckled batch suffice)
+                pp_o, gp_o = ev_o.panoptic_maps(pred3[b].copy(), gt3[b])
+                assert np.array_equal(pp[b].cpu().numpy(), pp_o) and np.array_equal(gp[b].cpu().numpy(), gp_o)
+                ev_o.add_image(pred3[b].copy(), gt3[b])
+        ev_b.add_images(pt, gtt)
+        rb, rs = ev_b.evaluate(), ev_s.evaluate()
+        for k in ("pq", "sq", "rq", "tp", "fp", "fn", "iou_sum"):
+            assert rb[k] == rs[k], k
+        if pred3.shape[0] <= 2:
+            ro = ev_o.evaluate()
+            for k in ("pq", "sq", "rq", "tp", "fp", "fn", "iou_sum"):
+                assert rb[k] == ro[k], k
+        assert rb["per_class"] == rs["per_class"]
+
+
+def test_joint_hist_batch_windows():
+    """Overlapping windows (stride < n_per_table) and a table that has to grow."""
+    from video_latent_diffusion_panoptic_segmentation_b200 import ops
+    rng = np.random.default_rng(5)
+    a = rng.integers(-1, 3000, size=(5, 64, 96)).astype(np.int32)
+    b = rng.integers(0, 7, size=(5, 64, 96)).astype(np.int32)
+    at, bt = torch.from_numpy(a).to(DEV), torch.from_numpy(b).to(DEV)
+    hw = 64 * 96
+    for k in (1, 2, 3):
+        got = ops.joint_hist_batch(at, bt, 5 - k + 1, k * hw, hw, capacity=256)
+        for w, (ga, gb, gc) in enumerate(got):
+            key = a[w:w + k].astype(np.int64).ravel() * 16 + b[w:w + k].ravel()
+            u, c = np.unique(key, return_counts=True)
+            assert np.array_equal(ga * 16 + gb, u) and np.array_equal(gc, c)

@@ -88,6 +88,9 @@ SIGNATURES = {
     "ldm_ccl_scratch_bytes": (C.c_size_t, [c_i32, c_i32, c_i32]),
     "ldm_ccl_label4": (C.c_int, [c_vp, c_i32, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
     "ldm_joint_hist": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i32, c_vp, c_vp]),
+    "ldm_city_pan_scratch_bytes": (C.c_size_t, [c_i32, c_i32, c_i32, c_i32]),
+    "ldm_city_pan_maps": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_i32, c_i32, c_i32, c_vp]),
+    "ldm_joint_hist_batch": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp]),
     "ldm_pan_insert": (C.c_int, [c_vp, c_vp, c_i32, c_i32, c_vp, c_i64, c_vp]),
     "ldm_pan_combine": (C.c_int, [c_vp, c_vp, c_i32, c_vp, c_i64, c_vp]),
     "ldm_id_mask": (C.c_int, [c_vp, c_vp, c_i32, c_vp, c_i32, c_i32, c_i64, c_vp]),

@@ -423,6 +423,169 @@ __global__ void joint_hist_kernel(const int32_t* __restrict__ a, const int32_t* 
 }
 
 
+// ---------------------------------------------------------------- batched panoptic maps of the Cityscapes evaluator
+// One labelling pass for ALL thing classes of ALL images of a batch, prediction and ground truth together
+// (cityscapes_pap_eval.py:66-110). A pixel takes part when slot[map][label] >= 0 (its label is a thing class; `map` is
+// 0 for the B prediction maps, 1 for the B ground-truth maps); two 4-neighbours are connected when they carry the SAME
+// label, so the components are exactly those of the per-class binary masks; scipy numbers the components of one class
+// mask in raster order of their first pixel, i.e. a root's number is its rank among the roots of its own class.
+constexpr int kMaxThings = 32;
+__device__ __forceinline__ int thing_slot(const int8_t* __restrict__ slot, int label) {
+  return (label >= 0 && label < 256) ? (int)slot[label] : -1;
+}
+__global__ void ccl_multi_init_kernel(const int32_t* __restrict__ pred, const int32_t* __restrict__ gt,
+                                      const int8_t* __restrict__ slots, int32_t* __restrict__ L, long long hw, int B,
+                                      int pred_void, int ignore_label) {
+  const long long n = 2ll * B * hw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int img = (int)(i / hw);
+    const bool is_gt = img >= B;
+    int lab = is_gt ? gt[i - (long long)B * hw] : pred[i];
+    if (!is_gt && lab == pred_void) lab = ignore_label;   // pred_seg[pred_seg == -1] = ignore_label (:66)
+    L[i] = thing_slot(slots + (is_gt ? 256 : 0), lab) >= 0 ? (int)(i % hw) : -1;
+  }
+}
+__device__ __forceinline__ int map_label(const int32_t* __restrict__ pred, const int32_t* __restrict__ gt, int img,
+                                         long long px, long long hw, int B, int pred_void, int ignore_label) {
+  if (img >= B) return gt[(long long)(img - B) * hw + px];
+  const int lab = pred[(long long)img * hw + px];
+  return lab == pred_void ? ignore_label : lab;
+}
+__global__ void ccl_multi_merge_kernel(int32_t* __restrict__ Lall, const int32_t* __restrict__ pred,
+                                       const int32_t* __restrict__ gt, int H, int W, int B, int pred_void,
+                                       int ignore_label) {
+  const long long hw = (long long)H * W;
+  const int img = blockIdx.y;
+  int32_t* L = Lall + (long long)img * hw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += (long long)gridDim.x * blockDim.x) {
+    if (L[i] < 0) continue;
+    const int lab = map_label(pred, gt, img, i, hw, B, pred_void, ignore_label);
+    const int x = (int)(i % W);
+    if (x > 0 && L[i - 1] >= 0 && map_label(pred, gt, img, i - 1, hw, B, pred_void, ignore_label) == lab)
+      cc_union(L, (int)i, (int)i - 1);
+    if (i >= W && L[i - W] >= 0 && map_label(pred, gt, img, i - W, hw, B, pred_void, ignore_label) == lab)
+      cc_union(L, (int)i, (int)(i - W));
+  }
+}
+// block_counts layout: [2B images][nslots][nblocks]
+__global__ void ccl_multi_count_kernel(int32_t* __restrict__ Lall, const int32_t* __restrict__ pred,
+                                       const int32_t* __restrict__ gt, const int8_t* __restrict__ slots,
+                                       int32_t* __restrict__ block_counts, long long hw, int B, int nslots,
+                                       int pred_void, int ignore_label) {
+  __shared__ int cnt[kMaxThings];
+  if (threadIdx.x < kMaxThings) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const int img = blockIdx.y;
+  int32_t* L = Lall + (long long)img * hw;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < hw && L[i] >= 0) {
+    const int r = cc_find(L, (int)i);
+    L[i] = r;
+    if (r == (int)i) {
+      const int sl = thing_slot(slots + (img >= B ? 256 : 0), map_label(pred, gt, img, i, hw, B, pred_void, ignore_label));
+      atomicAdd(&cnt[sl], 1);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < nslots)
+    block_counts[((long long)img * nslots + threadIdx.x) * gridDim.x + blockIdx.x] = cnt[threadIdx.x];
+}
+__global__ void ccl_multi_rank_kernel(const int32_t* __restrict__ Lall, const int32_t* __restrict__ pred,
+                                      const int32_t* __restrict__ gt, const int8_t* __restrict__ slots,
+                                      const int32_t* __restrict__ block_offsets, int32_t* __restrict__ rank_all,
+                                      long long hw, int B, int nslots, int pred_void, int ignore_label) {
+  // rank[root pixel] = 1-based number of the component among the components of its class, in raster order of the roots
+  __shared__ int warp_tot[32][kMaxThings];
+  const int img = blockIdx.y;
+  const int32_t* L = Lall + (long long)img * hw;
+  int32_t* rank = rank_all + (long long)img * hw;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int k = lane; k < kMaxThings; k += 32) warp_tot[wid][k] = 0;
+  __syncwarp();
+  const bool root = (i < hw) && (L[i] == (int)i);
+  int sl = -1;
+  if (root) sl = thing_slot(slots + (img >= B ? 256 : 0), map_label(pred, gt, img, i, hw, B, pred_void, ignore_label));
+  const unsigned same = __match_any_sync(0xffffffffu, sl);     // lanes with the same slot (-1: not a root)
+  if (root && lane == __ffs(same) - 1) warp_tot[wid][sl] = __popc(same);
+  __syncthreads();
+  if (root) {
+    int prefix = block_offsets[((long long)img * nslots + sl) * gridDim.x + blockIdx.x];
+    for (int k = 0; k < wid; ++k) prefix += warp_tot[k][sl];
+    prefix += __popc(same & ((1u << lane) - 1));
+    rank[i] = prefix + 1;
+  }
+}
+// pan maps of :76-110 from the labelled roots, both maps of an image in one pass
+__global__ void city_pan_final_kernel(const int32_t* __restrict__ Lall, const int32_t* __restrict__ rank_all,
+                                      const int32_t* __restrict__ pred, const int32_t* __restrict__ gt,
+                                      int32_t* __restrict__ pred_pan, int32_t* __restrict__ gt_pan, long long hw, int B,
+                                      int pred_void, int ignore_label, int max_ins) {
+  const long long n = (long long)B * hw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long img = i / hw;
+    int p = pred[i];
+    if (p == pred_void) p = ignore_label;
+    const int g = gt[i];
+    const int lp = Lall[i], lg = Lall[n + i];
+    // ground truth: thing pixels -> sem * max_ins + component, ignore -> -1 (:46-49)
+    int gp = lg >= 0 ? g * max_ins + rank_all[n + img * hw + lg] : g;
+    if (g == ignore_label) gp = -1;
+    // prediction: zeros, stuff labels copied, thing pixels -> label * max_ins + component (:90-105); ignore -> -1 (:108-110)
+    int pp = lp >= 0 ? p * max_ins + rank_all[img * hw + lp] : p;
+    if (p == ignore_label) pp = 0;
+    if (g == ignore_label || p == ignore_label) pp = -1;
+    gt_pan[i] = gp;
+    pred_pan[i] = pp;
+  }
+}
+// joint histograms of n_tables (possibly overlapping) windows of two id streams: table t counts the pairs
+// (a[t * stride + j], b[t * stride + j]), j < n_per_table, in its own hash table keys/counts[t * cap ...]
+__global__ void joint_hist_batch_kernel(const int32_t* __restrict__ a, const int32_t* __restrict__ b,
+                                        long long n_per_table, long long tstride, unsigned long long* __restrict__ keys_all,
+                                        int32_t* __restrict__ counts_all, int cap, int32_t* __restrict__ overflow) {
+  const int t = blockIdx.y;
+  const int32_t* at = a + (long long)t * tstride;
+  const int32_t* bt = b + (long long)t * tstride;
+  unsigned long long* keys = keys_all + (long long)t * cap;
+  int32_t* counts = counts_all + (long long)t * cap;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long nround = ((n_per_table + stride - 1) / stride) * stride;  // keep warps converged for match_any
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
+    const bool valid = i < n_per_table;
+    const unsigned long long key =
+        valid ? (((unsigned long long)(uint32_t)at[i] << 32) | (unsigned long long)(uint32_t)bt[i]) : kEmptyKey;
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    const int leader = __ffs(peers) - 1;
+    if (valid && (int)(threadIdx.x & 31) == leader) {
+      const int add = __popc(peers);
+      unsigned long long hsh = key * 0x9E3779B97F4A7C15ull;
+      int slot = (int)((hsh >> 32) & (unsigned)(cap - 1));
+      int probes = 0;
+      while (true) {
+        const unsigned long long prev = atomicCAS(&keys[slot], kEmptyKey, key);
+        if (prev == kEmptyKey || prev == key) {
+          atomicAdd(&counts[slot], add);
+          break;
+        }
+        slot = (slot + 1) & (cap - 1);
+        if (++probes >= cap) {
+          overflow[t] = 1;
+          break;
+        }
+      }
+    }
+  }
+}
+__global__ void hash_clear_batch_kernel(unsigned long long* keys, int32_t* counts, long long n, int32_t* overflow,
+                                        int n_tables) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    keys[i] = kEmptyKey;
+    counts[i] = 0;
+    if (i < n_tables) overflow[i] = 0;
+  }
+}
+
 // ---------------------------------------------------------------- small id-map helpers of the PQ evaluators
 __global__ void pan_insert_kernel(const int32_t* __restrict__ sem, const int32_t* __restrict__ labels, int target,
                                   int max_ins, int32_t* __restrict__ pan, long long n) {
@@ -574,6 +737,67 @@ extern "C" int ldm_joint_hist(const int32_t* a, const int32_t* b, int64_t n, uns
   joint_hist_kernel<<<grid1d(n, 256, 8), 256, 0, s>>>(a, b, n, keys, counts, capacity, overflow);
   count_launch(2);
   return check_launch("joint_hist_kernel");
+}
+
+extern "C" size_t ldm_city_pan_scratch_bytes(int32_t B, int32_t H, int32_t W, int32_t n_things) {
+  const long long hw = (long long)H * W;
+  const long long nblocks = (hw + 1023) / 1024;
+  return (size_t)(sizeof(int32_t) * (4ll * B * hw + 2ll * B * n_things * (nblocks + 1)));
+}
+
+extern "C" int ldm_city_pan_maps(const int32_t* pred_seg, const int32_t* gt_sem, int32_t* pred_pan, int32_t* gt_pan,
+                                 const int8_t* thing_slots, int32_t n_things, int32_t ignore_label, int32_t max_ins,
+                                 int32_t* scratch, int32_t B, int32_t H, int32_t W, ldm_stream_t stream) {
+  using namespace ldm_host;
+  LDM_REQUIRE(pred_seg && gt_sem && pred_pan && gt_pan && thing_slots && scratch && B > 0 && H > 0 && W > 0,
+              LDM_ERR_BAD_ARG, "ldm_city_pan_maps: bad arg");
+  LDM_REQUIRE(n_things >= 0 && n_things <= kMaxThings, LDM_ERR_BAD_SHAPE, "ldm_city_pan_maps: at most %d thing classes",
+              kMaxThings);
+  const long long hw = (long long)H * W;
+  LDM_REQUIRE(hw < (1ll << 31) && 255ll * max_ins + hw < (1ll << 31), LDM_ERR_BAD_SHAPE,
+              "ldm_city_pan_maps: ids overflow int32");
+  const long long n2 = 2ll * B * hw;
+  const int nblocks = (int)((hw + 1023) / 1024);
+  const int ns = n_things > 0 ? n_things : 1;
+  int32_t* Lbuf = scratch;
+  int32_t* rank = scratch + n2;
+  int32_t* bcnt = scratch + 2 * n2;
+  int32_t* ncomp = bcnt + 2ll * B * ns * nblocks;
+  cudaStream_t s = as_stream(stream);
+  const int pred_void = -1;
+  ccl_multi_init_kernel<<<grid1d(n2, 256), 256, 0, s>>>(pred_seg, gt_sem, thing_slots, Lbuf, hw, B, pred_void, ignore_label);
+  if (n_things > 0) {
+    ccl_multi_merge_kernel<<<dim3(grid1d(hw, 256, 8), 2 * B), 256, 0, s>>>(Lbuf, pred_seg, gt_sem, H, W, B, pred_void,
+                                                                         ignore_label);
+    ccl_multi_count_kernel<<<dim3(nblocks, 2 * B), 1024, 0, s>>>(Lbuf, pred_seg, gt_sem, thing_slots, bcnt, hw, B, ns,
+                                                                pred_void, ignore_label);
+    ccl_scan_blocks_kernel<<<2 * B * ns, 1024, 0, s>>>(bcnt, ncomp, nblocks);
+    ccl_multi_rank_kernel<<<dim3(nblocks, 2 * B), 1024, 0, s>>>(Lbuf, pred_seg, gt_sem, thing_slots, bcnt, rank, hw, B, ns,
+                                                               pred_void, ignore_label);
+  }
+  city_pan_final_kernel<<<grid1d((long long)B * hw, 256), 256, 0, s>>>(Lbuf, rank, pred_seg, gt_sem, pred_pan, gt_pan, hw,
+                                                                       B, pred_void, ignore_label, max_ins);
+  count_launch(n_things > 0 ? 6 : 2);
+  return check_launch("city_pan_maps kernels");
+}
+
+extern "C" int ldm_joint_hist_batch(const int32_t* a, const int32_t* b, int64_t n_per_table, int64_t stride,
+                                    int32_t n_tables, unsigned long long* keys, int32_t* counts, int32_t capacity,
+                                    int32_t* overflow, ldm_stream_t stream) {
+  using namespace ldm_host;
+  LDM_REQUIRE(a && b && keys && counts && overflow && n_per_table > 0 && stride >= 0 && n_tables > 0, LDM_ERR_BAD_ARG,
+              "ldm_joint_hist_batch: bad arg");
+  LDM_REQUIRE(capacity >= 64 && (capacity & (capacity - 1)) == 0 && n_tables <= 65535, LDM_ERR_BAD_SHAPE,
+              "ldm_joint_hist_batch: capacity must be a power of two >= 64, at most 65535 tables");
+  cudaStream_t s = as_stream(stream);
+  const long long slots = (long long)capacity * n_tables;
+  hash_clear_batch_kernel<<<grid1d(slots > n_tables ? slots : n_tables, 256, 2), 256, 0, s>>>(keys, counts, slots, overflow,
+                                                                                               n_tables);
+  int gx = grid1d(n_per_table, 256, 8) / n_tables;
+  if (gx < 8) gx = 8;
+  joint_hist_batch_kernel<<<dim3(gx, n_tables), 256, 0, s>>>(a, b, n_per_table, stride, keys, counts, capacity, overflow);
+  count_launch(2);
+  return check_launch("joint_hist_batch_kernel");
 }
 
 extern "C" int ldm_pan_insert(const int32_t* sem, const int32_t* labels, int32_t target, int32_t max_ins, int32_t* pan,

@@ -20,7 +20,7 @@ stay on the GPUs that produced them:
 import numpy as np
 import torch
 
-from ..ldmseg.evaluations.new_eval import aggregate, vpq_eval
+from ..ldmseg.evaluations.new_eval import aggregate, vpq_eval, vpq_from_hist
 from .. import ops
 
 i32 = torch.int32
@@ -152,6 +152,16 @@ def dvpq_clip_sharded(pred_cat, pred_ins, gt_cat, gt_ins, n_frames, eval_frames=
     if with_depth:
         maps += [depth_pred, depth_gt]
     ext = exchange_halo(maps, k - 1, n_frames)
+    n_win = max(0, min(hi, n_frames - k + 1) - lo)
+    if eval_fn is None and not with_depth and n_win > 0:
+        # all windows of this rank at once: pan ids of every frame, ONE launch for the n_win joint histograms (window
+        # i = frames [i, i + k) of the frame-major maps), ONE device->host copy, then the reference's matching loops
+        H, W = ext[0].shape[-2:]
+        pred = ops.pan_combine(ext[0].contiguous(), ext[1].contiguous(), max_ins)
+        gt = ops.pan_combine(ext[2].contiguous(), ext[3].contiguous(), max_ins)
+        rows = [vpq_from_hist(g, p, c, max_ins=max_ins) + (0,)
+                for g, p, c in ops.joint_hist_batch(gt, pred, n_win, k * H * W, H * W)]
+        return reduce_rows(rows, max(0, n_frames - k + 1), device=pred_cat.device)
     if eval_fn is None:
         def eval_fn(pc, pi, gc, gi, dp, dg):
             return eval_window_device(pc, pi, gc, gi, dp, dg, depth_thres, max_ins, depth_bits)

@@ -36,10 +36,10 @@ def trained_like_rgb_latents(n_frames, h, w, seed=1234, first_frame=0, amplitude
     return torch.from_numpy(out)
 
 
-def block_majority_labels(ids, block=8, void=-1):
-    """Every block x block tile gets the label that covers most of its pixels in `ids` ([B, H, W] integer tensor, labels
-    >= 0, `void` = -1; ties go to the smaller value, void included). Coarse-graining is neutral: the tile grid knows
-    nothing about where the prediction's boundaries are."""
+def block_majority_tiles(ids, block=8, void=-1):
+    """[B, H, W] integer ids (labels >= 0, `void` = -1) -> [B, ceil(H/block), ceil(W/block)] int64: for every
+    block x block tile the value that covers most of its pixels (ties go to the smaller value, void included).
+    Coarse-graining is neutral: the tile grid knows nothing about where the prediction's boundaries are."""
     B, H, W = ids.shape
     hb, wb = (H + block - 1) // block, (W + block - 1) // block
     lab = ids.long() - void                                     # void -> 0, label l -> l + 1
@@ -49,31 +49,54 @@ def block_majority_labels(ids, block=8, void=-1):
     tile = (ty[:, None] * wb + tx[None, :]).expand(B, H, W)
     key = (torch.arange(B, device=ids.device)[:, None, None] * (hb * wb) + tile) * n + lab
     hist = torch.bincount(key.reshape(-1), minlength=B * hb * wb * n).view(B, hb * wb, n)
-    win = hist.argmax(dim=2)                                    # first maximum = smallest value
-    return (win.gather(1, tile.reshape(B, -1)).view(B, H, W) + void).to(ids.dtype)
+    return (hist.argmax(dim=2) + void).view(B, hb, wb)          # first maximum = smallest value
 
 
-def teacher_ground_truth(ids, block=8, min_area=4096, relabel_every=4, relabel_offset=128):
-    """Synthetic ground-truth labels [B, H, W] (same dtype as `ids`, 0 = ignore as in the Cityscapes evaluator,
+def block_majority_labels(ids, block=8, void=-1):
+    """block_majority_tiles expanded back to [B, H, W] (same dtype as `ids`)."""
+    B, H, W = ids.shape
+    t = block_majority_tiles(ids, block, void)
+    return t.repeat_interleave(block, 1).repeat_interleave(block, 2)[:, :H, :W].to(ids.dtype).contiguous()
+
+
+def teacher_ground_truth(ids, block=8, min_area=4096, relabel_every=4, relabel_offset=128,
+                         thing_ids=(11, 12, 13, 14, 15, 16, 17, 18)):
+    """Synthetic ground-truth labels [B, H, W] (same dtype / device as `ids`; 0 = ignore as in the Cityscapes evaluator,
     cityscapes_pap_eval.py:108-110) derived from a teacher prediction `ids` (-1 = void, labels >= 0):
       * block majority on a `block`-pixel grid (boundaries move by up to block / 2 pixels: matched IoUs land well
         inside (0.5, 1), not at 1);
-      * labels that cover fewer than `min_area` pixels of a frame become ignore (segments near the merge's count_th are
-        the ones a 1 % id difference can create or destroy);
+      * labels that cover fewer than `min_area` pixels of a frame become ignore, and so do the 4-connected components
+        of the thing classes (which the evaluator matches one by one, cityscapes_pap_eval.py:76-84) below that size:
+        an annotation does not contain segments near the size at which a 0.5 % id difference decides a match;
       * every label with ``label % relabel_every == relabel_every - 1`` is renamed ``label + relabel_offset``: a false
         negative for the ground truth and a false positive for the prediction.
-    Label 0 of the prediction is void for the evaluator (pred == 0 is its ignore label too), hence ignore here."""
-    gt = block_majority_labels(ids, block)
-    B = gt.shape[0]
-    n = int(gt.max().item()) + 2
-    area = torch.stack([torch.bincount((gt[b] + 1).reshape(-1).long(), minlength=n) for b in range(B)])   # [B, n]
-    small = area < min_area
-    small[:, :2] = True                                          # void (-1) and label 0
-    drop = small.gather(1, (gt + 1).reshape(B, -1).long()).view_as(gt)
-    out = torch.where(drop, torch.zeros_like(gt), gt)
-    if relabel_every > 0:
-        out = torch.where((out > 0) & (out % relabel_every == relabel_every - 1), out + relabel_offset, out)
-    return out
+    Label 0 of the prediction is void for the evaluator (pred == 0 is its ignore label too), hence ignore here. The
+    filters work on the tile map (48 x 156 tiles for a 384 x 1248 frame) on the host: input generation, not the path."""
+    from scipy import ndimage
+    B, H, W = ids.shape
+    tiles = block_majority_tiles(ids, block).cpu().numpy()       # [B, hb, wb] int64
+    px = block * block
+    out = np.zeros_like(tiles)
+    for b in range(B):
+        t = tiles[b]
+        keep = np.zeros_like(t, dtype=bool)
+        for lab in np.unique(t):
+            if lab <= 0:
+                continue
+            m = t == lab
+            if int(m.sum()) * px < min_area:
+                continue
+            if int(lab) in thing_ids:
+                cc, n = ndimage.label(m)                         # 4-connectivity: the evaluator's components
+                sizes = np.bincount(cc.ravel(), minlength=n + 1) * px
+                m = m & (sizes[cc] >= min_area)
+            keep |= m
+        g = np.where(keep, t, 0)
+        if relabel_every > 0:
+            g = np.where((g > 0) & (g % relabel_every == relabel_every - 1), g + relabel_offset, g)
+        out[b] = g
+    gt = torch.from_numpy(out).to(ids.device)
+    return gt.repeat_interleave(block, 1).repeat_interleave(block, 2)[:, :H, :W].to(ids.dtype).contiguous()
 
 
 def split_cat_ins(ids, n_cat=19, void_cat=19, void=-1, ignore=None, ignore_cat=255):

@@ -1,11 +1,14 @@
 """B200 mirror of ``CityscapesPanopticEvaluator`` (ldmseg/evaluations/cityscapes_pap_eval.py:9-249).
 
 The reference labels connected components with scipy on the CPU and then computes an O(#gt x #pred x H x W) table of
-boolean-mask IoUs. Here the pixel work is three kinds of integer kernels on the GPU --
-4-connected component labelling with scipy numbering (ldm_ccl_label4), id-map composition (ldm_pan_insert /
-ldm_id_mask) and ONE joint (gt, pred) id histogram (ldm_joint_hist) -- after which every mask intersection / area
-is an integer in a table of a few hundred entries, and the reference's greedy matching (:119-174) runs on those
-integers in the same order, with the same float64 divisions, so TP / FP / FN / iou_sum are bit-identical.
+boolean-mask IoUs. Here the pixel work of a whole BATCH of images is two C-ABI calls --
+``ldm_city_pan_maps`` (one 4-connected component labelling over all thing classes of all predictions and ground truths
+at once, scipy numbering per class, and the composition of both panoptic id maps) and ``ldm_joint_hist_batch`` (one
+(gt, pred) id histogram per image) -- and ONE device->host copy of the histogram tables, after which every mask
+intersection / area is an integer in a table of a few hundred entries, and the reference's greedy matching (:119-174)
+runs on those integers in the same order, with the same float64 divisions, so TP / FP / FN / iou_sum are bit-identical.
+``panoptic_maps`` keeps the step-by-step form (ldm_ccl_label4 per class, ldm_pan_insert, ldm_id_mask) that the batched
+kernels are tested against.
 """
 import numpy as np
 import torch
@@ -67,9 +70,44 @@ class CityscapesPanopticEvaluator:
     def _cat(self, i):
         return (i // self.max_ins) if i >= self.max_ins else i
 
+    def _thing_slots(self):
+        """int8 [2, 256] device table for ldm_city_pan_maps: row 0 prediction (the ignore label is never a thing there,
+        :97-98), row 1 ground truth."""
+        if getattr(self, "_slots", None) is None:
+            things = sorted(t for t in self.thing_ids if 0 <= t < 256)
+            if len(things) != len(self.thing_ids) or len(things) > 32:
+                raise ValueError("thing ids must lie in [0, 256) and number at most 32")
+            tab = np.full((2, 256), -1, np.int8)
+            for i, t in enumerate(things):
+                tab[1, t] = i
+                if t != self.ignore_label:
+                    tab[0, t] = i
+            self._slots = (torch.from_numpy(tab).to(self.device), len(things))
+        return self._slots
+
+    def add_images(self, pred_segs, gt_semsegs):
+        """add_image for a batch ([B,H,W] int32 device tensors, or anything add_image takes stacked along dim 0):
+        two kernel sequences and one device->host copy for the whole batch."""
+        dev = self.device
+        pred = _to_dev_i32(pred_segs, dev)
+        gt = _to_dev_i32(gt_semsegs, dev)
+        if pred.dim() == 2:
+            pred, gt = pred[None], gt[None]
+        slots, n_things = self._thing_slots()
+        pred_pan, gt_pan = ops.city_pan_maps(pred, gt, slots, n_things, self.ignore_label, self.max_ins)
+        B, H, W = pred.shape
+        for g, p, c in ops.joint_hist_batch(gt_pan, pred_pan, B, H * W, H * W):
+            self._match(g, p, c)
+
     def add_image(self, pred_seg, gt_semseg):
+        self.add_images(pred_seg, gt_semseg)
+
+    def add_image_stepwise(self, pred_seg, gt_semseg):
+        """The unbatched form (one labelling per thing class): the test reference for add_images."""
         pred_pan, gt_pan = self.panoptic_maps(pred_seg, gt_semseg)
-        g, p, c = ops.joint_hist(gt_pan, pred_pan)
+        self._match(*ops.joint_hist(gt_pan, pred_pan))
+
+    def _match(self, g, p, c):
         gt_area, pred_area, joint = {}, {}, {}
         for gi, pi, ci in zip(g.tolist(), p.tolist(), c.tolist()):
             gt_area[gi] = gt_area.get(gi, 0) + ci

@@ -30,6 +30,11 @@ def vpq_eval(element, max_ins=2 ** 20, ign_id=255, num_cat=20, guard_union=False
     (iou_per_class, tp_per_class, fn_per_class, fp_per_class), float64[num_cat]."""
     pred_ids, gt_ids = element
     gv, pv, cv = ops.joint_hist(_dev_i32(gt_ids, device), _dev_i32(pred_ids, device))
+    return vpq_from_hist(gv, pv, cv, max_ins=max_ins, ign_id=ign_id, num_cat=num_cat, guard_union=guard_union)
+
+
+def vpq_from_hist(gv, pv, cv, max_ins=2 ** 20, ign_id=255, num_cat=20, guard_union=False):
+    """The matching loops of vpq_eval (eval_dvpq.py:50-101) on a joint (gt, pred) id histogram sorted by (gt, pred)."""
     iou_c, tp_c = np.zeros(num_cat, np.float64), np.zeros(num_cat, np.float64)
     fn_c, fp_c = np.zeros(num_cat, np.float64), np.zeros(num_cat, np.float64)
     gt_area, pred_area, joint = {}, {}, {}

@@ -203,7 +203,8 @@ def random_vae_image_state_dict(seed=2, **cfg):
 #      nine taps, classes beyond the centroids switched off by their bias) -- coherent segments that persist from
 #      frame to frame, margins like a trained model's.
 TRAINED_LIKE = dict(conv_out_gain=32.0, rgb_amplitude=300.0, regions=40, drift=0.5,
-                    head_centroids=48, head_gain=40.0, head_offset=0.5, head_iters=15, head_stride=7)
+                    head_centroids=48, head_gain=40.0, head_offset=1.0, head_iters=15, head_stride=7,
+                    head_skip_labels=(12, 13, 14, 15, 16, 17, 18))
 TRAINED_LIKE_MODEL_KWARGS = dict(in_channels=8, init_mode_seg="copy", init_mode_image="copy", cond_channels=0)
 
 
@@ -229,14 +230,22 @@ def trained_like_seg_decoder_(sd):
 
 @torch.no_grad()
 def fit_seg_head(features, out_channels=128, centroids=TRAINED_LIKE["head_centroids"], gain=TRAINED_LIKE["head_gain"],
-                 offset=TRAINED_LIKE["head_offset"], iters=TRAINED_LIKE["head_iters"], stride=TRAINED_LIKE["head_stride"]):
+                 offset=TRAINED_LIKE["head_offset"], iters=TRAINED_LIKE["head_iters"], stride=TRAINED_LIKE["head_stride"],
+                 skip_labels=TRAINED_LIKE["head_skip_labels"]):
     """features: [1, C, H, W] f32, the input of the decoder's last conv (GroupNorm + SiLU output) for one teacher
     frame. Returns (weight [out, C, 3, 3], bias [out]) on the CPU:
         logit_c(x) = g * ( p_c . (box3x3(f)(x) - mu) - |p_c|^2 / 2 - offset * mean|p|^2 ),    g = gain / mean|p|^2
     with p_c the k-means centroids (Lloyd, `iters` rounds, started from evenly spaced samples: deterministic) of the
-    centred, box-filtered features sampled every `stride`-th pixel. argmax_c is the nearest centroid; the winner's
-    logit is positive and the others mostly negative, which the merge's sigmoid-overlap test (trainers_ldm_cond.py:
-    1316-1321) needs; classes >= centroids get bias -1e4."""
+    centred, box-filtered features sampled every `stride`-th pixel. argmax_c is the nearest centroid. The offset sets
+    how much of the plane a class claims through its sigmoid, i.e. the ratio of the merge's overlap test
+    (argmax area / sigmoid area >= overlap_th, trainers_ldm_cond.py:1316-1321): with `offset` = 1 every class passes
+    with a ratio > 1.3, far from the 0.5 threshold (at offset 0.5 the ratios sit between 0.3 and 0.7 and a 0.5 % id
+    difference decides whether a whole segment survives). Centroid k becomes class ids[k], ids = 0..127 without
+    `skip_labels`: the Cityscapes evaluator splits the labels 11..18 into connected components and counts every
+    unmatched one as a false positive (cityscapes_pap_eval.py:96-105,166-174); a random UNet's texture gives such a
+    label ~15 stray components per frame, so with 8 of 48 slots on thing ids the PQ is dominated by ~120 tiny false
+    positives per frame whose number moves by 1-2 % under a 0.5 % id difference. One slot (11) stays a thing class.
+    The classes without a centroid get bias -1e4."""
     import torch.nn.functional as F
     f = features.float()
     C = f.shape[1]
@@ -256,8 +265,9 @@ def fit_seg_head(features, out_channels=128, centroids=TRAINED_LIKE["head_centro
     g = gain / float(n2.mean())
     weight = torch.zeros((out_channels, C, 3, 3), dtype=torch.float32)
     bias = torch.full((out_channels,), -1.0e4, dtype=torch.float32)
-    weight[:centroids] = (g * P / 9.0).cpu()[:, :, None, None].expand(centroids, C, 3, 3)
-    bias[:centroids] = (g * (-(P @ mu) - 0.5 * n2 - offset * n2.mean())).cpu()
+    ids = torch.tensor([c for c in range(out_channels) if c not in set(skip_labels)][:centroids])
+    weight[ids] = (g * P / 9.0).cpu()[:, :, None, None].expand(centroids, C, 3, 3)
+    bias[ids] = (g * (-(P @ mu) - 0.5 * n2 - offset * n2.mean())).cpu()
     return weight, bias
 
 

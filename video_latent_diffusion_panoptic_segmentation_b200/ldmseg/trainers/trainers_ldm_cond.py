@@ -351,8 +351,7 @@ class TrainerDiffusion:
                         and (masks is None or bool(masks.to(torch.bool).all())))
             if identity:  # every resize / crop of :1264-1284 is the identity: fused tail
                 ids, cleaned, _ = self.panoptic_ids(latents)
-                for b in range(B):
-                    evaluator.add_image(cleaned[b], gt_semseg[b])
+                evaluator.add_images(cleaned, gt_semseg if torch.is_tensor(gt_semseg) else torch.stack(list(gt_semseg)))
                 all_cleaned.append(cleaned)
             else:
                 per_image = self.panoptic_ids_resized(latents, rgb_size, masks, im_sizes)

@@ -305,6 +305,59 @@ def ccl_label4(sem, target):
     return labels, ncomp
 
 
+def _decode_hist_table(k, c):
+    """One hash table (uint64 keys, int32 counts as numpy arrays) -> (a, b, counts) int64 arrays sorted by (a, b)."""
+    import numpy as np
+    used = k != np.uint64(L.HASH_EMPTY)
+    k, c = k[used], c[used].astype(np.int64)
+    av = (k >> np.uint64(32)).astype(np.uint32).view(np.int32).astype(np.int64)
+    bv = (k & np.uint64(0xFFFFFFFF)).astype(np.uint32).view(np.int32).astype(np.int64)
+    order = np.lexsort((bv, av))
+    return av[order], bv[order], c[order]
+
+
+def joint_hist_batch(a, b, n_tables, n_per_table, stride, capacity=1 << 11):
+    """`n_tables` joint histograms in ONE launch and ONE device->host copy: table t counts the pairs
+    (a.flat[t * stride + j], b.flat[t * stride + j]), j < n_per_table (all images of a batch: stride = n_per_table =
+    H * W; sliding windows of k frames: stride = H * W, n_per_table = k * H * W). Returns a list of (a_ids, b_ids,
+    counts) int64 numpy triples sorted by (a, b). The tables start at 2 048 slots and grow 8x when one fills up."""
+    _chk(a, i32, "a"); _chk(b, i32, "b")
+    if (n_tables - 1) * stride + n_per_table > a.numel() or a.numel() != b.numel():
+        raise L.LdmError("joint_hist_batch: the last table reads past the end of the maps")
+    dev = a.device
+    keys = torch.empty((n_tables, capacity), dtype=torch.int64, device=dev)
+    counts = torch.empty((n_tables, capacity), dtype=i32, device=dev)
+    ovf = torch.empty(n_tables, dtype=i32, device=dev)
+    L.check(L.lib().ldm_joint_hist_batch(_p(a), _p(b), n_per_table, stride, n_tables, _p(keys), _p(counts), capacity,
+                                         _p(ovf), _stream()), "ldm_joint_hist_batch")
+    # one packed transfer: [keys as 2 x int32 | counts | overflow]
+    packed = torch.cat([keys.view(i32).reshape(-1), counts.reshape(-1), ovf]).cpu().numpy()
+    nk = n_tables * capacity
+    if packed[3 * nk:].any():
+        if capacity >= 1 << 23:
+            raise L.LdmError("joint_hist_batch: more than 2^23 distinct id pairs in one table")
+        return joint_hist_batch(a, b, n_tables, n_per_table, stride, capacity * 8)
+    import numpy as np
+    k = packed[:2 * nk].view(np.uint64).reshape(n_tables, capacity)
+    c = packed[2 * nk:3 * nk].reshape(n_tables, capacity)
+    return [_decode_hist_table(k[t], c[t]) for t in range(n_tables)]
+
+
+def city_pan_maps(pred_seg, gt_sem, thing_slots, n_things, ignore_label=0, max_ins=1 << 20):
+    """Batched cityscapes_pap_eval.py:66-110: pred_seg / gt_sem i32 [B,H,W] -> (pred_pan, gt_pan) i32 [B,H,W].
+    thing_slots: int8 [2, 256] device tensor (see include/ldmseg_b200.h)."""
+    _chk(pred_seg, i32, "pred_seg"); _chk(gt_sem, i32, "gt_sem"); _chk(thing_slots, torch.int8, "thing_slots")
+    if pred_seg.shape != gt_sem.shape or pred_seg.dim() != 3:
+        raise L.LdmError(f"city_pan_maps: prediction {tuple(pred_seg.shape)} vs ground truth {tuple(gt_sem.shape)}")
+    B, H, W = pred_seg.shape
+    pred_pan, gt_pan = torch.empty_like(pred_seg), torch.empty_like(gt_sem)
+    nbytes = L.lib().ldm_city_pan_scratch_bytes(B, H, W, n_things)
+    scratch = torch.empty(nbytes // 4, dtype=i32, device=pred_seg.device)
+    L.check(L.lib().ldm_city_pan_maps(_p(pred_seg), _p(gt_sem), _p(pred_pan), _p(gt_pan), _p(thing_slots), n_things,
+                                      ignore_label, max_ins, _p(scratch), B, H, W, _stream()), "ldm_city_pan_maps")
+    return pred_pan, gt_pan
+
+
 def joint_hist(a, b, capacity=1 << 10):
     """Counts of distinct (a[i], b[i]) pairs. Returns (a_ids, b_ids, counts) as int64 numpy arrays sorted by
     (a, b) -- i.e. the np.unique(a*offset+b, return_counts=True) of the reference in ascending key order.

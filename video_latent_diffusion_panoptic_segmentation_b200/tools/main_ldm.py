@@ -250,7 +250,7 @@ def main_worker(gpu, ngpus_per_node, cfg_dist, p, name="b200"):
             lat = trainer.sample([""] * data["rgb_latents"].shape[0], T, seed=42,
                                  rgb_latents=data["rgb_latents"].to(device))
             _, cleaned, _ = trainer.panoptic_ids(lat)
-            data["semseg"] = SY.teacher_ground_truth(cleaned).cpu()
+            data["semseg"] = SY.teacher_ground_truth(cleaned, min_area=min(4096, H * W // 64)).cpu()
     res = trainer.compute_metrics(["pq"], threshold_output=True, save_images=False, seed=42,
                                   dataloader=batches, num_inference_steps=T)
     if world > 1:
