@@ -259,10 +259,12 @@ class Workload:
         n = self.n_local
         self.rgb_host = SY.trained_like_rgb_latents(n, self.h, self.w, seed=1234, first_frame=self.lo).pin_memory()
         self.rgb_dev = self.rgb_host.to(dev)
-        self.noise_host = {}   # the reference re-seeds its generator for every batch (:1091-1095, :1246): same noise per batch
-        for b in {self.batch, n % self.batch} - {0}:
-            self.noise_host[b] = torch.randn((b, 4, self.h, self.w), generator=torch.Generator().manual_seed(42)).pin_memory()
-        self.noise_dev = {b: v.to(dev) for b, v in self.noise_host.items()}
+        # Noise belongs to the GLOBAL frame (seed 42 + frame index), so a frame gets the same noise whatever the world
+        # size and batch split are -- the ids digests of different N are then comparable. (The reference re-seeds one
+        # generator per batch, :1091-1095, :1246: its noise depends on how the sampler happened to batch the frames.)
+        self.noise_host = torch.stack([torch.randn((4, self.h, self.w), generator=torch.Generator().manual_seed(42 + f))
+                                       for f in range(self.lo, self.hi)]).pin_memory() if n else torch.empty((0, 4, self.h, self.w))
+        self.noise_dev = self.noise_host.to(dev)
         self.ids_host = torch.empty((n, self.H, self.W), dtype=torch.int32).pin_memory()
         self.cleaned = torch.empty((n, self.H, self.W), dtype=torch.int32, device=dev)
         self.gt_dev = torch.zeros((n, self.H, self.W), dtype=torch.int32, device=dev)
@@ -276,7 +278,7 @@ class Workload:
         """Teacher pass (also the first warm-up): GT = coarse, partly mislabelled copy of this pipeline's own prediction."""
         for a, b in self.batches():
             lat = self.tr.sample([""] * (b - a), self.T, seed=None, rgb_latents=self.rgb_dev[a:b], scheduler=self.sched,
-                                 noise=self.noise_dev[b - a])
+                                 noise=self.noise_dev[a:b])
             _, cleaned, _ = self.tr.panoptic_ids(lat)
             self.gt_dev[a:b] = self.SY.teacher_ground_truth(cleaned)
         self.gt_host = self.gt_dev.cpu().pin_memory()
@@ -288,10 +290,10 @@ class Workload:
         self.evaluator.reset()
         for a, b in self.batches():
             if resident:
-                rgb, noise, gt = self.rgb_dev[a:b], self.noise_dev[b - a], self.gt_dev[a:b]
+                rgb, noise, gt = self.rgb_dev[a:b], self.noise_dev[a:b], self.gt_dev[a:b]
             else:   # host buffers in, ids out: the copies are part of the timed region
                 rgb = self.rgb_host[a:b].to(dev, non_blocking=True)
-                noise = self.noise_host[b - a]
+                noise = self.noise_host[a:b]
                 gt = self.gt_host[a:b].to(dev, non_blocking=True)
             lat = self.tr.sample([""] * (b - a), self.T, seed=None, rgb_latents=rgb, scheduler=self.sched, noise=noise)
             _, cleaned, _ = self.tr.panoptic_ids(lat)
@@ -406,7 +408,7 @@ def extras(line, wl, plan, args, env):
         wl.evaluator.reset()
         ev[0].record()
         lat = wl.tr.sample([""] * (b - a), T, seed=None, rgb_latents=wl.rgb_dev[a:b], scheduler=wl.sched,
-                           noise=wl.noise_dev[b - a])
+                           noise=wl.noise_dev[a:b])
         ev[1].record()
         _, cleaned, _ = wl.tr.panoptic_ids(lat)
         ev[2].record()
@@ -548,7 +550,7 @@ def torch_gpu_baseline(wl, our_fps):
     UO.USE_SDPA = True
     sched = LO.DDIMOracle()
     sched.set_timesteps_inference(T)
-    rgb, lat0 = wl.rgb_dev[:B], wl.noise_dev[B]
+    rgb, lat0 = wl.rgb_dev[:B], wl.noise_dev[:B]
     out = {}
     tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
     try:

@@ -593,6 +593,16 @@ CHECKS = {
     "groupnorm_320": lambda: check_groupnorm(320),
     "groupnorm_960cat": lambda: check_groupnorm(640, 320, 1872),
     "groupnorm_1920cat_nosilu": lambda: check_groupnorm(1280, 640, 468, silu=False, eps=1e-6),
+    # B = 8 at the 48x156 level: the cooperative two-sweep kernel; everything smaller: the one-pass cluster kernel
+    "groupnorm_L0_b8_coop": lambda: check_groupnorm(320, 0, 7488, B=8),
+    "groupnorm_L1_640_b8_tail": lambda: check_groupnorm(640, 0, 1872, B=8),   # slice longer than the register cache
+    "groupnorm_L3_2560cat_b8": lambda: check_groupnorm(1280, 1280, 120, B=8),
+    "groupnorm_L2_1280_b1": lambda: check_groupnorm(1280, 0, 468, B=1),       # 16 channel sets of two groups
+    "groupnorm_L0_320_b1": lambda: check_groupnorm(320, 0, 7488, B=1),
+    "groupnorm_ragged_hw": lambda: check_groupnorm(320, 0, 101, B=3),
+    "groupnorm_tiny_hw": lambda: check_groupnorm(1280, 0, 5, B=2),            # fewer pixels than cluster ranks
+    "groupnorm_cpg8": lambda: check_groupnorm(256, 0, 1000, B=1),
+    "groupnorm_cpg4_cat": lambda: check_groupnorm(64, 64, 3000, B=2, silu=False),
     "gemv": check_gemv,
     "timestep_sinusoid": check_timestep_sinusoid,
     "conv_small_cin": check_conv_small_cin,

@@ -107,7 +107,7 @@ __device__ __forceinline__ void gn_apply_body(float* sh, const __nv_bfloat16* __
   const int b = blockIdx.y;
   const int ppb = blockDim.y;
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  const double n = (double)cpg * (double)HW;
+  const double inv_n = 1.0 / ((double)cpg * (double)HW);  // (one division, off the dependent chain below)
   // fold the per-chunk partials in fp64: kFoldSlices threads per group take every kFoldSlices-th chunk, then one
   // thread per group adds the slices in order (fixed order -> bit-reproducible). (A warp per group with a shuffle tree
   // was measured slower: three rounds of L2 latency for the 32 groups instead of one.)
@@ -134,11 +134,11 @@ __device__ __forceinline__ void gn_apply_body(float* sh, const __nv_bfloat16* __
       a += shd[(sl * groups + g) * 2];
       q += shd[(sl * groups + g) * 2 + 1];
     }
-    const double m = a / n;
-    double var = q / n - m * m;
-    if (var < 0.0) var = 0.0;
+    // (fp64 only for the E[x^2] - mean^2 cancellation: no fp64 division / square root on the critical path)
+    const double m = a * inv_n;
+    const double var = fma(-m, m, q * inv_n);
     sh[g] = (float)m;
-    sh[groups + g] = (float)(1.0 / sqrt(var + (double)eps));
+    sh[groups + g] = rsqrtf(fmaxf((float)var, 0.f) + eps);
   }
   __syncthreads();
   const int c0 = threadIdx.x * 8;
@@ -233,6 +233,185 @@ gn_fused_kernel(const __nv_bfloat16* __restrict__ x1, const __nv_bfloat16* __res
       counters[B + b] = 0u;
     }
   }
+}
+
+// GroupNorm(+SiLU) for the shapes whose image fits the register files of a few SMs (everything below the 48x156 level):
+// ONE pass over HBM, no cooperative launch, no global barrier. A cluster of kGnClu CTAs owns (image, channel set): CTA r
+// takes the r-th pixel slice, keeps its vectors in REGISTERS (kGnRegVec x 16 bytes per thread; a longer slice re-reads
+// its tail from L2), the per-group moments of the slices meet through distributed shared memory (one cluster barrier,
+// folded in rank order in fp64: deterministic), and the apply pass runs from the registers. The channel sets
+// (whole groups, blockIdx.y) only add parallelism. The cooperative kernel above sat on a 15 us floor of launch +
+// global counter barrier + second sweep for these shapes (7 - 57 MB at B = 8, all of them at B = 1).
+constexpr int kGnCluMax = 8;
+
+__device__ __forceinline__ float2 ld_dsmem_f32x2(const float2* p, uint32_t rank) {
+  uint32_t a;
+  float2 v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(a) : "r"(smem_u32(p)), "r"(rank));
+  asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
+  return v;
+}
+
+template <int kGnRegVec>
+__global__ void __launch_bounds__(512, 1)
+gn_cluster_kernel(const __nv_bfloat16* __restrict__ x1, const __nv_bfloat16* __restrict__ x2, int c1, int c2, int HW,
+                  int groups, int slab_c, double inv_n, const float* __restrict__ gamma, const float* __restrict__ beta,
+                  float eps, int silu, __nv_bfloat16* __restrict__ out) {
+  extern __shared__ float sh[];  // [ppb][slab_c] sums | [ppb][slab_c] sums of squares | slice moments | mean, rstd
+  pdl_launch_dependents();
+  pdl_wait();
+  const int C = c1 + c2;
+  const int cpg = C / groups;
+  const int gps = slab_c / cpg;  // groups of this channel set
+  const uint32_t rank = cluster_ctarank();
+  const int nclu = (int)gridDim.x;  // the cluster spans the x dimension: pixel slices of one (image, channel set)
+  const int set = blockIdx.y, b = blockIdx.z;
+  const int v = threadIdx.x, y = threadIdx.y, vps = blockDim.x, ppb = blockDim.y;
+  const int tid = y * vps + v, nthr = vps * ppb;
+  const int cl = v * 8;                 // channel inside the set
+  const int c0 = set * slab_c + cl;     // channel of the virtual concat
+  const __nv_bfloat16* src;
+  int cs;
+  if (c0 < c1) {
+    src = x1 + (long long)b * HW * c1 + c0; cs = c1;
+  } else {
+    src = x2 + (long long)b * HW * c2 + (c0 - c1); cs = c2;
+  }
+  // (scale / shift operands: in flight while the statistics are taken)
+  const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c0)), gb = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
+  const float4 ba = __ldg(reinterpret_cast<const float4*>(beta + c0)), bb = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
+  const int per = (HW + nclu - 1) / nclu;
+  const int p0 = (int)rank * per + y;
+  const int p1 = min(HW, ((int)rank + 1) * per);
+
+  uint4 u[kGnRegVec];
+#pragma unroll
+  for (int k = 0; k < kGnRegVec; ++k) {
+    const int pix = p0 + k * ppb;
+    u[k] = pix < p1 ? ld_nc_v4(src + pix * cs) : make_uint4(0u, 0u, 0u, 0u);
+  }
+  float s[8], ss[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
+  auto acc8 = [&](const uint4& w) {
+    const float2 f0 = unpack_bf16(w.x), f1 = unpack_bf16(w.y), f2 = unpack_bf16(w.z), f3 = unpack_bf16(w.w);
+    const float f[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j] += f[j];
+      ss[j] = fmaf(f[j], f[j], ss[j]);
+    }
+  };
+#pragma unroll
+  for (int k = 0; k < kGnRegVec; ++k) acc8(u[k]);  // (zeros past the slice add nothing)
+  {
+    int pix = p0 + kGnRegVec * ppb;  // a slice longer than the register cache: its tail is read again by the apply pass
+    for (; pix + 3 * ppb < p1; pix += 4 * ppb) {
+      const uint4 w0 = ld_nc_v4(src + pix * cs), w1 = ld_nc_v4(src + (pix + ppb) * cs);
+      const uint4 w2 = ld_nc_v4(src + (pix + 2 * ppb) * cs), w3 = ld_nc_v4(src + (pix + 3 * ppb) * cs);
+      acc8(w0); acc8(w1); acc8(w2); acc8(w3);
+    }
+    for (; pix < p1; pix += ppb) acc8(ld_nc_v4(src + pix * cs));
+  }
+
+  float* shs = sh + y * slab_c + cl;
+  float* shq = sh + (ppb + y) * slab_c + cl;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    shs[j] = s[j];
+    shq[j] = ss[j];
+  }
+  __syncthreads();
+  // Fixed-order folds, short dependency chains (a serial fp64 fold per group cost more than the loads):
+  // every channel over the pixel lanes (fp32, <= 64 terms) ...
+  for (int c = tid; c < 2 * slab_c; c += nthr) {
+    float* col = sh + (c < slab_c ? c : ppb * slab_c + (c - slab_c));
+    float a = 0.f;
+    for (int yy = 0; yy < ppb; ++yy) a += col[yy * slab_c];
+    col[0] = a;
+  }
+  __syncthreads();
+  // ... every group over its channels: one warp per group, lanes stride the channels, xor tree ...
+  float2* part = reinterpret_cast<float2*>(sh + 2 * ppb * slab_c);  // [gps] (sum, sum of squares) of this slice
+  float* stat = reinterpret_cast<float*>(part + gps);                // mean[gps], rstd[gps]
+  {
+    const int warp = tid >> 5, lane = tid & 31, nfull = nthr >> 5;  // (a ragged last warp stays out of the shuffles)
+    if (warp < nfull) {
+      for (int g = warp; g < gps; g += nfull) {
+        float a = 0.f, q = 0.f;
+        for (int c = lane; c < cpg; c += 32) {
+          a += sh[g * cpg + c];
+          q += sh[ppb * slab_c + g * cpg + c];
+        }
+        a = warp_sum(a);
+        q = warp_sum(q);
+        if (lane == 0) part[g] = make_float2(a, q);
+      }
+    }
+  }
+  cluster_sync_all();  // every slice's moments are in its CTA's shared memory
+  // ... and the slices in rank order (fp64 for the E[x^2] - mean^2 cancellation only)
+  if (tid < gps) {
+    float2 pr[kGnCluMax];
+#pragma unroll
+    for (int r = 0; r < kGnCluMax; ++r) pr[r] = r < nclu ? ld_dsmem_f32x2(part + tid, (uint32_t)r) : make_float2(0.f, 0.f);
+    double a = 0.0, q = 0.0;
+#pragma unroll
+    for (int r = 0; r < kGnCluMax; ++r) {
+      a += (double)pr[r].x;
+      q += (double)pr[r].y;
+    }
+    const double m = a * inv_n;
+    double var = fma(-m, m, q * inv_n);
+    stat[tid] = (float)m;
+    stat[gps + tid] = rsqrtf(fmaxf((float)var, 0.f) + eps);
+  }
+  __syncthreads();
+  // no CTA may exit (its shared memory would go away) before every peer has read its moments: arrive now, wait last
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+
+  float sc[8], sf[8];
+  {
+    const float gm[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+    const float bt[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = (cl + j) / cpg;
+      sc[j] = stat[gps + g] * gm[j];
+      sf[j] = fmaf(-stat[g], sc[j], bt[j]);
+    }
+  }
+  __nv_bfloat16* dst = out + (long long)b * HW * C + c0;
+  auto apply8 = [&](const uint4& w, int pix) {
+    const float2 f0 = unpack_bf16(w.x), f1 = unpack_bf16(w.y), f2 = unpack_bf16(w.z), f3 = unpack_bf16(w.w);
+    float f[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float t = fmaf(f[j], sc[j], sf[j]);
+      f[j] = silu ? silu_f(t) : t;
+    }
+    uint4 o;
+    o.x = pack_bf16(f[0], f[1]);
+    o.y = pack_bf16(f[2], f[3]);
+    o.z = pack_bf16(f[4], f[5]);
+    o.w = pack_bf16(f[6], f[7]);
+    *reinterpret_cast<uint4*>(dst + pix * C) = o;
+  };
+#pragma unroll
+  for (int k = 0; k < kGnRegVec; ++k) {
+    const int pix = p0 + k * ppb;
+    if (pix < p1) apply8(u[k], pix);
+  }
+  {
+    int pix = p0 + kGnRegVec * ppb;
+    for (; pix + 3 * ppb < p1; pix += 4 * ppb) {
+      const uint4 w0 = ld_nc_v4(src + pix * cs), w1 = ld_nc_v4(src + (pix + ppb) * cs);
+      const uint4 w2 = ld_nc_v4(src + (pix + 2 * ppb) * cs), w3 = ld_nc_v4(src + (pix + 3 * ppb) * cs);
+      apply8(w0, pix); apply8(w1, pix + ppb); apply8(w2, pix + 2 * ppb); apply8(w3, pix + 3 * ppb);
+    }
+    for (; pix < p1; pix += ppb) apply8(ld_nc_v4(src + pix * cs), pix);
+  }
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // LayerNorm: one warp per row, row cached in registers (C <= 32*8*kMaxVec).
@@ -471,6 +650,54 @@ extern "C" int ldm_groupnorm_silu(const ldm_groupnorm_desc* d, ldm_stream_t stre
   if (ppb < 1) ppb = 1;
   if (ppb > d->HW) ppb = d->HW;
   const int chunks = gn_chunks(d->B, d->HW, ppb);
+  // Small images: the one-pass cluster kernel. Choose (pixel slices per cluster, channel sets of whole groups and whole
+  // 16-byte vectors): as many CTAs as fit one wave, the smallest cluster among equals (no exchange at all when a CTA
+  // can own whole groups of an image), at most max_vec vectors per thread (beyond that the two-sweep kernel wins).
+  {
+    static const int max_vec = [] { const char* e = getenv("LDM_GN_CLUSTER_MAXVEC"); return e ? atoi(e) : 18; }();
+    const int cpg = C / d->groups;
+    int best_clu = 0, best_sets = 0, best_ctas = 0;
+    for (int clu = 1; clu <= kGnCluMax; clu *= 2) {
+      // co-resident clusters at one CTA per SM (measured: 15 clusters of 8 on B200; the GPCs do not all hold 16 free SMs)
+      const int max_clusters = clu == 1 ? num_sms() : (clu == 8 ? 14 : (clu == 4 ? 32 : 68));
+      for (int n_sets = d->groups; n_sets >= 1; n_sets /= 2) {
+        if (d->groups % n_sets) continue;
+        const int slab_c = C / n_sets;
+        if (slab_c % 8 || slab_c % cpg || slab_c / 8 > 512) continue;
+        const int ctas = d->B * clu * n_sets;
+        if (ctas > num_sms() || d->B * n_sets > max_clusters) continue;
+        const int per = (d->HW + clu - 1) / clu;
+        int ppbc = 512 / (slab_c / 8);
+        if (ppbc > per) ppbc = per;
+        if ((slab_c / 8) * ppbc < 32 || (per + ppbc - 1) / ppbc > max_vec) continue;
+        if (ctas > best_ctas) {
+          best_ctas = ctas; best_clu = clu; best_sets = n_sets;
+        }
+      }
+    }
+    if (best_ctas > 0 && (long long)d->HW * (d->c1 > c2 ? d->c1 : c2) < (1LL << 31)) {
+      const int clu = best_clu, slab_c = C / best_sets, cvps = slab_c / 8, gps = slab_c / cpg;
+      const int per = (d->HW + clu - 1) / clu;
+      const int cppb = 512 / cvps < per ? 512 / cvps : per;
+      const int vec = (per + cppb - 1) / cppb;
+      const size_t shc = sizeof(float) * 2 * (size_t)cppb * slab_c + sizeof(float) * 4 * gps;
+      LDM_REQUIRE(shc <= 100 * 1024, LDM_ERR_BAD_SHAPE, "ldm_groupnorm_silu: cluster path smem %zu", shc);
+      auto go = [&](auto kern) -> int {
+        cudaError_t ae = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        if (ae != cudaSuccess) return set_error(LDM_ERR_CUDA, "cudaFuncSetAttribute(gn_cluster): %s", cudaGetErrorString(ae));
+        cudaError_t le = launch_pdl(kern, dim3(clu, best_sets, d->B), dim3(cvps, cppb), shc, s, clu,
+                                    reinterpret_cast<const __nv_bfloat16*>(d->x1), reinterpret_cast<const __nv_bfloat16*>(d->x2),
+                                    d->c1, c2, d->HW, d->groups, slab_c, 1.0 / ((double)cpg * (double)d->HW), d->gamma,
+                                    d->beta, d->eps, d->silu, reinterpret_cast<__nv_bfloat16*>(d->out));
+        if (le != cudaSuccess) return set_error(LDM_ERR_CUDA, "gn_cluster_kernel launch: %s", cudaGetErrorString(le));
+        count_launch();
+        return check_launch("gn_cluster_kernel");
+      };
+      if (vec <= 4) return go(gn_cluster_kernel<4>);
+      if (vec <= 8) return go(gn_cluster_kernel<8>);
+      return go(gn_cluster_kernel<12>);
+    }
+  }
   float* partial = reinterpret_cast<float*>(d->stats);
   const size_t sh1 = sizeof(float) * 2 * (size_t)ppb * C;
   static bool attr_set = false;
