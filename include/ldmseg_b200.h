@@ -35,7 +35,7 @@ enum ldm_status {
   LDM_ERR_DRIVER = -6
 };
 
-int ldm_abi_version(void); /* 2 since ldm_gemm_desc.qkv_part0 / ldm_attn_desc.kv_seq were added */
+int ldm_abi_version(void); /* 3 since ldm_gemm_desc.splitk_ws was added (2: qkv_part0 / ldm_attn_desc.kv_seq) */
 const char* ldm_last_error(void);
 /* 0 when the current device is compute capability 10.0 (B200); LDM_ERR_ARCH otherwise. */
 int ldm_check_device(void);
@@ -94,9 +94,19 @@ typedef struct ldm_gemm_desc {
                            given, a short-K pointwise GEMM adds `residual` on the tensor core: the residual rows
                            are streamed by TMA as extra K blocks against identity weights instead of being read
                            row by row in the epilogue. NULL: always the epilogue path.                    */
+  void* splitk_ws;      /* optional split-K workspace (caller-owned device memory, 16-byte aligned, no initial
+                           contents needed, may be shared by all calls of one stream). When given, launches with
+                           few tiles and a long K (small M: the 6x20 level, or one frame per GPU) cut every tile's K
+                           range into work items that run on different SMs and leave fp32 partial tiles here; a
+                           second small launch adds them in a fixed order (bit-reproducible run to run) and applies
+                           the epilogue. NULL: never split.                                                    */
+  int64_t splitk_ws_bytes;
 } ldm_gemm_desc;
 
 int ldm_gemm_bf16(const ldm_gemm_desc* d, ldm_stream_t stream);
+/* The tiling the calling thread's last ldm_gemm_bf16 launch chose (tests and profiling tools): N tile width, 1 for the
+ * CTA-pair kernel, work items per tile (1 = no split-K). Any pointer may be NULL. */
+int ldm_gemm_last_config(int32_t* block_n, int32_t* pair, int32_t* split_k);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Fused flash-style self-attention, softmax(Q K^T * scale) V, per (image, head).

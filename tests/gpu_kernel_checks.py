@@ -315,6 +315,37 @@ def check_gemm_conv3x3(B=2, H=12, W=39, c1=128, c2=0, N=192, block_n=0):
     return _stats(out, ref, f"conv3x3 B={B} {H}x{W} c1={c1} c2={c2} N={N}", 5e-2, 2e-2)
 
 
+def check_gemm_splitk(B=1, H=6, W=20, c1=1280, c2=0, N=1280, taps=9, residual=True, rowbias=True):
+    """Long K, few tiles: the K range of every tile is cut into work items (ldm_gemm_desc.splitk_ws); the partials are
+    added in slice order by a second small launch, so repeated launches are bit-identical."""
+    x1 = _randn((B, H, W, c1), 36, 1.0, bf16)
+    x2 = _randn((B, H, W, c2), 37, 1.0, bf16) if c2 else None
+    C = c1 + c2
+    wp = _randn((N, taps * C), 38, 0.01, bf16)
+    bias = _randn((N,), 39)
+    rb = _randn((B, N), 41) if rowbias else None
+    res = _randn((B * H * W, N), 40, 1.0, bf16) if residual else None
+    outs = []
+    for _ in range(3):
+        out = _empty((B, H, W, N), dtype=bf16, device=DEV)
+        ops.gemm(x1, wp, out, a2=x2, taps=taps, bias=bias, rowbias=rb, residual=res)
+        outs.append(out)
+    bn, pair, split = ops.gemm_last_config()
+    assert split > 1, f"expected a split-K launch for M={B * H * W} K={taps * C}, got block_n={bn} pair={pair} split={split}"
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]), "split-K launches are not bit-reproducible"
+    xin = x1 if x2 is None else torch.cat([x1, x2], -1)
+    if taps == 9:
+        ref = F.conv2d(xin.float().permute(0, 3, 1, 2), wp.float().view(N, 3, 3, C).permute(0, 3, 1, 2), bias, padding=1)
+        ref = ref.permute(0, 2, 3, 1)
+    else:
+        ref = xin.float() @ wp.float().t() + bias
+    if rowbias:
+        ref = ref + rb.view(B, 1, 1, N)
+    if residual:
+        ref = ref + res.float().view(B, H, W, N)
+    return _stats(outs[0], ref, f"split-K x{split} bn={bn} pair={pair} B={B} {H}x{W} C={C} N={N} taps={taps}", 5e-2, 2e-2)
+
+
 def check_gemm_concat_1x1():
     B, H, W, c1, c2, N = 2, 6, 20, 128, 64, 128
     x1, x2 = _randn((B, H, W, c1), 41, 1.0, bf16), _randn((B, H, W, c2), 42, 1.0, bf16)
@@ -620,6 +651,11 @@ CHECKS = {
     "gemm_conv3x3_L0": lambda: check_gemm_conv3x3(1, 48, 156, 320, 0, 320),
     "gemm_conv3x3_L3": lambda: check_gemm_conv3x3(3, 6, 20, 256, 0, 256),
     "gemm_concat_1x1": check_gemm_concat_1x1,
+    "gemm_splitk_conv_L3_b1": check_gemm_splitk,
+    "gemm_splitk_conv_L3_b8": lambda: check_gemm_splitk(8),
+    "gemm_splitk_conv_L3_cat_b2": lambda: check_gemm_splitk(2, c1=1280, c2=1280, rowbias=False),
+    "gemm_splitk_conv_L2_b1": lambda: check_gemm_splitk(1, 12, 39, 640, 0, 1280, residual=False),
+    "gemm_splitk_1x1_k5120_b1": lambda: check_gemm_splitk(1, 6, 20, 5120, 0, 1280, taps=1, rowbias=False),
     "gemm_geglu": check_gemm_geglu,
     "gemm_qkv_40": check_gemm_qkv,
     "gemm_qkv_160": lambda: check_gemm_qkv(1, 8, 160, 468),

@@ -19,7 +19,7 @@ LDM_GEMM_CONVT_LN_SILU = 1 << 4
 LDM_GEMM_OUT_NCHW_F32 = 1 << 5
 
 HASH_EMPTY = 0x8000000000000000
-ABI_VERSION = 2  # must equal ldm_abi_version() of the built library (descriptor struct layouts)
+ABI_VERSION = 3  # must equal ldm_abi_version() of the built library (descriptor struct layouts)
 
 
 class GemmDesc(C.Structure):
@@ -31,7 +31,7 @@ class GemmDesc(C.Structure):
         ("block_n", c_i32), ("flags", c_i32),
         ("heads", c_i32), ("head_dim", c_i32), ("dpad", c_i32), ("seq", c_i32), ("seq_pad", c_i32),
         ("vt_rows", c_i32), ("n_store", c_i32), ("qkv_part0", c_i32),
-        ("identity", c_vp),
+        ("identity", c_vp), ("splitk_ws", c_vp), ("splitk_ws_bytes", C.c_int64),
     ]
 
 
@@ -59,6 +59,7 @@ SIGNATURES = {
     "ldm_gemm_bf16": (C.c_int, [C.POINTER(GemmDesc), c_vp]),
     "ldm_flash_attn_fwd": (C.c_int, [C.POINTER(AttnDesc), c_vp]),
     "ldm_attn_vt_rows": (C.c_int, [C.c_int]),
+    "ldm_gemm_last_config": (C.c_int, [C.POINTER(c_i32), C.POINTER(c_i32), C.POINTER(c_i32)]),
     "ldm_groupnorm_silu": (C.c_int, [C.POINTER(GroupNormDesc), c_vp]),
     "ldm_groupnorm_scratch_bytes": (C.c_size_t, [c_i32, c_i32]),
     "ldm_layernorm": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_f32, c_vp]),

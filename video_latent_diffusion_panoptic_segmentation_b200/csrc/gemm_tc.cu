@@ -26,6 +26,7 @@ LDM_GEMM_DECLARE(launch_gemm_geglu)
 LDM_GEMM_DECLARE(launch_gemm_qkv)
 LDM_GEMM_DECLARE(launch_gemm_direct)
 LDM_GEMM_DECLARE(launch_gemm_convt)
+LDM_GEMM_DECLARE(launch_gemm_split)
 }  // namespace ldm_gemm
 
 namespace {
@@ -67,28 +68,58 @@ void pick_box(int H, int W, int taps, int* bw_out, int* bh_out) {
 // layers. The pair's cross-CTA accumulator hand-off costs more per item, so short-K GEMMs stay on single CTAs.
 // Avoids the two failure modes of "largest tile that divides N": a second, nearly empty wave (150 tiles on 148 SMs) and a
 // handful of huge tiles when M is small (M = 960 at the 6x20 level).
-int pick_block_n(int N, long m_tiles, long kblocks, int sms, bool pair, int taps, double* cost_out) {
+// Split-K (max_split > 1: the caller has a workspace and a plain bf16 epilogue): each tile becomes `split` work items
+// over contiguous K ranges, which fills the SMs when there are few tiles and lets the wide, cheap-per-column block_n
+// run at small M. An item then writes its 128 x block_n fp32 partial (~8 cycles per column) and a second, small launch
+// (splitk_fixup_kernel: ~3 us of launch + L2 latency, then the partials at L2 bandwidth) finishes the tiles. Adopted
+// only when the model sees a clear gain (12 %): it was fitted on few shapes (tools/bench_gemm_shapes.py).
+int pick_block_n(int N, long m_tiles, long kblocks, int sms, bool pair, int taps, double* cost_out, int max_split = 1,
+                 long ws_floats = 0, int* split_out = nullptr) {
   static const int cands[] = {256, 224, 192, 160, 128, 96};
   static const double mma_single[] = {167, 158, 151, 141, 111, 106};
   static const double mma_pair[] = {160, 149, 136, 124, 99, 92};
-  int best = 256;
-  double best_cost = -1.0;
+  static const int splits[] = {1, 2, 3, 4, 5, 6, 8, 10, 12, 16};
+  int best = 256, best_s = 256, best_split = 1;
+  double best_cost = -1.0, best_cost_s = -1.0;
   const long m_units = pair ? (m_tiles + 1) / 2 : m_tiles;
+  const long m_alloc = pair ? 2 * m_units : m_units;
   const long workers = pair ? sms / 2 : sms;
   for (int i = 0; i < 6; ++i) {
     const int c = cands[i];
     if (c == 224 && taps != 9) continue;  // 224 only pays on the long-K convolutions (and is erratic on short K)
     const long n_tiles = (N + c - 1) / c;
-    const long waves = (m_units * n_tiles + workers - 1) / workers;
-    const double item = (double)kblocks * 4.0 * (pair ? mma_pair[i] : mma_single[i]) +
-                        (pair ? 3300.0 + 11.0 * c : 1000.0 + 17.0 * c);
-    const double cost = (double)waves * item;
-    if (best_cost < 0 || cost < best_cost * 0.999) {
-      best_cost = cost;
-      best = c;
+    for (int si = 0; si < 10; ++si) {
+      const int sp = splits[si];
+      if (sp > max_split) break;
+      if (sp > 1) {
+        if (kblocks / sp < (pair ? 24 : 8)) break;  // an item should still be a pipeline-filling main loop
+        if ((long)sp * m_alloc * n_tiles * c * 128 > ws_floats) break;
+      }
+      const long waves = (m_units * n_tiles * sp + workers - 1) / workers;
+      const double item = (double)((kblocks + sp - 1) / sp) * 4.0 * (pair ? mma_pair[i] : mma_single[i]) +
+                          (pair ? 3300.0 + 11.0 * c : 1000.0 + 17.0 * c) + (sp > 1 ? 8.0 * c : 0.0);
+      double cost = (double)waves * item;
+      if (sp > 1) cost += 6000.0 + (double)sp * m_alloc * n_tiles * c * 128.0 * 4.0 / 2000.0;
+      if (sp == 1) {
+        if (best_cost < 0 || cost < best_cost * 0.999) {
+          best_cost = cost;
+          best = c;
+        }
+      } else if (best_cost_s < 0 || cost < best_cost_s * 0.999) {
+        best_cost_s = cost;
+        best_s = c;
+        best_split = sp;
+      }
     }
   }
+  if (best_cost_s > 0 && best_cost_s < 0.88 * best_cost) {
+    best_cost = best_cost_s;
+    best = best_s;
+  } else {
+    best_split = 1;
+  }
   if (cost_out) *cost_out = best_cost;
+  if (split_out) *split_out = best_split;
   return best;
 }
 
@@ -124,6 +155,96 @@ bool staged_enabled() {
     v = e ? atoi(e) : 1;
   }
   return v != 0;
+}
+
+// LDM_GEMM_SPLITK=0 keeps every tile on one work item (A/B timing)
+bool splitk_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LDM_GEMM_SPLITK");
+    v = e ? atoi(e) : 1;
+  }
+  return v != 0;
+}
+
+thread_local int g_last_cfg[3] = {0, 0, 1};  // block_n, pair, split_k of this thread's last ldm_gemm_bf16 launch
+
+constexpr size_t kSplitCounterBytes = 0;
+
+// Second half of a split-K launch: out = epilogue(sum over the slices, in slice order, of the fp32 partial tiles).
+// One CTA per (tile, 16 output columns): the partials are tile-column-major (lanes = rows: coalesced), the sums cross a
+// small shared-memory transpose, and every row leaves as two 16-byte vectors (one full 32-byte sector).
+struct FixupParams {
+  const float* ws;
+  long long slice_stride;
+  int split, tiles_x, tiles_y, bw, bh, W, H, m_tiles, n_tiles, block_n, N, silu;
+  const float* bias;
+  const float* rowbias;
+  const __nv_bfloat16* residual;
+  __nv_bfloat16* out;
+};
+
+__global__ void __launch_bounds__(256) splitk_fixup_kernel(const FixupParams p) {
+  __shared__ float tile[kBlockM][17];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int cb = blockIdx.x, n_tile = blockIdx.y, m_tile = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long tile_off = ((long long)m_tile * p.n_tiles + n_tile) * (long long)(p.block_n * kBlockM);
+  {
+    // thread: columns cb*16 + warp*2 + {0, 1}, rows lane + 32 i. Four slices of loads in flight, added in slice order.
+    float a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = 0.f;
+    const float* src = p.ws + tile_off + (long long)(cb * 16 + warp * 2) * kBlockM + lane;
+    for (int s0 = 0; s0 < p.split; s0 += 4) {
+      float v[4][8];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          v[q][k] = s0 + q < p.split ? __ldcg(src + (long long)(s0 + q) * p.slice_stride + (k >> 2) * kBlockM + (k & 3) * 32) : 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] += v[q][k];  // (+ 0.0f past the last slice: exact)
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tile[(k & 3) * 32 + lane][warp * 2 + (k >> 2)] = a[k];
+  }
+  __syncthreads();
+  const int r = threadIdx.x >> 1, vec = threadIdx.x & 1;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int b = m_tile / tiles_per_img;
+  const int rem = m_tile - b * tiles_per_img;
+  const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+  const int ly = r / p.bw, lx = r - ly * p.bw;
+  const int y = ty * p.bh + ly, x = tx * p.bw + lx;
+  const int n = n_tile * p.block_n + cb * 16 + vec * 8;
+  if (r >= p.bw * p.bh || y >= p.H || x >= p.W || n >= p.N) return;
+  const long long grow = ((long long)b * p.H + y) * p.W + x;
+  float f[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] = tile[r][vec * 8 + j];
+  if (p.bias) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n)), b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
+    f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+  }
+  if (p.rowbias) {
+    const float* rb = p.rowbias + (long long)b * p.N + n;
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(rb)), b1 = __ldg(reinterpret_cast<const float4*>(rb + 4));
+    f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+  }
+  if (p.residual) {
+    const uint4 u = ld_nc_v4(p.residual + grow * p.N + n);
+    const float2 a0 = unpack_bf16(u.x), a1 = unpack_bf16(u.y), a2 = unpack_bf16(u.z), a3 = unpack_bf16(u.w);
+    f[0] += a0.x; f[1] += a0.y; f[2] += a1.x; f[3] += a1.y; f[4] += a2.x; f[5] += a2.y; f[6] += a3.x; f[7] += a3.y;
+  }
+  if (p.silu) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j]);
+  }
+  store_bf16x8(p.out + grow * p.N + n, f);
 }
 
 // LDM_GEMM_PAIR=0 / 1 forces the single-CTA / CTA-pair kernel (A/B timing); default: the cost model decides.
@@ -171,8 +292,18 @@ extern "C" int ldm_gemm_bf16(const ldm_gemm_desc* d, ldm_stream_t stream) {
   p.kblocks = p.kblocks1 + (c2 + kBlockK - 1) / kBlockK;
   const long kblocks_total = (long)d->taps * p.kblocks;
   double cost1 = 0.0, cost2 = 0.0;
-  const int bn1 = pick_block_n(d->N, p.m_tiles, kblocks_total, num_sms(), false, d->taps, &cost1);
-  const int bn2 = pick_block_n(d->N, p.m_tiles, kblocks_total, num_sms(), true, d->taps, &cost2);
+  // split-K needs the caller's workspace and the plain bf16 [rows, N] epilogue (checked again below)
+  const bool split_ok = d->splitk_ws && d->splitk_ws_bytes > 0 && d->block_n <= 0 &&
+                        !(flags & (LDM_GEMM_OUT_F32 | LDM_GEMM_OUT_NCHW_F32 | LDM_GEMM_QKV_SPLIT |
+                                   LDM_GEMM_CONVT_LN_SILU | LDM_GEMM_GEGLU)) &&
+                        d->N >= 64 && d->N % 8 == 0 && staged_enabled() && splitk_enabled() &&
+                        (reinterpret_cast<uintptr_t>(d->splitk_ws) & 15) == 0;
+  const long ws_floats = split_ok ? (long)((d->splitk_ws_bytes - kSplitCounterBytes) / 4) : 0;
+  int sp1 = 1, sp2 = 1;
+  const int bn1 = pick_block_n(d->N, p.m_tiles, kblocks_total, num_sms(), false, d->taps, &cost1, split_ok ? 16 : 1,
+                               ws_floats, &sp1);
+  const int bn2 = pick_block_n(d->N, p.m_tiles, kblocks_total, num_sms(), true, d->taps, &cost2, split_ok ? 16 : 1,
+                               ws_floats, &sp2);
   // an explicit block_n keeps the single-CTA kernel (unless the A/B override forces pairs on a pairable block_n)
   const bool pair_ok = p.m_tiles >= 2 && !(flags & LDM_GEMM_CONVT_LN_SILU) &&
                        (d->block_n <= 0 || (pair_override() == 1 && d->block_n >= 64 && d->block_n % 32 == 0));
@@ -192,6 +323,7 @@ extern "C" int ldm_gemm_bf16(const ldm_gemm_desc* d, ldm_stream_t stream) {
     pair = false;
   }
   int block_n = d->block_n > 0 ? d->block_n : (qkv_tma ? 160 : (pair ? bn2 : bn1));
+  int split_k = d->block_n > 0 || qkv_tma ? 1 : (pair ? sp2 : sp1);
   if ((flags & LDM_GEMM_GEGLU) && d->block_n <= 0 && block_n < 128) block_n = 128;  // staged GEGLU blocks span 128 columns
   LDM_REQUIRE(block_n % 32 == 0 && block_n >= 32 && block_n <= 256, LDM_ERR_BAD_ARG, "ldm_gemm_bf16: block_n=%d",
               block_n);
@@ -229,6 +361,13 @@ extern "C" int ldm_gemm_bf16(const ldm_gemm_desc* d, ldm_stream_t stream) {
   const bool staged = !(flags & (LDM_GEMM_OUT_F32 | LDM_GEMM_OUT_NCHW_F32 | LDM_GEMM_QKV_SPLIT | LDM_GEMM_CONVT_LN_SILU)) &&
                       n_out >= 64 && n_out % 8 == 0 && block_n >= ((flags & LDM_GEMM_GEGLU) ? 128 : 64) && staged_enabled();
   p.flags = flags | debug_flags() | (staged ? kStagedStore : 0) | (qkv_tma ? kQkvStaged : 0);
+  if (!staged || block_n < 64) split_k = 1;
+  p.split_k = split_k;
+  if (split_k > 1) {
+    const long m_alloc = pair ? 2 * ((p.m_tiles + 1) / 2) : p.m_tiles;
+    p.ws = reinterpret_cast<float*>(d->splitk_ws);
+    p.ws_slice_stride = (long long)m_alloc * p.n_tiles * block_n * kBlockM;
+  }
   p.bias = d->bias;
   p.rowbias = d->rowbias;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(d->residual);
@@ -332,12 +471,12 @@ extern "C" int ldm_gemm_bf16(const ldm_gemm_desc* d, ldm_stream_t stream) {
   const int smem_bytes = p.stages * p.stage_bytes + kEpiStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   int grid;
   if (pair) {
-    const int units = ((p.m_tiles + 1) / 2) * p.n_tiles;
+    const int units = ((p.m_tiles + 1) / 2) * p.n_tiles * split_k;
     int clusters = num_sms() / 2;
     if (clusters > units) clusters = units;
     grid = 2 * clusters;
   } else {
-    const int num_tiles = p.m_tiles * p.n_tiles;
+    const int num_tiles = p.m_tiles * p.n_tiles * split_k;
     grid = num_sms();
     if (grid > num_tiles) grid = num_tiles;
   }
@@ -349,11 +488,39 @@ extern "C" int ldm_gemm_bf16(const ldm_gemm_desc* d, ldm_stream_t stream) {
     e = launch_gemm_qkv(pair, grid, smem_bytes, st, tmA1, tmA2, tmB, tmO, tmR, tmE, p);
   else if (staged && (flags & LDM_GEMM_GEGLU))
     e = launch_gemm_geglu(pair, grid, smem_bytes, st, tmA1, tmA2, tmB, tmO, tmR, tmE, p);
+  else if (staged && split_k > 1)
+    e = launch_gemm_split(pair, grid, smem_bytes, st, tmA1, tmA2, tmB, tmO, tmR, tmE, p);
   else if (staged)
     e = launch_gemm_staged(pair, grid, smem_bytes, st, tmA1, tmA2, tmB, tmO, tmR, tmE, p);
   else
     e = launch_gemm_direct(pair, grid, smem_bytes, st, tmA1, tmA2, tmB, tmO, tmR, tmE, p);
   if (e != cudaSuccess) return set_error(LDM_ERR_CUDA, "gemm_tc_kernel launch: %s", cudaGetErrorString(e));
+  if (split_k > 1) {
+    FixupParams f{};
+    f.ws = p.ws;
+    f.slice_stride = p.ws_slice_stride;
+    f.split = split_k;
+    f.tiles_x = p.tiles_x; f.tiles_y = p.tiles_y; f.bw = p.bw; f.bh = p.bh; f.W = p.W; f.H = p.H;
+    f.m_tiles = p.m_tiles; f.n_tiles = p.n_tiles; f.block_n = block_n; f.N = d->N;
+    f.silu = (flags & LDM_GEMM_SILU) ? 1 : 0;
+    f.bias = d->bias;
+    f.rowbias = d->rowbias;
+    f.residual = res_mma ? nullptr : reinterpret_cast<const __nv_bfloat16*>(d->residual);  // (else: on the tensor core)
+    f.out = reinterpret_cast<__nv_bfloat16*>(d->out);
+    cudaError_t fe = launch_pdl(splitk_fixup_kernel, dim3(block_n / 16, p.n_tiles, p.m_tiles), dim3(256), (size_t)0, st, 1, f);
+    if (fe != cudaSuccess) return set_error(LDM_ERR_CUDA, "splitk_fixup_kernel launch: %s", cudaGetErrorString(fe));
+    count_launch();
+  }
+  g_last_cfg[0] = block_n;
+  g_last_cfg[1] = pair ? 1 : 0;
+  g_last_cfg[2] = split_k;
   count_launch();
   return check_launch("gemm_tc_kernel");
+}
+
+extern "C" int ldm_gemm_last_config(int32_t* block_n, int32_t* pair, int32_t* split_k) {
+  if (block_n) *block_n = g_last_cfg[0];
+  if (pair) *pair = g_last_cfg[1];
+  if (split_k) *split_k = g_last_cfg[2];
+  return LDM_OK;
 }

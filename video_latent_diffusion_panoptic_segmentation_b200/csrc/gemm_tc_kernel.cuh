@@ -48,6 +48,10 @@ struct GemmParams {
   unsigned long long magic_seq, magic_c, magic_d;  // ceil(2^40 / divisor): x / d == (x * magic) >> 40 for x * d < 2^40
   int n_store;      // OUT_NCHW_F32: leading output channels actually stored
   long long img_px; // pixels per image of the un-flattened problem (H*W)
+  // split-K (kEpiSplit): every tile is computed by split_k work items, each over a contiguous range of the K blocks
+  int split_k;
+  float* ws;                  // fp32 partial tiles [split_k][m_tiles_alloc][n_tiles][block_n][128 rows]
+  long long ws_slice_stride;  // floats per slice
 };
 
 __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* dst, const float* v) {
@@ -69,7 +73,13 @@ __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* dst, const float* v)
 //                the accumulator on the leader's barrier.
 // kEpi selects the epilogue at compile time (one instantiation per mode keeps each kernel's hot loop small: the
 // all-modes-in-one kernel was 170 KB of SASS and its epilogue warps stalled on instruction fetch):
-enum { kEpiStaged = 0, kEpiGeglu = 1, kEpiQkv = 2, kEpiDirect = 3, kEpiConvT = 4 };
+// kEpiSplit = split-K: when M is small and K long (the 6x20 level: 8 x 14 tiles for 148 SMs, 180 - 360 K blocks each;
+// at B = 1 a single row of tiles) the K range of a tile is cut into split_k work items. Each item leaves its fp32
+// partial tile in an L2-resident workspace; splitk_fixup_kernel (gemm_tc.cu) then adds the partials IN SLICE ORDER
+// (bit-reproducible) and applies the plain epilogue on all SMs. (A first version let the tile's last-arriving item do
+// that inside this kernel: one SM pulling split_k x 48 - 128 KB through ~10 rounds of L2 latency cost more than the
+// main loop it saved -- 29 us instead of 45 at M = 120, no gain at M = 960.)
+enum { kEpiStaged = 0, kEpiGeglu = 1, kEpiQkv = 2, kEpiDirect = 3, kEpiConvT = 4, kEpiSplit = 5 };
 
 template <bool kPair, int kEpi>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -131,6 +141,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   // work items: (m_unit, n_tile) with m_unit = one M tile, or a pair of consecutive M tiles
   const int m_units = kPair ? (p.m_tiles + 1) / 2 : p.m_tiles;
   const int num_tiles = m_units * p.n_tiles;
+  constexpr bool kSplit = kEpi == kEpiSplit;
+  const int split = kSplit ? p.split_k : 1;
+  const int num_items = num_tiles * split;   // item = tile * split + slice: the slices of a tile run on different SMs
+  const int kmain = p.taps * p.kblocks;      // K blocks of a tile without the residual blocks
   const int tiles_per_img = p.tiles_x * p.tiles_y;
   const uint32_t a_bytes = (uint32_t)(p.bw * p.bh) * (kBlockK * 2);
   const int b_rows = kPair ? p.block_n / 2 : p.block_n;   // weight rows this CTA loads per k-block
@@ -141,7 +155,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = worker; tile < num_tiles; tile += num_workers) {
+      for (int item = worker; item < num_items; item += num_workers) {
+        const int tile = kSplit ? item / split : item;
+        const int slice = kSplit ? item - tile * split : 0;
+        const int k_lo = kSplit ? (int)((long long)kmain * slice / split) : 0;
+        const int k_hi = kSplit ? (int)((long long)kmain * (slice + 1) / split) : kmain;
         const int n_tile = tile / m_units;
         const int m_unit = tile - n_tile * m_units;
         const int m_tile = kPair ? 2 * m_unit + (int)rank : m_unit;  // == m_tiles for the odd tail: all-OOB box, zeros
@@ -151,10 +169,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         const int tx = rem - ty * p.tiles_x;
         const int x0 = tx * p.bw, y0 = ty * p.bh;
         const int n0 = n_tile * p.block_n + (int)rank * b_rows;
-        for (int tap = 0; tap < p.taps; ++tap) {
+        int tap = k_lo / p.kblocks, kb = k_lo - tap * p.kblocks;
+        for (int ki = k_lo; ki < k_hi; ++ki) {
           const int dy = (p.taps == 9) ? tap / 3 - 1 : 0;
           const int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
-          for (int kb = 0; kb < p.kblocks; ++kb) {
+          {
             if (p.flags & kDbgNoWait) continue;
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * p.stage_bytes;
@@ -179,10 +198,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
               phase ^= 1;
             }
           }
+          if (++kb == p.kblocks) {
+            kb = 0;
+            ++tap;
+          }
         }
         // residual as extra K blocks: A = residual[rows of this tile, 64 output columns], B = the matching band of the
-        // identity matrix (row n of the tile x column n), so that D += R on the tensor core
-        for (int j = 0; j < p.res_kblocks; ++j) {
+        // identity matrix (row n of the tile x column n), so that D += R on the tensor core (split-K: the last slice)
+        const int nres = (slice == split - 1) ? p.res_kblocks : 0;
+        for (int j = 0; j < nres; ++j) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * p.stage_bytes;
           uint8_t* sb = sa + kABytes;
@@ -213,8 +237,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      const int ksteps = p.taps * p.kblocks + p.res_kblocks;
-      for (int tile = worker; tile < num_tiles; tile += num_workers) {
+      for (int item = worker; item < num_items; item += num_workers) {
+        int ksteps = kmain + p.res_kblocks;
+        if (kSplit) {
+          const int slice = item % split;
+          ksteps = (int)((long long)kmain * (slice + 1) / split) - (int)((long long)kmain * slice / split) +
+                   (slice == split - 1 ? p.res_kblocks : 0);
+        }
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)as * 256u;
@@ -270,7 +299,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     int sb = 0;                                  // staging buffer of the next output block (alternates)
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = worker; tile < num_tiles; tile += num_workers) {
+    for (int item = worker; item < num_items; item += num_workers) {
+      const int tile = kSplit ? item / split : item;
+      const int slice = kSplit ? item - tile * split : 0;
       const int n_tile = tile / m_units;
       const int m_unit = tile - n_tile * m_units;
       const int m_tile = kPair ? 2 * m_unit + (int)rank : m_unit;
@@ -295,7 +326,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       // staged path: both halves work on the same 64-column output block, half h on its 32-column chunk h, so chunk
       // ci of a thread covers columns min(ci*64, block_n-64) + h*32; direct path: a half owns every other chunk.
       uint4 rs[4][4];
-      const bool use_res = plain && p.residual != nullptr && valid && p.res_kblocks == 0;
+      const bool use_res = !kSplit && plain && p.residual != nullptr && valid && p.res_kblocks == 0;
       if (use_res) {
         const __nv_bfloat16* rrow = p.residual + grow * p.N + n0;
 #pragma unroll
@@ -313,7 +344,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)as * 256u;
 
-      if constexpr (kEpi == kEpiConvT) {
+      // split-K: this item's fp32 partial tile goes to the workspace, column-major inside the tile (the 32 lanes of a
+      // warp = 32 consecutive rows write 128 contiguous bytes per column); the fix-up kernel does the rest
+      if constexpr (kSplit) {
+        const long long tile_off = ((long long)m_tile * p.n_tiles + n_tile) * (long long)(p.block_n * kBlockM);
+        float* wdst = p.ws + (long long)slice * p.ws_slice_stride + tile_off + r;
+        for (int c = half * 32; c < p.block_n; c += 64) {
+          uint32_t v[32];
+          tmem_ld32(t_addr + c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) wdst[(c + j) * kBlockM] = __uint_as_float(v[j]);
+        }
+      }
+
+      if constexpr (kSplit) {
+      } else if constexpr (kEpi == kEpiConvT) {
         if (half == 0) {
         // One N tile == one (dy,dx) sub-pixel of ConvTranspose2d(k=2,s=2); LayerNorm2d over its block_n channels.
         const int cout = p.block_n;

@@ -42,6 +42,20 @@ def _identity(device):
     return _EYE[key]
 
 
+_SPLITK_WS = {}
+SPLITK_WS_BYTES = 64 << 20   # fp32 partial tiles of the split-K launches
+
+
+def _splitk_ws(device):
+    """Split-K workspace shared by every GEMM on `device` (ldm_gemm_desc.splitk_ws). The launches that use it are
+    ordered by the stream they run on: one stream at a time per device (the eager warm-up and the graph capture of a
+    plan are sequential). Allocated at the first eager call, i.e. before any graph capture."""
+    key = torch.device(device).index
+    if key not in _SPLITK_WS:
+        _SPLITK_WS[key] = torch.zeros(SPLITK_WS_BYTES, dtype=torch.uint8, device=device)
+    return _SPLITK_WS[key]
+
+
 def gemm(a1, w, out=None, *, a2=None, taps=1, bias=None, rowbias=None, residual=None, flags=0, block_n=0,
          qkv=None, ln=None, n_store=0):
     """out = epilogue(conv/gemm(a1 ++ a2, w)). a1/a2: [B,H,W,C] or [rows,C] bf16; w: [N, taps*(c1+c2)] bf16.
@@ -61,6 +75,8 @@ def gemm(a1, w, out=None, *, a2=None, taps=1, bias=None, rowbias=None, residual=
     d.bias, d.rowbias, d.residual = _p(bias), _p(rowbias), _p(residual)
     if residual is not None:
         d.identity = _p(_identity(a1.device))
+    ws = _splitk_ws(a1.device)
+    d.splitk_ws, d.splitk_ws_bytes = _p(ws), ws.numel()
     d.B, d.H, d.W, d.c1 = B, H, W, c1
     d.c2 = 0 if a2 is None else a2.shape[-1]
     d.N = w.shape[0]
@@ -85,6 +101,13 @@ def gemm(a1, w, out=None, *, a2=None, taps=1, bias=None, rowbias=None, residual=
         d.ln_gamma, d.ln_beta, d.ln_eps = _p(g), _p(b_), eps
     L.check(L.lib().ldm_gemm_bf16(C.byref(d), _stream()), "ldm_gemm_bf16")
     return out
+
+
+def gemm_last_config():
+    """(block_n, pair, split_k) of this thread's last gemm launch."""
+    bn, pr, sk = C.c_int32(), C.c_int32(), C.c_int32()
+    L.lib().ldm_gemm_last_config(C.byref(bn), C.byref(pr), C.byref(sk))
+    return bn.value, bool(pr.value), sk.value
 
 
 def alloc_qkv(B, heads, seq, d, device):
