@@ -110,3 +110,18 @@ def test_header_compiles_as_c_and_struct_offsets_match_ctypes(tmp_path):
         assert int(out[cname]) == C.sizeof(ctype), cname
         for f in ctype._fields_:
             assert int(out[f"{cname}.{f[0]}"]) == getattr(ctype, f[0]).offset, (cname, f[0])
+
+
+def test_product_library_reads_no_environment():
+    """The header promises no global mutable state: the A/B switches (LDM_GEMM_*, LDM_ATTN_*, LDM_GN_*, LDM_PDL) exist only
+    in diagnostic builds (-DLDM_DIAG, LDM_BUILD_DIAG=1); the product .so does not even import getenv."""
+    import subprocess
+    from video_latent_diffusion_panoptic_segmentation_b200 import _lib as L
+    from video_latent_diffusion_panoptic_segmentation_b200 import build as B
+    if B.DIAG:
+        import pytest
+        pytest.skip("diagnostic build requested through LDM_BUILD_DIAG")
+    out = subprocess.run(["nm", "-D", "--undefined-only", L.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    assert "getenv" not in out, "libldmseg_b200.so imports getenv: a diagnostic switch leaked into the product build"
+    strings = subprocess.run(["strings", L.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    assert "LDM_GEMM_SPLITK" not in strings and "LDM_ATTN_POLY" not in strings

@@ -1,4 +1,5 @@
 #!/bin/bash
+# (the LDM_* switches exist only in a diagnostic build: LDM_BUILD_DIAG=1 python -m video_latent_diffusion_panoptic_segmentation_b200.build, then rebuild the product library before committing numbers)
 # 1 GPU: kernel checks of the norm kernels, then their device times at B = 8 and B = 1 with the cluster path off / on
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k 'groupnorm or layernorm' 2>&1 | tail -12

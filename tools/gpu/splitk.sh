@@ -1,4 +1,5 @@
 #!/bin/bash
+# (the LDM_* switches exist only in a diagnostic build: LDM_BUILD_DIAG=1 python -m video_latent_diffusion_panoptic_segmentation_b200.build, then rebuild the product library before committing numbers)
 # 1 GPU: split-K checks, then the tile-count-bound GEMM shapes with and without split-K at B = 8 and B = 1
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k 'gemm' 2>&1 | tail -15

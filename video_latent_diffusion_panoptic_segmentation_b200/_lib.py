@@ -100,7 +100,6 @@ SIGNATURES = {
 }
 
 _lib = None
-_device_ok = False
 
 
 class LdmError(RuntimeError):
@@ -129,13 +128,10 @@ def load():
 
 def lib():
     """Library handle for compute calls: additionally requires a B200 (sm_100) as the current CUDA device."""
-    global _device_ok
     l = load()
-    if not _device_ok:
-        rc = l.ldm_check_device()
-        if rc != 0:
-            raise LdmError(f"ldm_check_device failed ({rc}): {l.ldm_last_error().decode()}")
-        _device_ok = True
+    rc = l.ldm_check_device()   # the CURRENT device, every time (a process may drive several; the check is two cached queries)
+    if rc != 0:
+        raise LdmError(f"ldm_check_device failed ({rc}): {l.ldm_last_error().decode()}")
     return l
 
 

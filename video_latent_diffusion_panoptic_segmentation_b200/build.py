@@ -18,6 +18,12 @@ FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",
 ]
+# LDM_BUILD_DIAG=1: compile the diagnostic environment switches in (csrc/host_util.h: A/B timing by tools/gpu/*.sh). The
+# product build reads no environment variable. The two flavours keep separate object directories.
+DIAG = os.environ.get("LDM_BUILD_DIAG", "0") not in ("", "0")
+if DIAG:
+    FLAGS.append("-DLDM_DIAG")
+    OBJ = os.path.join(HERE, "build_diag")
 
 
 def sources():
@@ -56,11 +62,17 @@ def build(force=False, verbose=False):
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         results = list(ex.map(lambda s: _compile(s, force, verbose), srcs))
     objs = [o for o, _ in results]
-    if force or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
+    stamp = os.path.join(OBJ, ".linked")
+    if force or not os.path.exists(LIB) or not os.path.exists(stamp) or \
+            any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs) or os.path.getmtime(stamp) < os.path.getmtime(LIB):
         cmd = [NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+        for other in (os.path.join(HERE, "build", ".linked"), os.path.join(HERE, "build_diag", ".linked")):
+            if os.path.exists(other):
+                os.remove(other)   # the library now holds this flavour's objects
+        open(stamp, "w").close()
     return LIB
 
 

@@ -409,11 +409,9 @@ int launch(const ldm_attn_desc* d, cudaStream_t s) {
   p.scale_log2 = d->scale * 1.4426950408889634f;
   p.out = reinterpret_cast<__nv_bfloat16*>(d->out);
   auto kern = flash_attn40_kernel<kPoly>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  {  // per launch (the attribute is per device; see gemm_tc_inst.cuh)
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (e != cudaSuccess) return set_error(LDM_ERR_CUDA, "cudaFuncSetAttribute(attn40): %s", cudaGetErrorString(e));
-    attr_set = true;
   }
   dim3 grid((d->seq + 255) / 256, BH);
   cudaError_t le = launch_pdl(kern, grid, dim3(kThreads), (size_t)kSmem, s, 1, tmQ, tmK, tmV, p);
@@ -425,12 +423,8 @@ int launch(const ldm_attn_desc* d, cudaStream_t s) {
 }  // namespace
 
 int ldm_launch_attn40(const ldm_attn_desc* d, cudaStream_t s) {
-  static int poly = -1;  // LDM_ATTN_POLY=0..4: A/B timing of the FMA-pipe exp2 share (n of 8 pairs)
-  if (poly < 0) {
-    const char* e = getenv("LDM_ATTN_POLY");
-    poly = e ? atoi(e) : 2;
-  }
-  switch (poly) {
+  // LDM_ATTN_POLY=0..4 (diagnostic builds): A/B timing of the FMA-pipe exp2 share (n of 8 pairs)
+  switch (ldm_host::diag_env("LDM_ATTN_POLY", 2)) {
     case 0: return launch<0>(d, s);
     case 1: return launch<1>(d, s);
     case 3: return launch<3>(d, s);

@@ -407,11 +407,9 @@ int launch_attn(const ldm_attn_desc* d, cudaStream_t s) {
   p.scale_log2 = d->scale * 1.4426950408889634f;
   p.out = reinterpret_cast<__nv_bfloat16*>(d->out);
   auto kern = flash_attn_kernel<D, NQ, BKV, STAGES, kPoly>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  {  // per launch (the attribute is per device; see gemm_tc_inst.cuh)
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
     if (e != cudaSuccess) return set_error(LDM_ERR_CUDA, "cudaFuncSetAttribute(attn): %s", cudaGetErrorString(e));
-    attr_set = true;
   }
   dim3 grid((d->seq + 128 * NQ - 1) / (128 * NQ), BH);
   cudaError_t le = launch_pdl(kern, grid, dim3(Cfg::kThreads), (size_t)Cfg::kSmem, s, 1, tmQ, tmK, tmV, p);
@@ -438,17 +436,10 @@ extern "C" int ldm_flash_attn_fwd(const ldm_attn_desc* d, ldm_stream_t stream) {
   cudaStream_t s = as_stream(stream);
   switch (d->head_dim) {
     case 40: {
-      static int split = -1;  // LDM_ATTN40=0: the generic kernel below instead of attn40_tc.cu (A/B timing)
-      if (split < 0) {
-        const char* e = getenv("LDM_ATTN40");
-        split = e ? atoi(e) : 1;
-      }
-      if (split) return ldm_launch_attn40(d, s);
-      static int poly = -1;  // LDM_ATTN_POLY=0..4: A/B timing of the FMA-pipe exp2 share (n of 8)
-      if (poly < 0) {
-        const char* e = getenv("LDM_ATTN_POLY");
-        poly = e ? atoi(e) : 2;
-      }
+      // diagnostic builds: LDM_ATTN40=0 runs the generic kernel below instead of attn40_tc.cu, LDM_ATTN_POLY=0..4 sets
+      // the FMA-pipe share of the exponentials (n of 8) -- A/B timing
+      if (diag_env("LDM_ATTN40", 1)) return ldm_launch_attn40(d, s);
+      const int poly = diag_env("LDM_ATTN_POLY", 2);
       if (poly == 0) return launch_attn<40, 2, 128, 4, 0>(d, s);
       if (poly == 1) return launch_attn<40, 2, 128, 4, 1>(d, s);
       if (poly == 3) return launch_attn<40, 2, 128, 4, 3>(d, s);
@@ -456,12 +447,8 @@ extern "C" int ldm_flash_attn_fwd(const ldm_attn_desc* d, ldm_stream_t stream) {
       return launch_attn<40, 2, 128, 4, 2>(d, s);
     }
     case 80: {
-      static int v = -1;  // LDM_ATTN_D80=0: one query group, 128-key blocks; 1 (default): two groups, 64-key blocks
-      if (v < 0) {
-        const char* e = getenv("LDM_ATTN_D80");
-        v = e ? atoi(e) : 1;
-      }
-      if (v == 0) return launch_attn<80, 1, 128, 3, 0>(d, s);
+      // LDM_ATTN_D80=0 (diagnostic builds): one query group, 128-key blocks; default: two groups, 64-key blocks
+      if (diag_env("LDM_ATTN_D80", 1) == 0) return launch_attn<80, 1, 128, 3, 0>(d, s);
       return launch_attn<80, 2, 64, 4, 0>(d, s);
     }
     case 160:

@@ -338,11 +338,7 @@ extern "C" int ldm_conv_out(const void* x, const float* w, const float* bias, fl
   LDM_REQUIRE(cout > 0 && cout <= kMaxCoutSmall && cin % 8 == 0 && 9 * cin * cout * 4 <= 200 * 1024, LDM_ERR_BAD_SHAPE,
               "ldm_conv_out: cin=%d cout=%d unsupported", cin, cout);
   const size_t shb = sizeof(float) * 9 * cin * cout;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(conv_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_set = true;
-  }
+  cudaFuncSetAttribute(conv_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);  // (per device)
   const int grid = num_sms() * 2;
   conv_out_kernel<<<grid, 256, shb, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), w, bias, out, B, h,
                                                          wd, cin, cout);

@@ -124,48 +124,24 @@ int pick_block_n(int N, long m_tiles, long kblocks, int sms, bool pair, int taps
 }
 
 int debug_flags() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("LDM_GEMM_DEBUG");
-    v = 0;
-    if (e && strstr(e, "notma")) v |= kDbgNoTma;
-    if (e && strstr(e, "nomma")) v |= kDbgNoMma;
-    if (e && strstr(e, "nowait")) v |= kDbgNoWait | kDbgNoTma;
-    if (e && strstr(e, "nofence")) v |= kDbgNoFence;
-    if (e && strstr(e, "keepcommit")) v |= kDbgKeepCommit;
-  }
+  using ldm_host::diag_env_has;
+  int v = 0;
+  if (diag_env_has("LDM_GEMM_DEBUG", "notma")) v |= kDbgNoTma;
+  if (diag_env_has("LDM_GEMM_DEBUG", "nomma")) v |= kDbgNoMma;
+  if (diag_env_has("LDM_GEMM_DEBUG", "nowait")) v |= kDbgNoWait | kDbgNoTma;
+  if (diag_env_has("LDM_GEMM_DEBUG", "nofence")) v |= kDbgNoFence;
+  if (diag_env_has("LDM_GEMM_DEBUG", "keepcommit")) v |= kDbgKeepCommit;
   return v;
 }
 
 // Residual on the tensor core for main loops of up to this many K blocks (LDM_GEMM_RESMMA overrides, 0 = never)
-int resmma_max_kblocks() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("LDM_GEMM_RESMMA");
-    v = e ? atoi(e) : 1 << 30;
-  }
-  return v;
-}
+int resmma_max_kblocks() { return ldm_host::diag_env("LDM_GEMM_RESMMA", 1 << 30); }
 
 // LDM_GEMM_STAGED=0 keeps the direct (row-per-thread) global stores (A/B timing)
-bool staged_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("LDM_GEMM_STAGED");
-    v = e ? atoi(e) : 1;
-  }
-  return v != 0;
-}
+bool staged_enabled() { return ldm_host::diag_env("LDM_GEMM_STAGED", 1) != 0; }
 
 // LDM_GEMM_SPLITK=0 keeps every tile on one work item (A/B timing)
-bool splitk_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("LDM_GEMM_SPLITK");
-    v = e ? atoi(e) : 1;
-  }
-  return v != 0;
-}
+bool splitk_enabled() { return ldm_host::diag_env("LDM_GEMM_SPLITK", 1) != 0; }
 
 thread_local int g_last_cfg[3] = {0, 0, 1};  // block_n, pair, split_k of this thread's last ldm_gemm_bf16 launch
 
@@ -248,14 +224,7 @@ __global__ void __launch_bounds__(256) splitk_fixup_kernel(const FixupParams p) 
 }
 
 // LDM_GEMM_PAIR=0 / 1 forces the single-CTA / CTA-pair kernel (A/B timing); default: the cost model decides.
-int pair_override() {
-  static int v = -2;
-  if (v == -2) {
-    const char* e = getenv("LDM_GEMM_PAIR");
-    v = e ? atoi(e) : -1;
-  }
-  return v;
-}
+int pair_override() { return ldm_host::diag_env("LDM_GEMM_PAIR", -1); }
 
 }  // namespace
 
@@ -312,7 +281,7 @@ extern "C" int ldm_gemm_bf16(const ldm_gemm_desc* d, ldm_stream_t stream) {
   // QKV head split: with block_n = 160 (the only multiple of the 32-column TMEM chunk that 40-, 80- and 160-wide heads
   // all divide) every tile holds whole heads of one part, and the q / k tiles can leave through TMA stores
   // (LDM_GEMM_QKV_TMA=0: the row-per-thread stores, A/B timing)
-  static const bool qkv_tma_enabled = [] { const char* e = getenv("LDM_GEMM_QKV_TMA"); return e ? atoi(e) != 0 : true; }();
+  const bool qkv_tma_enabled = diag_env("LDM_GEMM_QKV_TMA", 1) != 0;
   bool qkv_tma = false;
   if ((flags & LDM_GEMM_QKV_SPLIT) && qkv_tma_enabled && d->block_n <= 0 && !d->bias && !d->rowbias && d->head_dim > 0 &&
       160 % d->head_dim == 0 && (d->heads * d->head_dim) % 160 == 0 && p.H == 1 && p.bw == kBlockM && p.bh == 1 &&

@@ -8,14 +8,11 @@ template <int kEpi>
 cudaError_t launch_epi(bool pair, int grid, int smem_bytes, cudaStream_t stream, const CUtensorMap& tmA1,
                        const CUtensorMap& tmA2, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmR,
                        const CUtensorMap& tmE, const GemmParams& p) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<false, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(gemm_tc_kernel<true, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  // (per launch, not cached: the attribute belongs to the current device's copy of the function and a process may
+  // drive several devices; the call is a few hundred nanoseconds and is not a stream operation)
+  cudaError_t e = pair ? cudaFuncSetAttribute(gemm_tc_kernel<true, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget)
+                       : cudaFuncSetAttribute(gemm_tc_kernel<false, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+  if (e != cudaSuccess) return e;
   if (pair)
     return ldm_host::launch_pdl(gemm_tc_kernel<true, kEpi>, dim3(grid), dim3(kThreads), (size_t)smem_bytes, stream, 2, tmA1,
                                 tmA2, tmB, tmO, tmR, tmE, p);

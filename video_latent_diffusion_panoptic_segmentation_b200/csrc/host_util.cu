@@ -28,22 +28,28 @@ int check_launch(const char* what) {
   return LDM_OK;
 }
 
-bool pdl_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("LDM_PDL");
-    v = e ? atoi(e) : 0;
-  }
-  return v != 0;
+#ifdef LDM_DIAG
+int diag_env(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
 }
+bool diag_env_has(const char* name, const char* word) {
+  const char* e = getenv(name);
+  return e && strstr(e, word);
+}
+#endif
 
+// SM count of the CURRENT device (a process may drive several): immutable per-device cache
 int num_sms() {
-  static int sms = 0;
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::atomic<int>& slot = cache[dev & 63];
+  int sms = slot.load(std::memory_order_relaxed);
   if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = 148;
+    slot.store(sms, std::memory_order_relaxed);
   }
   return sms;
 }

@@ -22,9 +22,21 @@ int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims
 
 inline cudaStream_t as_stream(ldm_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
-// LDM_PDL=1 turns programmatic dependent launch on. Measured on B200 inside the CUDA graph of the UNet plan: 8.58 fps
-// with it, 8.63 without (launch gaps are already hidden by the graph), so the default is off.
-bool pdl_enabled();
+// Diagnostic switches (A/B timing by the scripts under tools/): compiled in only with -DLDM_DIAG
+// (`LDM_BUILD_DIAG=1 python -m video_latent_diffusion_panoptic_segmentation_b200.build --force`). The product library reads
+// NO environment variable; its only process-wide state are immutable per-device caches (SM count).
+#ifdef LDM_DIAG
+int diag_env(const char* name, int dflt);              // atoi(getenv(name)) or dflt
+bool diag_env_has(const char* name, const char* word);  // strstr(getenv(name), word)
+#else
+inline int diag_env(const char*, int dflt) { return dflt; }
+inline bool diag_env_has(const char*, const char*) { return false; }
+#endif
+
+// LDM_PDL=1 (diagnostic build) turns programmatic dependent launch on. Measured on B200 inside the CUDA graph of the UNet
+// plan: 8.58 fps with it, 8.63 without at 8 frames per batch, +0.3 % at one frame (launch gaps are already hidden by
+// the graph; the fat GEMM / attention CTAs cannot co-reside with their predecessor's anyway), so it is off.
+inline bool pdl_enabled() { return diag_env("LDM_PDL", 0) != 0; }
 
 // Launch with programmatic stream serialisation (the kernel must call pdl_wait() before its first global access) and,
 // optionally, a thread-block cluster of `cluster` CTAs.

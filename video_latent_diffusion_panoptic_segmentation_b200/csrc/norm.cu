@@ -654,7 +654,7 @@ extern "C" int ldm_groupnorm_silu(const ldm_groupnorm_desc* d, ldm_stream_t stre
   // 16-byte vectors): as many CTAs as fit one wave, the smallest cluster among equals (no exchange at all when a CTA
   // can own whole groups of an image), at most max_vec vectors per thread (beyond that the two-sweep kernel wins).
   {
-    static const int max_vec = [] { const char* e = getenv("LDM_GN_CLUSTER_MAXVEC"); return e ? atoi(e) : 18; }();
+    const int max_vec = diag_env("LDM_GN_CLUSTER_MAXVEC", 18);  // (0 in a diagnostic build: never this path)
     const int cpg = C / d->groups;
     int best_clu = 0, best_sets = 0, best_ctas = 0;
     for (int clu = 1; clu <= kGnCluMax; clu *= 2) {
@@ -700,24 +700,12 @@ extern "C" int ldm_groupnorm_silu(const ldm_groupnorm_desc* d, ldm_stream_t stre
   }
   float* partial = reinterpret_cast<float*>(d->stats);
   const size_t sh1 = sizeof(float) * 2 * (size_t)ppb * C;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    attr_set = true;
-  }
+  cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);  // (per device)
   LDM_REQUIRE(sh1 <= 96 * 1024, LDM_ERR_BAD_SHAPE, "ldm_groupnorm_silu: C=%d too large", C);
   const size_t sh2 = sizeof(float) * 2 * d->groups + sizeof(double) * 2 * 8 * d->groups;
-  static int fused = -1;  // LDM_GN_FUSED=0: the two-launch path (A/B timing)
-  if (fused < 0) {
-    const char* e = getenv("LDM_GN_FUSED");
-    fused = e ? atoi(e) : 1;
-  }
+  const int fused = diag_env("LDM_GN_FUSED", 1);  // 0 (diagnostic builds): the two-launch path (A/B timing)
   if (fused && (long long)chunks * d->B <= 2LL * num_sms() && vpp * ppb <= 512) {
-    static bool attr2 = false;
-    if (!attr2) {
-      cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-      attr2 = true;
-    }
+    cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     unsigned int* counters = reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(d->stats) +
                                                              gn_partial_bytes(d->B, d->groups));
     cudaLaunchConfig_t cfg = {};
