@@ -384,8 +384,13 @@ def run_config(name, args, env):
                                "fn": int(v["fn"].sum()), "fp": int(v["fp"].sum())} for k, v in dv.items()},
             "ids_digest": {"frames": len(digs), "per_frame_first16": digs[:16],
                            "all": hashlib.sha256("".join(digs).encode()).hexdigest()[:16],
-                           "note": "sha256 of the merged int32 id map of every global frame, in frame order; equal "
-                                   "values at different N mean bit-identical ids"},
+                           "first8": hashlib.sha256("".join(digs[:8]).encode()).hexdigest()[:16],
+                           "note": "sha256 of the merged int32 id map of every global frame, in frame order (noise and "
+                                   "inputs belong to the global frame). `first8` covers global frames 0-7: in the weak-"
+                                   "scaling configs it is the same at every N (same frames, same batch of 8 per GPU = "
+                                   "the same kernels: bit-identical ids). In the strong-scaling configs the batch per GPU "
+                                   "changes with N, and with it the tiling (block_n, split-K, GroupNorm slices) and the "
+                                   "fp32 summation order: ids then agree up to bf16 rounding flips, see pq / dvpq"},
             "whole_job_frac_of_tensor_peak": fps / world * (T * work["unet_step"] + work["ae"]) / (tf_sus * 1e12)}
 
     if rank == 0:
