@@ -602,6 +602,8 @@ def run_ours(args):
     L.lib()  # fails loudly if the CUDA library is missing or the device is not sm_100
     p = copy.deepcopy(main_ldm.BASE)
     env = {"world": world, "rank": rank, "local": local, "dev": dev, "models": main_ldm.build_models(p, dev, seed=0)}
+    if args.ln_fold:
+        env["models"][1].ln_fold = True   # read when the weights are packed (first forward)
     for name in args.config.split(","):
         run_config(name, args, env)
     if world > 1:
@@ -636,6 +638,7 @@ def main():
     ap.add_argument("--clip-frames", type=int, default=None, help="override the clip length (strong-scaling configs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true")
+    ap.add_argument("--ln-fold", action="store_true", help="A/B: LayerNorm folded into the GEMMs around it instead of its own pass (slower, see DESIGN.md)")
     ap.add_argument("--profile-out", default=None, help="write the per-launch CUDA-event profile of one UNet forward")
     args = ap.parse_args()
     for name in args.config.split(","):

@@ -101,6 +101,20 @@ typedef struct ldm_gemm_desc {
                            second small launch adds them in a fixed order (bit-reproducible run to run) and applies
                            the epilogue. NULL: never split.                                                    */
   int64_t splitk_ws_bytes;
+  /* LayerNorm folded into the GEMMs around it (diffusers BasicTransformerBlock.norm1 / norm2 / norm3 in front of
+     to_q|k|v and ff.net.0) -- no normalisation pass and no normalised copy of the activations:
+       LN(x) W^T + b = rstd_m (x (gamma o W)^T - mean_m g) + (b + W beta),   g[n] = sum_c (gamma o W)[n, c].
+     The GEMM that WRITES x (plain bf16 epilogue) also writes, per 32-column chunk and row, the sum and the sum of
+     squares of its bf16 outputs into row_stats_out (f32 [ceil(N / 32), rows, 2]: part-major, so that a warp's 32 rows
+     are 256 contiguous bytes on both sides). The GEMM that READS x (QKV_SPLIT or GEGLU, pointwise) runs on the raw x
+     with w = gamma o W, bias = b + W beta, ln_colsum = g, and applies the row's mean / rstd in its epilogue from
+     ln_stats (the producer's row_stats_out; ln_parts = ceil(c1 / 32) partials per row, added in index order:
+     bit-reproducible).                                                                                         */
+  void* row_stats_out;
+  const void* ln_stats;
+  const float* ln_colsum;
+  float ln_fold_eps;
+  int32_t ln_parts;
 } ldm_gemm_desc;
 
 int ldm_gemm_bf16(const ldm_gemm_desc* d, ldm_stream_t stream);

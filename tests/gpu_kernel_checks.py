@@ -375,6 +375,60 @@ def check_gemm_geglu():
     return _stats(out, ref, "gemm GEGLU", 3e-2, 2e-2)
 
 
+def check_ln_fold(kind="qkv", B=2, heads=8, d=40, seq=300, mean_shift=0.5):
+    """LayerNorm folded into the GEMMs around it (ldm_gemm_desc.ln_stats): the producer GEMM (bias + residual) writes
+    the per-row moments of its bf16 output; the consumer (QKV split or GEGLU) runs on the raw rows with gamma-scaled
+    weights and normalises in its epilogue. Reference: fp32 LayerNorm of the producer's bf16 output, then the Linear."""
+    C = heads * d
+    M = B * seq
+    a = _randn((M, C), 90, 1.0, bf16)
+    wprod = _randn((C, C), 91, 0.05, bf16)
+    bprod = _randn((C,), 92) + mean_shift          # a row mean that is not small against the spread
+    res = _randn((M, C), 93, 1.0, bf16)
+    x = _empty((M, C), dtype=bf16, device=DEV)
+    stats = _empty(((C + 31) // 32, M, 2), dtype=torch.float32, device=DEV)   # part-major
+    stats.fill_(float("nan"))
+    ops.gemm(a, wprod, x, bias=bprod, residual=res, row_stats=stats)
+    xs = x.float().view(M, -1, 32).transpose(0, 1)
+    assert not torch.isnan(stats).any(), "row_stats has unwritten entries"
+    _stats(stats[:, :, 0], xs.sum(-1), "row_stats sum", 2e-3, 1e-4)
+    _stats(stats[:, :, 1], xs.pow(2).sum(-1), "row_stats sum of squares", 2e-3, 1e-4)
+    gamma, beta = _randn((C,), 94) * 0.3 + 1.0, _randn((C,), 95) * 0.2
+    xn = F.layer_norm(x.float(), (C,), gamma, beta, 1e-5)
+    if kind == "qkv":
+        w = _randn((3 * C, C), 96, 0.05)
+        w2, b2, colsum = ops.fold_layernorm(w, None, gamma, beta)
+        q, k, vt, dpad, seq_pad = _alloc_qkv(B, heads, seq, d)
+        ops.gemm(x, w2, None, bias=b2, flags=L.LDM_GEMM_QKV_SPLIT, ln_fold=(stats, colsum, 1e-5),
+                 qkv=dict(q=q, k=k, vt=vt, heads=heads, head_dim=d, dpad=dpad, seq=seq, seq_pad=seq_pad))
+        ref = (xn @ w.t()).view(B, seq, 3, heads, d)
+        qr = ref[:, :, 0].permute(0, 2, 1, 3).reshape(B * heads, seq, d)
+        kr = ref[:, :, 1].permute(0, 2, 1, 3).reshape(B * heads, seq, d)
+        vr = ref[:, :, 2].permute(0, 2, 3, 1).reshape(B * heads, d, seq)
+        _stats(q[:, :, :d], qr, "ln-fold qkv q", 4e-2, 2e-2)
+        _stats(k[:, :, :d], kr, "ln-fold qkv k", 4e-2, 2e-2)
+        assert float(q[:, :, d:].abs().max()) == 0.0, "q padding overwritten"
+        return _stats(vt[:, :d, :seq], vr, f"ln-fold qkv vt d={d} seq={seq}", 4e-2, 2e-2)
+    inner = 4 * C
+    w, b = _randn((8 * C, C), 97, 0.05), _randn((8 * C,), 98)
+    idx = torch.arange(inner).view(-1, 16)
+    perm = torch.cat([idx, idx + inner], dim=1).reshape(-1).to(DEV)
+    w2, b2, colsum = ops.fold_layernorm(w[perm].contiguous(), b[perm].contiguous(), gamma, beta)
+    out = _empty((M, inner), dtype=bf16, device=DEV)
+    ops.gemm(x, w2, out, bias=b2, flags=L.LDM_GEMM_GEGLU, ln_fold=(stats, colsum, 1e-5))
+    val, gate = (xn @ w.t() + b).chunk(2, dim=-1)
+    ref = val * F.gelu(gate)
+    # the un-folded path on the same inputs (LayerNorm kernel -> bf16 -> GEMM): the fold must not be less accurate
+    xl, out2 = _empty((M, C), dtype=bf16, device=DEV), _empty((M, inner), dtype=bf16, device=DEV)
+    ops.layernorm(x, gamma, beta, xl, 1e-5)
+    ops.gemm(xl, w[perm].contiguous().to(bf16), out2, bias=b[perm].contiguous(), flags=L.LDM_GEMM_GEGLU)
+    rel = lambda o: ((o.float() - ref).pow(2).sum().sqrt() / ref.pow(2).sum().sqrt()).item()
+    assert rel(out) <= 1.25 * rel(out2) + 5e-4, f"ln-fold GEGLU rel L2 {rel(out):.2e} vs un-folded {rel(out2):.2e}"
+    r = _stats(out, ref, f"ln-fold GEGLU C={C} M={M}", 8e-2, 3e-2)
+    r["rel_l2_unfolded"] = rel(out2)
+    return r
+
+
 def _alloc_qkv(B, heads, seq, d):
     q = ops.alloc_qkv(B, heads, seq, d, DEV)
     return q["q"], q["k"], q["vt"], q["dpad"], q["seq_pad"]
@@ -664,6 +718,14 @@ CHECKS = {
     "gemm_qkv_80_vec": lambda: check_gemm_qkv(3, 8, 80, 472),
     "gemm_qkv_40_vec_level0": lambda: check_gemm_qkv(1, 8, 40, 7488),
     "gemm_convt": check_gemm_convt,
+    # LayerNorm folded into producer / consumer epilogues: QKV direct stores, QKV through TMA stores (whole 128-token
+    # tiles of one image), 80- and 160-wide heads, GEGLU staged; a large row mean (cancellation in the mean term)
+    "ln_fold_qkv_40": check_ln_fold,
+    "ln_fold_qkv_40_level0": lambda: check_ln_fold("qkv", 1, 8, 40, 7488),
+    "ln_fold_qkv_80": lambda: check_ln_fold("qkv", 2, 8, 80, 472),
+    "ln_fold_qkv_160_big_mean": lambda: check_ln_fold("qkv", 2, 8, 160, 120, mean_shift=4.0),
+    "ln_fold_geglu_320": lambda: check_ln_fold("geglu", 2, 8, 40, 300),
+    "ln_fold_geglu_1280": lambda: check_ln_fold("geglu", 3, 8, 160, 120),
     "attn_40_tail": check_attention,
     "attn_40_long": lambda: check_attention(1, 2, 40, 1872),
     "attn_40_fold_tail": lambda: check_attention(1, 2, 40, 300, log2_units=True),

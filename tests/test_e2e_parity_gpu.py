@@ -75,7 +75,11 @@ def world():
     return dict(o_unet=o_unet, unet=unet, fitted=fitted, trainer=trainer, hw=(h, w))
 
 
-@pytest.mark.parametrize("T,B", [(10, 8), (50, 8)])
+# 16 frames: with 8 (about 470 segments in 19 classes) ONE borderline segment that the bf16 path keeps and the fp32 path
+# drops (count_th = 512 pixels) moves the class-averaged PQ by 0.05 - 0.1 point, i.e. the 0.1-point tolerance of
+# north_star was being tested at the resolution of the statistic itself (seen in round 2: T = 50, 8 frames, FP 221 vs 219
+# -> |dPQ| 0.113 with unchanged per-step errors and 0.48 % differing pixels).
+@pytest.mark.parametrize("T,B", [(10, 16), (50, 16)])
 def test_full_pipeline_pq_dvpq_vs_oracle(world, T, B):
     from oracle import eval_oracle as EO
     from oracle import ldmseg_oracle as LO

@@ -174,6 +174,26 @@ def test_unet_eps_frame_sizes_vs_oracle(models, shape, t):
     assert out.sample.shape == (B, 4, h, w) and rel < 3e-2 and mx < 0.15, (shape, t, rel, mx)
 
 
+def test_unet_layernorm_fold_option_vs_oracle(models):
+    """UNet.ln_fold = True (LayerNorm folded into the QKV / GEGLU GEMMs, off by default because it measured slower):
+    same tolerance against the oracle as the default path, and no further from it than the default path is."""
+    from video_latent_diffusion_panoptic_segmentation_b200.ldmseg.models import UNet
+    unet = UNet(device=DEV)
+    unet.ln_fold = True
+    unet.load_state_dict(models["o_unet"].state_dict())
+    unet.remove_cross_attention()
+    B, h, w = 2, 16, 24
+    x = torch.randn((B, 8, h, w), generator=torch.Generator().manual_seed(13)).to(DEV)
+    ts = torch.tensor(499, device=DEV)
+    got = unet(x, ts, encoder_hidden_states=None).sample
+    base = models["unet"](x, ts, encoder_hidden_states=None).sample
+    with torch.no_grad():
+        ref = models["o_unet"](x, ts, encoder_hidden_states=None)
+    rel, rel_base = _rel(got, ref), _rel(base, ref)
+    assert rel < 3e-2 and rel <= 1.5 * rel_base + 1e-3, (rel, rel_base)
+    assert not torch.equal(got, base)  # the option really took the other path
+
+
 def test_sampler_vs_oracle(models):
     from oracle import ldmseg_oracle as LO
     from video_latent_diffusion_panoptic_segmentation_b200.ldmseg.schedulers import DDIMNoiseScheduler

@@ -32,6 +32,7 @@ class GemmDesc(C.Structure):
         ("heads", c_i32), ("head_dim", c_i32), ("dpad", c_i32), ("seq", c_i32), ("seq_pad", c_i32),
         ("vt_rows", c_i32), ("n_store", c_i32), ("qkv_part0", c_i32),
         ("identity", c_vp), ("splitk_ws", c_vp), ("splitk_ws_bytes", C.c_int64),
+        ("row_stats_out", c_vp), ("ln_stats", c_vp), ("ln_colsum", c_vp), ("ln_fold_eps", c_f32), ("ln_parts", c_i32),
     ]
 
 

@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 flash_attn40_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // an offset, not an integer round trip: the compiler keeps the shared address space (LDS / STS instead of generic LD / ST)
   uint8_t* sQ = smem;                   // 2 * kQBytes
   uint8_t* sKV = sQ + 2 * kQBytes;      // kStages * kStageBytes
   float* sMerge = reinterpret_cast<float*>(sKV + kStages * kStageBytes);  // kMergeBytes

@@ -27,6 +27,8 @@ LDM_GEMM_DECLARE(launch_gemm_qkv)
 LDM_GEMM_DECLARE(launch_gemm_direct)
 LDM_GEMM_DECLARE(launch_gemm_convt)
 LDM_GEMM_DECLARE(launch_gemm_split)
+LDM_GEMM_DECLARE(launch_gemm_geglu_ln)
+LDM_GEMM_DECLARE(launch_gemm_qkv_ln)
 }  // namespace ldm_gemm
 
 namespace {
@@ -262,7 +264,7 @@ extern "C" int ldm_gemm_bf16(const ldm_gemm_desc* d, ldm_stream_t stream) {
   const long kblocks_total = (long)d->taps * p.kblocks;
   double cost1 = 0.0, cost2 = 0.0;
   // split-K needs the caller's workspace and the plain bf16 [rows, N] epilogue (checked again below)
-  const bool split_ok = d->splitk_ws && d->splitk_ws_bytes > 0 && d->block_n <= 0 &&
+  const bool split_ok = d->splitk_ws && d->splitk_ws_bytes > 0 && d->block_n <= 0 && !d->row_stats_out &&
                         !(flags & (LDM_GEMM_OUT_F32 | LDM_GEMM_OUT_NCHW_F32 | LDM_GEMM_QKV_SPLIT |
                                    LDM_GEMM_CONVT_LN_SILU | LDM_GEMM_GEGLU)) &&
                         d->N >= 64 && d->N % 8 == 0 && staged_enabled() && splitk_enabled() &&
@@ -283,7 +285,8 @@ extern "C" int ldm_gemm_bf16(const ldm_gemm_desc* d, ldm_stream_t stream) {
   // (LDM_GEMM_QKV_TMA=0: the row-per-thread stores, A/B timing)
   const bool qkv_tma_enabled = diag_env("LDM_GEMM_QKV_TMA", 1) != 0;
   bool qkv_tma = false;
-  if ((flags & LDM_GEMM_QKV_SPLIT) && qkv_tma_enabled && d->block_n <= 0 && !d->bias && !d->rowbias && d->head_dim > 0 &&
+  if ((flags & LDM_GEMM_QKV_SPLIT) && qkv_tma_enabled && d->block_n <= 0 && (!d->bias || d->ln_stats) && !d->rowbias &&
+      d->head_dim > 0 &&
       160 % d->head_dim == 0 && (d->heads * d->head_dim) % 160 == 0 && p.H == 1 && p.bw == kBlockM && p.bh == 1 &&
       d->dpad == ((d->head_dim + 63) / 64) * 64 && d->seq >= kBlockM && kblocks_total <= 6) {
     // only where the epilogue, not the main loop, bounds the tile (K <= 384: the 48x156 level). Measured: 105 -> 73 us
@@ -322,7 +325,7 @@ extern "C" int ldm_gemm_bf16(const ldm_gemm_desc* d, ldm_stream_t stream) {
   p.taps = d->taps;
   p.ktap = d->c1 + c2;
   p.stage_bytes = kABytes + (pair ? block_n / 2 : block_n) * kBlockK * 2;
-  p.stages = (kSmemBudget - 2048 - kEpiStageBytes) / p.stage_bytes;
+  p.stages = (kSmemBudget - (1024 + 256) /* alignment slack + barriers, see smem_bytes below */ - kEpiStageBytes) / p.stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   LDM_REQUIRE(p.stages >= 2, LDM_ERR_BAD_SHAPE, "ldm_gemm_bf16: not enough shared memory for 2 stages");
   // bf16 [rows, N] outputs (and GEGLU's [rows, N/2]) leave through shared memory + TMA store
@@ -362,6 +365,25 @@ extern "C" int ldm_gemm_bf16(const ldm_gemm_desc* d, ldm_stream_t stream) {
     LDM_REQUIRE((long long)d->B * d->H * d->W * d->seq < (1LL << 40) && (long long)d->N * d->heads * d->head_dim < (1LL << 40),
                 LDM_ERR_BAD_SHAPE, "ldm_gemm_bf16: QKV split extents too large for the multiply-shift division");
   }
+  // LayerNorm fold (see ldm_gemm_desc.ln_stats)
+  if (d->row_stats_out)
+    LDM_REQUIRE(staged && !(flags & LDM_GEMM_GEGLU), LDM_ERR_BAD_ARG,
+                "ldm_gemm_bf16: row_stats_out needs the plain bf16 [rows, N] epilogue (N >= 64, N %% 8 == 0)");
+  if (d->ln_stats) {
+    LDM_REQUIRE((flags & (LDM_GEMM_GEGLU | LDM_GEMM_QKV_SPLIT)) && d->ln_colsum && d->taps == 1 && !d->a2 && !d->rowbias &&
+                    d->ln_parts == (d->c1 + 31) / 32 && d->N % 8 == 0,
+                LDM_ERR_BAD_ARG, "ldm_gemm_bf16: ln_stats needs a GEGLU / QKV_SPLIT pointwise GEMM, ln_colsum and "
+                "ln_parts == ceil(c1 / 32) (got %d for c1 = %d)", d->ln_parts, d->c1);
+    LDM_REQUIRE((flags & LDM_GEMM_QKV_SPLIT) || staged, LDM_ERR_BAD_SHAPE,
+                "ldm_gemm_bf16: the folded GEGLU needs the staged epilogue (N >= 128, N %% 32 == 0)");
+  }
+  p.row_stats = reinterpret_cast<float*>(d->row_stats_out);
+  p.ln_stats = reinterpret_cast<const float*>(d->ln_stats);
+  p.ln_colsum = d->ln_colsum;
+  p.ln_parts = d->ln_parts;
+  p.rows_total = (long long)d->B * d->H * d->W;
+  p.ln_invc = 1.0f / (float)d->c1;
+  p.ln_fold_eps = d->ln_fold_eps;
   p.n_store = d->n_store > 0 ? d->n_store : d->N;
   p.img_px = (long long)d->H * d->W;
 
@@ -453,8 +475,12 @@ extern "C" int ldm_gemm_bf16(const ldm_gemm_desc* d, ldm_stream_t stream) {
   const cudaStream_t st = as_stream(stream);
   if (flags & LDM_GEMM_CONVT_LN_SILU)
     e = launch_gemm_convt(pair, grid, smem_bytes, st, tmA1, tmA2, tmB, tmO, tmR, tmE, p);
+  else if ((flags & LDM_GEMM_QKV_SPLIT) && d->ln_stats)
+    e = launch_gemm_qkv_ln(pair, grid, smem_bytes, st, tmA1, tmA2, tmB, tmO, tmR, tmE, p);
   else if (flags & LDM_GEMM_QKV_SPLIT)
     e = launch_gemm_qkv(pair, grid, smem_bytes, st, tmA1, tmA2, tmB, tmO, tmR, tmE, p);
+  else if (staged && (flags & LDM_GEMM_GEGLU) && d->ln_stats)
+    e = launch_gemm_geglu_ln(pair, grid, smem_bytes, st, tmA1, tmA2, tmB, tmO, tmR, tmE, p);
   else if (staged && (flags & LDM_GEMM_GEGLU))
     e = launch_gemm_geglu(pair, grid, smem_bytes, st, tmA1, tmA2, tmB, tmO, tmR, tmE, p);
   else if (staged && split_k > 1)

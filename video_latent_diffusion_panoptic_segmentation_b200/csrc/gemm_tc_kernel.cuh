@@ -14,7 +14,7 @@ constexpr int kMaxStages = 8;
 constexpr int kEpiWarps = 8;  // two warps per TMEM lane quadrant, each takes every other 32-column chunk
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kSmemBudget = 227 * 1024;
-constexpr int kEpiStageBytes = 2 * 16384 + 1024;  // epilogue output staging for the TMA-store path + per-half bias slice
+constexpr int kEpiStageBytes = 2 * 16384 + 1280;  // epilogue output staging for the TMA-store path + bias and LN column-sum slices (128 floats each; QKV_SPLIT with the LN fold: 160 each)
 // Diagnostic switches (env LDM_GEMM_DEBUG, never set by the product): isolate the two halves of the main loop.
 constexpr int kStagedStore = 1 << 20; // internal: epilogue writes the output through shared memory + TMA store
 constexpr int kQkvStaged = 1 << 21;   // internal (QKV_SPLIT): q / k tiles are whole heads and leave through TMA stores
@@ -48,6 +48,13 @@ struct GemmParams {
   unsigned long long magic_seq, magic_c, magic_d;  // ceil(2^40 / divisor): x / d == (x * magic) >> 40 for x * d < 2^40
   int n_store;      // OUT_NCHW_F32: leading output channels actually stored
   long long img_px; // pixels per image of the un-flattened problem (H*W)
+  // LayerNorm folded into the GEMMs around it (no normalisation pass, see ldm_gemm_desc.ln_stats):
+  float* row_stats;        // producer (staged epilogue): per row and 32-column chunk (sum, sum of squares) of the bf16 output
+  const float* ln_stats;   // consumer: the producer's partials of ITS INPUT rows, [ln_parts][rows][2]
+  const float* ln_colsum;  // consumer: g[n] = sum_c W'[n, c] (W' = gamma-scaled weight as stored)
+  int ln_parts;
+  long long rows_total;    // B * H * W: the partials are part-major, [parts][rows_total] (sum, sum of squares)
+  float ln_invc, ln_fold_eps;
   // split-K (kEpiSplit): every tile is computed by split_k work items, each over a contiguous range of the K blocks
   int split_k;
   float* ws;                  // fp32 partial tiles [split_k][m_tiles_alloc][n_tiles][block_n][128 rows]
@@ -79,16 +86,21 @@ __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* dst, const float* v)
 // (bit-reproducible) and applies the plain epilogue on all SMs. (A first version let the tile's last-arriving item do
 // that inside this kernel: one SM pulling split_k x 48 - 128 KB through ~10 rounds of L2 latency cost more than the
 // main loop it saved -- 29 us instead of 45 at M = 120, no gain at M = 960.)
-enum { kEpiStaged = 0, kEpiGeglu = 1, kEpiQkv = 2, kEpiDirect = 3, kEpiConvT = 4, kEpiSplit = 5 };
+// kEpiGegluLn / kEpiQkvLn = the GEGLU / QKV_SPLIT epilogues with the LayerNorm fold (ldm_gemm_desc.ln_stats) compiled
+// in. (As a runtime branch inside the plain instantiations the fold grew both kernels by a third and slowed them -- with
+// or without fold -- by 30 - 50 us per launch at the 48x156 level.)
+enum { kEpiStaged = 0, kEpiGeglu = 1, kEpiQkv = 2, kEpiDirect = 3, kEpiConvT = 4, kEpiSplit = 5, kEpiGegluLn = 6, kEpiQkvLn = 7 };
 
-template <bool kPair, int kEpi>
+template <bool kPair, int kEpiT>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
                const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmE, const GemmParams p) {
+  constexpr bool kLn = kEpiT == kEpiGegluLn || kEpiT == kEpiQkvLn;                                     // LayerNorm fold
+  constexpr int kEpi = kEpiT == kEpiGegluLn ? (int)kEpiGeglu : kEpiT == kEpiQkvLn ? (int)kEpiQkv : kEpiT;  // epilogue mode
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by SWIZZLE_128B tiles (the dynamic smem base is the same in both CTAs of a pair).
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // an offset, not an integer round trip: the compiler keeps the shared address space (LDS / STS instead of generic LD / ST)
   uint8_t* epi_smem = smem + p.stages * p.stage_bytes;  // 2 x 16 KiB output staging (one 128 x 64 bf16 block per half)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + kEpiStageBytes);
   uint64_t* empty_bar = full_bar + kMaxStages;
@@ -299,6 +311,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     int sb = 0;                                  // staging buffer of the next output block (alternates)
     int as = 0;
     uint32_t aphase = 0;
+    // LayerNorm fold: the row moments of a tile are loaded one tile ahead. This kernel is epilogue-bound at K = 320, all
+    // eight epilogue warps reach the loads at the same moment, and an L2 round trip in front of every tile was the whole
+    // cost of the fold (ncu: long_scoreboard on the first use; 110 -> 153 us for the GEGLU launch of the 48x156 level).
+    // part-major partials [ln_parts][rows]: the 32 lanes of a warp (consecutive rows) read 256 contiguous bytes per part.
+    constexpr int kLnPre = 20;  // partials held in registers across a tile (C = 320 / 640: all of them; 1280: half)
+    [[maybe_unused]] float2 ln_pre[kLnPre];
+    [[maybe_unused]] auto ln_issue = [&](int item2) {
+      const int tile2 = kSplit ? item2 / split : item2;
+      const int n_tile2 = tile2 / m_units;
+      const int m_unit2 = tile2 - n_tile2 * m_units;
+      const int m_tile2 = kPair ? 2 * m_unit2 + (int)rank : m_unit2;
+      const int b2 = m_tile2 / tiles_per_img;
+      const int rem2 = m_tile2 - b2 * tiles_per_img;
+      const int ty2 = rem2 / p.tiles_x;
+      const int tx2 = rem2 - ty2 * p.tiles_x;
+      const int ly2 = r / p.bw, lx2 = r - ly2 * p.bw;
+      const int y2 = ty2 * p.bh + ly2, x2 = tx2 * p.bw + lx2;
+      const bool valid2 = (m_tile2 < p.m_tiles) && (r < p.bw * p.bh) && (y2 < p.H) && (x2 < p.W);
+      const float2* sp = reinterpret_cast<const float2*>(p.ln_stats) + (((long long)b2 * p.H + y2) * p.W + x2);
+#pragma unroll
+      for (int j = 0; j < kLnPre; ++j)
+        ln_pre[j] = (valid2 && j < p.ln_parts) ? __ldg(sp + (long long)j * p.rows_total) : make_float2(0.f, 0.f);
+    };
+    if constexpr (kLn) {
+      if (worker < num_items) ln_issue(worker);
+    }
     for (int item = worker; item < num_items; item += num_workers) {
       const int tile = kSplit ? item / split : item;
       const int slice = kSplit ? item - tile * split : 0;
@@ -322,6 +360,49 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         qkv_s = (int)(grow - (long long)qkv_bi * p.seq);
       }
 
+      // LayerNorm fold: out = rstd (acc - mean g[n]) + b'[n] = ln_a acc + ln_c g[n] + b'[n] with this row's moments
+      float ln_a = 1.f, ln_c = 0.f;
+      constexpr bool ln_fold = kLn;
+      if constexpr (ln_fold) {
+        float su = 0.f, sq = 0.f;
+#pragma unroll
+        for (int j = 0; j < kLnPre; ++j) {  // fixed order: bit-reproducible (the slots past ln_parts hold zeros)
+          su += ln_pre[j].x;
+          sq += ln_pre[j].y;
+        }
+        if (valid) {
+          const float2* sp = reinterpret_cast<const float2*>(p.ln_stats) + grow;
+          for (int i = kLnPre; i < p.ln_parts; i += 10) {  // C = 1280: the second half, ten loads in flight at once
+            float2 t[10];
+#pragma unroll
+            for (int j = 0; j < 10; ++j)
+              t[j] = i + j < p.ln_parts ? __ldg(sp + (long long)(i + j) * p.rows_total) : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 10; ++j) {
+              su += t[j].x;
+              sq += t[j].y;
+            }
+          }
+        }
+        const float mean = su * p.ln_invc;
+        ln_a = rsqrtf(fmaxf(fmaf(-mean, mean, sq * p.ln_invc), 0.f) + p.ln_fold_eps);
+        ln_c = -mean * ln_a;
+        if (item + num_workers < num_items) ln_issue(item + num_workers);  // in flight during this tile's epilogue
+      }
+      // QKV_SPLIT with the fold: the tile's folded bias and column sums go through shared memory once (the epilogue
+      // bounds this kernel at K = 320; sixteen broadcast loads per 32-column chunk behind the TMEM wait were not free)
+      const bool ln_smem = kEpi == kEpiQkv && ln_fold && p.block_n <= 160;  // (wider tiles: broadcast loads)
+      float* sLn = reinterpret_cast<float*>(epi_smem + 2 * 16384);  // [0, 160) bias', [160, 320) g
+      if (ln_smem) {
+        named_bar_sync(1, 32 * kEpiWarps);  // the previous tile's readers are done
+        const int t = threadIdx.x - 64;
+        if (t < p.block_n) {
+          const int n = n0 + t;
+          sLn[t] = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.f;
+          sLn[160 + t] = n < p.N ? __ldg(p.ln_colsum + n) : 0.f;
+        }
+        named_bar_sync(1, 32 * kEpiWarps);
+      }
       // residual rows of this tile: issue every load now, so that they are in flight while the MMAs finish
       // staged path: both halves work on the same 64-column output block, half h on its 32-column chunk h, so chunk
       // ci of a thread covers columns min(ci*64, block_n-64) + h*32; direct path: a half owns every other chunk.
@@ -340,6 +421,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         }
       }
 
+      // staged epilogues without the fold: the tile's bias (+ per-image bias) goes to shared memory ONCE per tile and
+      // before the accumulator wait (per 64-column block it cost a global round trip behind every block's barrier).
+      // Safe without a barrier of its own: every read of the previous tile's values lies before that tile's last
+      // block barrier, and the first block barrier below publishes these.
+      constexpr bool tile_bias = staged && !kSplit && !kLn;
+      if constexpr (tile_bias) {
+        float* sbias = reinterpret_cast<float*>(epi_smem + 2 * 16384);
+        const int t = threadIdx.x - 64;
+        if (t < p.block_n) {
+          const int n = n0 + t;
+          float bv = 0.f;
+          if (n < p.N) {
+            if (p.bias) bv = __ldg(p.bias + n);
+            if (p.rowbias) bv += __ldg(p.rowbias + (long long)b * p.N + n);
+          }
+          sbias[t] = bv;
+        }
+      }
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)as * 256u;
@@ -418,10 +517,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           // a ragged last block is shifted left so that it ends at block_n: the overlap is rewritten with the same values
           const int c0 = min(ob * acc_w, p.block_n - acc_w);
           uint8_t* sbuf = epi_smem + sb * 16384;
-          float* sbias = reinterpret_cast<float*>(epi_smem + 2 * 16384) + sb * 128;
+          // (single-buffered: the next block's values are written after this block's second barrier, behind every read)
+          float* sbias = reinterpret_cast<float*>(epi_smem + 2 * 16384);
+          float* sgsum = sbias + 128;  // LN fold: g[n] of the same columns
           if (epi_leader) bulk_wait_read1();  // the store that last used this buffer (two blocks ago) has been read
-          {
-            // this block's bias values (bias + per-image bias) once, through shared memory
+          if constexpr (!tile_bias) {
+            // (fold: folded bias and column sums of this block; 2 x block_n floats do not fit the slice)
             const int t = threadIdx.x - 64;
             if (t < acc_w) {
               const int n = n0 + c0 + t;
@@ -431,6 +532,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                 if (p.rowbias) bv += __ldg(p.rowbias + (long long)b * p.N + n);
               }
               sbias[t] = bv;
+              if (ln_fold) sgsum[t] = n < p.N ? __ldg(p.ln_colsum + n) : 0.f;
             }
           }
           named_bar_sync(1, 32 * kEpiWarps);
@@ -442,18 +544,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             const int c = c0 + cc;
             uint32_t v[32];
             tmem_ld32(t_addr + c, v);
-            tmem_ld_wait();
             const int nc = n0 + c;
             float f[32];
             {
-              const float4* bp = reinterpret_cast<const float4*>(sbias + cc);
+              const float4* bp = reinterpret_cast<const float4*>(sbias + (tile_bias ? c : cc));
+              if (ln_fold) {
+                tmem_ld_wait();
+                const float4* gp = reinterpret_cast<const float4*>(sgsum + cc);
 #pragma unroll
-              for (int g = 0; g < 8; ++g) {
-                const float4 bv = bp[g];
-                f[g * 4] = __uint_as_float(v[g * 4]) + bv.x;
-                f[g * 4 + 1] = __uint_as_float(v[g * 4 + 1]) + bv.y;
-                f[g * 4 + 2] = __uint_as_float(v[g * 4 + 2]) + bv.z;
-                f[g * 4 + 3] = __uint_as_float(v[g * 4 + 3]) + bv.w;
+                for (int g = 0; g < 8; ++g) {
+                  const float4 bv = bp[g], gv = gp[g];
+                  f[g * 4] = fmaf(ln_a, __uint_as_float(v[g * 4]), fmaf(ln_c, gv.x, bv.x));
+                  f[g * 4 + 1] = fmaf(ln_a, __uint_as_float(v[g * 4 + 1]), fmaf(ln_c, gv.y, bv.y));
+                  f[g * 4 + 2] = fmaf(ln_a, __uint_as_float(v[g * 4 + 2]), fmaf(ln_c, gv.z, bv.z));
+                  f[g * 4 + 3] = fmaf(ln_a, __uint_as_float(v[g * 4 + 3]), fmaf(ln_c, gv.w, bv.w));
+                }
+              } else {
+                float4 bv[8];  // shared-memory reads under the TMEM load
+#pragma unroll
+                for (int g = 0; g < 8; ++g) bv[g] = bp[g];
+                tmem_ld_wait();
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                  f[g * 4] = __uint_as_float(v[g * 4]) + bv[g].x;
+                  f[g * 4 + 1] = __uint_as_float(v[g * 4 + 1]) + bv[g].y;
+                  f[g * 4 + 2] = __uint_as_float(v[g * 4 + 2]) + bv[g].z;
+                  f[g * 4 + 3] = __uint_as_float(v[g * 4 + 3]) + bv[g].w;
+                }
               }
             }
             if (geglu) {
@@ -483,13 +600,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = silu_f(f[j]);
               }
+              float st_s = 0.f, st_q = 0.f;
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
                 uint4 u;
                 u.x = pack_bf16(f[g * 8 + 0], f[g * 8 + 1]); u.y = pack_bf16(f[g * 8 + 2], f[g * 8 + 3]);
                 u.z = pack_bf16(f[g * 8 + 4], f[g * 8 + 5]); u.w = pack_bf16(f[g * 8 + 6], f[g * 8 + 7]);
                 *reinterpret_cast<uint4*>(rowp + (((half * 4 + g) ^ (r & 7)) << 4)) = u;
+                if (kEpi == kEpiStaged && p.row_stats) {  // moments of the values as the consumer will read them (bf16)
+                  const float2 a0 = unpack_bf16(u.x), a1 = unpack_bf16(u.y), a2 = unpack_bf16(u.z), a3 = unpack_bf16(u.w);
+                  st_s += ((a0.x + a0.y) + (a1.x + a1.y)) + ((a2.x + a2.y) + (a3.x + a3.y));
+                  st_q = fmaf(a0.x, a0.x, st_q); st_q = fmaf(a0.y, a0.y, st_q); st_q = fmaf(a1.x, a1.x, st_q);
+                  st_q = fmaf(a1.y, a1.y, st_q); st_q = fmaf(a2.x, a2.x, st_q); st_q = fmaf(a2.y, a2.y, st_q);
+                  st_q = fmaf(a3.x, a3.x, st_q); st_q = fmaf(a3.y, a3.y, st_q);
+                }
               }
+              // one partial per 32-column chunk and row (part = column / 32: independent of block_n; the overlap
+              // columns of a shifted last block are written twice with the same value)
+              if (kEpi == kEpiStaged && p.row_stats && valid && nc < p.N)
+                *reinterpret_cast<float2*>(p.row_stats + ((long long)(nc >> 5) * p.rows_total + grow) * 2) =
+                    make_float2(st_s, st_q);
             }
           }
           fence_proxy_async_smem();
@@ -534,6 +664,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                 for (int g = 0; g < 4; ++g)
                   if (g < ng) tmem_ld8(t_addr + cbase + g * 8, v + g * 8);
                 tmem_ld_wait();
+                if (ln_fold) {
+#pragma unroll
+                  for (int g = 0; g < 4; ++g)
+                    if (g < ng) {
+                      const int cl = cbase + g * 8;  // column inside the tile
+                      float4 g0, g1, b0, b1;
+                      if (ln_smem) {
+                        b0 = *reinterpret_cast<const float4*>(sLn + cl);
+                        b1 = *reinterpret_cast<const float4*>(sLn + cl + 4);
+                        g0 = *reinterpret_cast<const float4*>(sLn + 160 + cl);
+                        g1 = *reinterpret_cast<const float4*>(sLn + 160 + cl + 4);
+                      } else {
+                        const int n = n0 + cl;
+                        g0 = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + n));
+                        g1 = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + n + 4));
+                        b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+                        if (p.bias) {
+                          b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                          b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
+                        }
+                      }
+                      const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                      for (int j = 0; j < 8; ++j)
+                        v[g * 8 + j] = __float_as_uint(fmaf(ln_a, __uint_as_float(v[g * 8 + j]), fmaf(ln_c, gv[j], bv[j])));
+                    }
+                }
                 uint8_t* rowp = sbuf + r * 128;
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
@@ -579,7 +737,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (p.bias) {  // N % 8 == 0 (GEGLU: % 32): 4-wide groups are all-in or all-out
+          if (ln_smem) {  // rstd (acc - mean g[n]) + b'[n], both column vectors from shared memory
+            const float4* bp = reinterpret_cast<const float4*>(sLn + c);
+            const float4* gp = reinterpret_cast<const float4*>(sLn + 160 + c);
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              if (nc + g * 4 < p.N) {
+                const float4 gv = gp[g], bv = bp[g];
+                f[g * 4] = fmaf(ln_a, f[g * 4], fmaf(ln_c, gv.x, bv.x));
+                f[g * 4 + 1] = fmaf(ln_a, f[g * 4 + 1], fmaf(ln_c, gv.y, bv.y));
+                f[g * 4 + 2] = fmaf(ln_a, f[g * 4 + 2], fmaf(ln_c, gv.z, bv.z));
+                f[g * 4 + 3] = fmaf(ln_a, f[g * 4 + 3], fmaf(ln_c, gv.w, bv.w));
+              }
+          } else if (ln_fold) {  // rstd (acc - mean g[n]); the folded bias b' follows below
+            const float4* gp = reinterpret_cast<const float4*>(p.ln_colsum + nc);
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              if (nc + g * 4 < p.N) {
+                const float4 gv = __ldg(gp + g);
+                f[g * 4] = fmaf(ln_a, f[g * 4], ln_c * gv.x); f[g * 4 + 1] = fmaf(ln_a, f[g * 4 + 1], ln_c * gv.y);
+                f[g * 4 + 2] = fmaf(ln_a, f[g * 4 + 2], ln_c * gv.z); f[g * 4 + 3] = fmaf(ln_a, f[g * 4 + 3], ln_c * gv.w);
+              }
+          }
+          if (p.bias && !ln_smem) {  // N % 8 == 0 (GEGLU: % 32): 4-wide groups are all-in or all-out
             const float4* bp = reinterpret_cast<const float4*>(p.bias + nc);
 #pragma unroll
             for (int g = 0; g < 8; ++g)

@@ -87,6 +87,11 @@ class UNet:
         self._cross_attention_removed = False
         self.encoder_hid_proj = None
         self.use_cuda_graph = True
+        # BasicTransformerBlock's LayerNorms folded into the GEMMs around them (ldm_gemm_desc.ln_stats) instead of
+        # ldm_layernorm passes. Built, parity-checked and measured (tools/bench_ln_fold.py): it removes
+        # 0.54 ms of LayerNorm per forward but the QKV / GEGLU epilogues it lands in are issue-bound at K = 320 - 640
+        # and pay 0.9 ms for it, so the default is the separate pass.
+        self.ln_fold = False
         self.training = False
 
     # ------------------------------------------------------------------ construction (main_ldm.py:147-169)
@@ -254,17 +259,33 @@ class UNet:
             P[tb + ".norm1"], P[tb + ".norm3"] = norm(tb + ".norm1"), norm(tb + ".norm3")
             wqkv = torch.cat([sd[tb + ".attn1.to_q.weight"], sd[tb + ".attn1.to_k.weight"],
                               sd[tb + ".attn1.to_v.weight"]], 0)
-            P[tb + ".qkv"] = dv(wqkv, bf16)
+            if not self.ln_fold:
+                P[tb + ".qkv"] = dv(wqkv, bf16)
+
+            def folded(w, b, ln):
+                """(gamma o W in bf16, b + W beta, row sums of the rounded gamma o W): the Linear behind LayerNorm `ln`
+                in the form the GEMM epilogue normalises itself (ldm_gemm_desc.ln_stats)."""
+                w2, b2, cs = ops.fold_layernorm(w.float(), b, sd[ln + ".weight"].float(), sd[ln + ".bias"].float())
+                return dv(w2, bf16), dv(b2), dv(cs)
+
+            if self.ln_fold:
+                P[tb + ".qkv_ln"] = folded(wqkv, None, tb + ".norm1")
             P[tb + ".to_out"] = lin(tb + ".attn1.to_out.0")
             w1, b1 = sd[tb + ".ff.net.0.proj.weight"], sd[tb + ".ff.net.0.proj.bias"]
             inner = w1.shape[0] // 2
             idx = torch.arange(inner).view(-1, 16)
             perm = torch.cat([idx, idx + inner], dim=1).reshape(-1)  # 16 value rows, then their 16 gate rows
-            P[tb + ".ff1"] = (dv(w1[perm], bf16), dv(b1[perm]))
+            if not self.ln_fold:
+                P[tb + ".ff1"] = (dv(w1[perm], bf16), dv(b1[perm]))
+            else:
+                P[tb + ".ff1_ln"] = folded(w1[perm], b1[perm], tb + ".norm3")
             P[tb + ".ff2"] = lin(tb + ".ff.net.2")
             if P["cross"]:  # BasicTransformerBlock.norm2 / attn2 against encoder_hidden_states (SURVEY 8f rank 4)
                 P[tb + ".norm2"] = norm(tb + ".norm2")
-                P[tb + ".q2"] = dv(sd[tb + ".attn2.to_q.weight"], bf16)
+                if not self.ln_fold:
+                    P[tb + ".q2"] = dv(sd[tb + ".attn2.to_q.weight"], bf16)
+                else:
+                    P[tb + ".q2_ln"] = folded(sd[tb + ".attn2.to_q.weight"], None, tb + ".norm2")
                 P[tb + ".kv2"] = dv(torch.cat([sd[tb + ".attn2.to_k.weight"], sd[tb + ".attn2.to_v.weight"]], 0), bf16)
                 P[tb + ".to_out2"] = lin(tb + ".attn2.to_out.0")
         if P["cross"]:
@@ -304,6 +325,7 @@ class UNet:
         st.emb_silu = torch.empty((temb_dim,), dtype=f32, device=dev)
         st.temb_bias = torch.empty((P["temb_total"],), dtype=f32, device=dev)
         qkv_cache = {}
+        ln_stats_cache = {}  # per-row LayerNorm moments [C/32, M, 2], one buffer per level (producer -> consumer in stream order)
         ctx_plan = []  # launches that depend only on the context: run when it changes, not once per DDIM step
         st.ctx_len, st.context_in, st.context = ctx_len, None, None
         if cross:
@@ -362,15 +384,25 @@ class UNet:
             t0 = arena.alloc((B, H, W, C))
             add(ops.groupnorm, x, *P[name + ".norm"], t0, st.gn_stats, groups=groups, eps=1e-6, silu=False)
             hid = arena.alloc((M, C))
-            add(ops.gemm, t0.view(M, C), P[name + ".proj_in"][0], hid, bias=P[name + ".proj_in"][1])
+            # LayerNorm folded into the GEMMs on both sides of it (ops.gemm row_stats / ln_fold): the GEMM that writes
+            # the residual stream also writes its per-row moments, the QKV / GEGLU GEMM normalises in its epilogue
+            fold = self.ln_fold
+            if fold and (M, C) not in ln_stats_cache:
+                ln_stats_cache[(M, C)] = torch.empty(((C + 31) // 32, M, 2), dtype=f32, device=dev)
+            rs = ln_stats_cache[(M, C)] if fold else None
+            add(ops.gemm, t0.view(M, C), P[name + ".proj_in"][0], hid, bias=P[name + ".proj_in"][1], row_stats=rs)
             arena.release(t0)
             t1 = arena.alloc((M, C))
-            add(ops.layernorm, hid, *P[tb + ".norm1"], t1, 1e-5)
-            add(ops.gemm, t1, P[tb + ".qkv"], None, flags=L.LDM_GEMM_QKV_SPLIT, qkv=qkv)
+            if fold:
+                wq, bq, csq = P[tb + ".qkv_ln"]
+                add(ops.gemm, hid, wq, None, bias=bq, flags=L.LDM_GEMM_QKV_SPLIT, qkv=qkv, ln_fold=(rs, csq, 1e-5))
+            else:
+                add(ops.layernorm, hid, *P[tb + ".norm1"], t1, 1e-5)
+                add(ops.gemm, t1, P[tb + ".qkv"], None, flags=L.LDM_GEMM_QKV_SPLIT, qkv=qkv)
             add(ops.flash_attn, qkv["q"], qkv["k"], qkv["vt"], t1, B=B, heads=heads, seq=seq, head_dim=d,
                 dpad=qkv["dpad"], seq_pad=qkv["seq_pad"], scale=d ** -0.5)
             h2 = arena.alloc((M, C))
-            add(ops.gemm, t1, P[tb + ".to_out"][0], h2, bias=P[tb + ".to_out"][1], residual=hid)
+            add(ops.gemm, t1, P[tb + ".to_out"][0], h2, bias=P[tb + ".to_out"][1], residual=hid, row_stats=rs)
             arena.release(t1)
             arena.release(hid)
             if cross:
@@ -379,21 +411,29 @@ class UNet:
                 ctx_plan.append((ops.gemm, (st.context, P[tb + ".kv2"], None),
                                  dict(flags=L.LDM_GEMM_QKV_SPLIT, qkv=dict(kv, part0=1))))
                 t1 = arena.alloc((M, C))
-                add(ops.layernorm, h2, *P[tb + ".norm2"], t1, 1e-5)
-                add(ops.gemm, t1, P[tb + ".q2"], None, flags=L.LDM_GEMM_QKV_SPLIT,
-                    qkv=dict(q=qkv["q"], heads=heads, head_dim=d, dpad=qkv["dpad"], seq=seq, seq_pad=qkv["seq_pad"]))
+                q_only = dict(q=qkv["q"], heads=heads, head_dim=d, dpad=qkv["dpad"], seq=seq, seq_pad=qkv["seq_pad"])
+                if fold:
+                    wq2, bq2, csq2 = P[tb + ".q2_ln"]
+                    add(ops.gemm, h2, wq2, None, bias=bq2, flags=L.LDM_GEMM_QKV_SPLIT, qkv=q_only, ln_fold=(rs, csq2, 1e-5))
+                else:
+                    add(ops.layernorm, h2, *P[tb + ".norm2"], t1, 1e-5)
+                    add(ops.gemm, t1, P[tb + ".q2"], None, flags=L.LDM_GEMM_QKV_SPLIT, qkv=q_only)
                 add(ops.flash_attn, qkv["q"], kv["k"], kv["vt"], t1, B=B, heads=heads, seq=seq, head_dim=d,
                     dpad=kv["dpad"], seq_pad=kv["seq_pad"], scale=d ** -0.5, kv_seq=ctx_len)
                 h2b = arena.alloc((M, C))
-                add(ops.gemm, t1, P[tb + ".to_out2"][0], h2b, bias=P[tb + ".to_out2"][1], residual=h2)
+                add(ops.gemm, t1, P[tb + ".to_out2"][0], h2b, bias=P[tb + ".to_out2"][1], residual=h2, row_stats=rs)
                 arena.release(t1)
                 arena.release(h2)
                 h2 = h2b
-            t2 = arena.alloc((M, C))
-            add(ops.layernorm, h2, *P[tb + ".norm3"], t2, 1e-5)
             g = arena.alloc((M, 4 * C))
-            add(ops.gemm, t2, P[tb + ".ff1"][0], g, bias=P[tb + ".ff1"][1], flags=L.LDM_GEMM_GEGLU)
-            arena.release(t2)
+            if fold:
+                wf, bf_, csf = P[tb + ".ff1_ln"]
+                add(ops.gemm, h2, wf, g, bias=bf_, flags=L.LDM_GEMM_GEGLU, ln_fold=(rs, csf, 1e-5))
+            else:
+                t2 = arena.alloc((M, C))
+                add(ops.layernorm, h2, *P[tb + ".norm3"], t2, 1e-5)
+                add(ops.gemm, t2, P[tb + ".ff1"][0], g, bias=P[tb + ".ff1"][1], flags=L.LDM_GEMM_GEGLU)
+                arena.release(t2)
             h3 = arena.alloc((M, C))
             add(ops.gemm, g, P[tb + ".ff2"][0], h3, bias=P[tb + ".ff2"][1], residual=h2)
             arena.release(g)

@@ -57,12 +57,15 @@ def _splitk_ws(device):
 
 
 def gemm(a1, w, out=None, *, a2=None, taps=1, bias=None, rowbias=None, residual=None, flags=0, block_n=0,
-         qkv=None, ln=None, n_store=0):
+         qkv=None, ln=None, n_store=0, row_stats=None, ln_fold=None):
     """out = epilogue(conv/gemm(a1 ++ a2, w)). a1/a2: [B,H,W,C] or [rows,C] bf16; w: [N, taps*(c1+c2)] bf16.
 
     qkv = dict(q=, k=, vt=, heads=, head_dim=, dpad=, seq=, seq_pad=[, part0=]) for LDM_GEMM_QKV_SPLIT (part0 and the
     number of C-wide column blocks of w select which of q / k / v are written: see ldm_gemm_desc.qkv_part0);
     ln = (gamma, beta, eps) for LDM_GEMM_CONVT_LN_SILU.
+    LayerNorm fold (ldm_gemm_desc.ln_stats): row_stats = f32 [ceil(N/32), rows, 2] (part-major) written by the GEMM that produces x;
+    ln_fold = (row_stats of x, colsum f32 [N], eps) on the QKV_SPLIT / GEGLU GEMM that consumes x with the folded
+    weight / bias of fold_layernorm().
     """
     _chk(a1, bf16, "a1"); _chk(a2, bf16, "a2"); _chk(w, bf16, "w"); _chk(bias, f32, "bias")
     _chk(rowbias, f32, "rowbias"); _chk(residual, bf16, "residual")
@@ -99,8 +102,33 @@ def gemm(a1, w, out=None, *, a2=None, taps=1, bias=None, rowbias=None, residual=
         g, b_, eps = ln
         _chk(g, f32, "ln_gamma"); _chk(b_, f32, "ln_beta")
         d.ln_gamma, d.ln_beta, d.ln_eps = _p(g), _p(b_), eps
+    if row_stats is not None:
+        _chk(row_stats, f32, "row_stats")
+        if row_stats.numel() != B * H * W * ((d.N + 31) // 32) * 2:
+            raise L.LdmError(f"gemm: row_stats has {row_stats.numel()} floats, expected ceil(N/32) * rows * 2")
+        d.row_stats_out = _p(row_stats)
+    if ln_fold is not None:
+        st, colsum, eps = ln_fold
+        _chk(st, f32, "ln_stats"); _chk(colsum, f32, "ln_colsum")
+        d.ln_parts = (c1 + 31) // 32
+        if st.numel() != B * H * W * d.ln_parts * 2 or colsum.numel() != d.N:
+            raise L.LdmError("gemm: ln_fold stats / colsum shape mismatch")
+        d.ln_stats, d.ln_colsum, d.ln_fold_eps = _p(st), _p(colsum), eps
     L.check(L.lib().ldm_gemm_bf16(C.byref(d), _stream()), "ldm_gemm_bf16")
     return out
+
+
+def fold_layernorm(w, bias, gamma, beta):
+    """Weights of a Linear that follows a LayerNorm, for the folded form (ldm_gemm_desc.ln_stats). w: [N, C] in the
+    layout the GEMM consumes (bf16 or f32; already packed / interleaved / scaled), bias: f32 [N] or None, gamma / beta:
+    f32 [C]. Returns (w' bf16 [N, C] = gamma o w, bias' f32 [N] = bias + w beta, colsum f32 [N] = sum_c w'[n, c] of the
+    ROUNDED w', so that the mean term cancels exactly against what the tensor core multiplies)."""
+    wf = w.float()
+    w2 = (wf * gamma.float()[None, :]).to(bf16)
+    b2 = wf @ beta.float()
+    if bias is not None:
+        b2 = b2 + bias.float()
+    return w2.contiguous(), b2.contiguous(), w2.float().sum(dim=1).contiguous()
 
 
 def gemm_last_config():
