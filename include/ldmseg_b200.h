@@ -35,7 +35,7 @@ enum ldm_status {
   LDM_ERR_DRIVER = -6
 };
 
-int ldm_abi_version(void); /* 3 since ldm_gemm_desc.splitk_ws was added (2: qkv_part0 / ldm_attn_desc.kv_seq) */
+int ldm_abi_version(void); /* 4 since the LayerNorm-fold fields of ldm_gemm_desc (3: splitk_ws; 2: qkv_part0 / ldm_attn_desc.kv_seq) */
 const char* ldm_last_error(void);
 /* 0 when the current device is compute capability 10.0 (B200); LDM_ERR_ARCH otherwise. */
 int ldm_check_device(void);
@@ -226,6 +226,14 @@ int ldm_ddim_step(const float* eps, const float* sample, const float* coef, cons
 int ldm_ddim_step_cfg(const float* eps_uncond, const float* eps_text, float guidance_scale, const float* sample,
                       const float* coef, const int32_t* t_index, float* prev_sample, float* pred_x0, int64_t n,
                       ldm_stream_t stream);
+
+/* The same with the scheduler's clip_sample / use_clipped_model_output (ddim_scheduler.py:253-261): clip_sample_range
+ * > 0 clamps pred_original_sample to [-range, range] before prev_sample is formed (0: no clipping); with
+ * use_clipped_model_output the noise is re-derived from the clamped x0, `(sample - sqrt(a_t) * x0) / sqrt(1 - a_t)`.
+ * The reference's constructor default is clip_sample=True; base.yaml:55 turns it off for this path. */
+int ldm_ddim_step_clip(const float* eps_uncond, const float* eps_text, float guidance_scale, const float* sample,
+                       const float* coef, const int32_t* t_index, float* prev_sample, float* pred_x0, int64_t n,
+                       float clip_sample_range, int32_t use_clipped_model_output, ldm_stream_t stream);
 
 /* Layout helpers (NHWC bf16). */
 int ldm_upsample_nearest(const void* x, void* out, int32_t B, int32_t h, int32_t w, int32_t C, int32_t oh,

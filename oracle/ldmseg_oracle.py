@@ -52,12 +52,15 @@ class DDIMOracle:
         a_prev = self.alphas_cumprod[prev_t] if prev_t >= 0 else self.final_alpha_cumprod
         return (1 - a_t) ** 0.5, a_t ** 0.5, a_prev ** 0.5, (1 - a_prev) ** 0.5
 
-    def step(self, model_output, timestep, sample):
+    def step(self, model_output, timestep, sample, use_clipped_model_output=False):
+        """ddim_scheduler.py:218-269 (epsilon prediction; clip_sample :253-257, use_clipped_model_output :259-261)."""
         assert self.prediction_type == "epsilon"
         s1m_at, s_at, s_ap, s1m_ap = self.coefficients(timestep)
         x0 = (sample - s1m_at * model_output) / s_at
         if self.clip_sample:
             x0 = x0.clamp(-self.clip_sample_range, self.clip_sample_range)
+        if use_clipped_model_output:
+            model_output = (sample - s_at * x0) / s1m_at
         prev = s_ap * x0 + s1m_ap * model_output
         return prev, x0
 

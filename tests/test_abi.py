@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_error_string():
     lib = L.load()
-    assert lib.ldm_abi_version() == 3  # 3: splitk_ws; 2: qkv_part0 / kv_seq descriptor fields
+    assert lib.ldm_abi_version() == 4  # 4: LayerNorm-fold fields; 3: splitk_ws; 2: qkv_part0 / kv_seq descriptor fields
     assert isinstance(lib.ldm_last_error(), bytes)
     assert lib.ldm_launch_count() >= 0
 

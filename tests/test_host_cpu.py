@@ -59,6 +59,12 @@ def test_scheduler_mirror_host_schedule_matches_reference():
     o.set_timesteps_inference(50)
     for t in (999, 499, 19, 0):
         assert [float(c) for c in o.coefficients(t)] == coef[t].tolist()
+    for T in (50, 10, 7, 1000):  # the vectorised table against the reference's per-timestep 0-dim tensor ops, every row
+        s.set_timesteps_inference(T)
+        o.set_timesteps_inference(T)
+        ref = torch.stack([torch.stack(o.coefficients(t)) for t in range(1000)])
+        assert torch.equal(s.step_coefficients(), ref), T
+    s.set_timesteps_inference(50)
     # the fused kernel's formula, evaluated with torch on the CPU, reproduces the reference's step bit for bit
     eps, x = torch.from_numpy(z["eps"]), torch.from_numpy(z["x"])
     for t in (999, 499, 19):

@@ -37,6 +37,25 @@ def test_ddim_step_bit_exact_with_reference():
         assert np.array_equal(x0.numpy(), z[f"x0_{t}"])
 
 
+def test_ddim_step_clip_bit_exact_with_reference():
+    """clip_sample (the reference constructor's default) and use_clipped_model_output, vectors of the real scheduler
+    (tests/golden/make_golden_ddim_clip.py). The inputs are wide enough that the clamp bites."""
+    z = np.load(os.path.join(G, "ddim_steps_clip.npz"))
+    eps, x = torch.from_numpy(z["eps"]), torch.from_numpy(z["x"])
+    clipped = 0
+    for rng in (1.0, 0.5):
+        s = LO.DDIMOracle(clip_sample=True, clip_sample_range=rng)
+        s.set_timesteps_inference(50)
+        for t in (999, 499, 19):
+            for ucm in (False, True):
+                prev, x0 = s.step(eps, t, x, use_clipped_model_output=ucm)
+                tag = f"r{rng}_t{t}_u{int(ucm)}"
+                assert np.array_equal(prev.numpy(), z["prev_" + tag]), tag
+                assert np.array_equal(x0.numpy(), z["x0_" + tag]), tag
+                clipped += int((np.abs(z["x0_" + tag]) == rng).sum())
+    assert clipped > 100
+
+
 def test_seg_decoder_bit_exact_with_reference():
     z = np.load(os.path.join(G, "seg_decoder_small.npz"))
     cfg = GOLD["seg_decoder_small"]["cfg"]

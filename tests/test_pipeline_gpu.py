@@ -71,6 +71,25 @@ def test_scheduler_step_bit_exact_with_reference_fixture():
             assert np.array_equal(o["pred_original_sample"].cpu().numpy(), z[f"x0_{t}"])
 
 
+def test_scheduler_step_clip_sample_bit_exact_with_reference_fixture():
+    """ldm_ddim_step_clip: clip_sample=True (the reference constructor's default) with two ranges, with and without
+    use_clipped_model_output, against vectors of the real reference scheduler (make_golden_ddim_clip.py)."""
+    from video_latent_diffusion_panoptic_segmentation_b200.ldmseg.schedulers import DDIMNoiseScheduler
+    z = np.load(os.path.join(G, "ddim_steps_clip.npz"))
+    eps, x = torch.from_numpy(z["eps"]).to(DEV), torch.from_numpy(z["x"]).to(DEV)
+    for rng in (1.0, 0.5):
+        s = DDIMNoiseScheduler(**dict(SCHED_KW, clip_sample=True, clip_sample_range=rng))
+        s.set_timesteps_inference(50)
+        for t in (999, 499, 19):
+            for ucm in (False, True):
+                o = s.step(eps, t, x, use_clipped_model_output=ucm)
+                tag = f"r{rng}_t{t}_u{int(ucm)}"
+                assert np.array_equal(o.prev_sample.cpu().numpy(), z["prev_" + tag]), tag
+                assert np.array_equal(o.pred_original_sample.cpu().numpy(), z["x0_" + tag]), tag
+    with pytest.raises(Exception):
+        DDIMNoiseScheduler(**dict(SCHED_KW, clip_sample=True, clip_sample_range=0.0)).step(eps, 999, x)
+
+
 def test_seg_decoder_small_reference_fixture():
     from video_latent_diffusion_panoptic_segmentation_b200.ldmseg.models import GeneralVAESeg
     z = np.load(os.path.join(G, "seg_decoder_small.npz"))

@@ -19,7 +19,7 @@ LDM_GEMM_CONVT_LN_SILU = 1 << 4
 LDM_GEMM_OUT_NCHW_F32 = 1 << 5
 
 HASH_EMPTY = 0x8000000000000000
-ABI_VERSION = 3  # must equal ldm_abi_version() of the built library (descriptor struct layouts)
+ABI_VERSION = 4  # must equal ldm_abi_version() of the built library (descriptor struct layouts)
 
 
 class GemmDesc(C.Structure):
@@ -78,6 +78,7 @@ SIGNATURES = {
     "ldm_conv_out": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "ldm_ddim_step": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "ldm_ddim_step_cfg": (C.c_int, [c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "ldm_ddim_step_clip": (C.c_int, [c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_i32, c_vp]),
     "ldm_upsample_nearest": (C.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "ldm_im2col3x3_s2": (C.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "ldm_logits_to_ids": (C.c_int, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_i32, c_vp]),

@@ -14,7 +14,10 @@ using namespace ldm;
 // eps = eps_uncond + g * (eps_text - eps_uncond), three roundings in the reference's order.
 __global__ void ddim_step_kernel(const float* __restrict__ eps, const float* __restrict__ eps_text, float guidance,
                                  const float* sample, const float* __restrict__ coef,
-                                 const int32_t* __restrict__ t_index, float* prev, float* x0out, long long n) {
+                                 const int32_t* __restrict__ t_index, float* prev, float* x0out, long long n,
+                                 float clip, int reclip_eps) {
+  // clip > 0: pred_original_sample is clamped to [-clip, clip] (clip_sample, :253-257); reclip_eps: the noise is then
+  // re-derived from the clamped x0 (use_clipped_model_output, :259-261), both in the reference's op order
   const int ti = t_index ? *t_index : 0;
   const float s1m_at = coef[ti * 4 + 0];   // sqrt(1 - alpha_t)
   const float s_at = coef[ti * 4 + 1];     // sqrt(alpha_t)
@@ -36,6 +39,8 @@ __global__ void ddim_step_kernel(const float* __restrict__ eps, const float* __r
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       p0[j] = __fdiv_rn(__fsub_rn(xv[j], __fmul_rn(s1m_at, ev[j])), s_at);
+      if (clip > 0.f) p0[j] = fminf(fmaxf(p0[j], -clip), clip);
+      if (reclip_eps) ev[j] = __fdiv_rn(__fsub_rn(xv[j], __fmul_rn(s_at, p0[j])), s1m_at);
       pv[j] = __fadd_rn(__fmul_rn(s_ap, p0[j]), __fmul_rn(s1m_ap, ev[j]));
     }
     if (prev) reinterpret_cast<float4*>(prev)[i] = make_float4(pv[0], pv[1], pv[2], pv[3]);
@@ -46,7 +51,9 @@ __global__ void ddim_step_kernel(const float* __restrict__ eps, const float* __r
        i += (long long)gridDim.x * blockDim.x) {
     float e = eps[i];
     if (eps_text) e = __fadd_rn(e, __fmul_rn(guidance, __fsub_rn(eps_text[i], e)));
-    const float p0 = __fdiv_rn(__fsub_rn(sample[i], __fmul_rn(s1m_at, e)), s_at);
+    float p0 = __fdiv_rn(__fsub_rn(sample[i], __fmul_rn(s1m_at, e)), s_at);
+    if (clip > 0.f) p0 = fminf(fmaxf(p0, -clip), clip);
+    if (reclip_eps) e = __fdiv_rn(__fsub_rn(sample[i], __fmul_rn(s_at, p0)), s1m_at);
     if (prev) prev[i] = __fadd_rn(__fmul_rn(s_ap, p0), __fmul_rn(s1m_ap, e));
     if (x0out) x0out[i] = p0;
   }
@@ -258,20 +265,32 @@ int grid_for(long long work_items, int threads) {
 
 extern "C" int ldm_ddim_step(const float* eps, const float* sample, const float* coef, const int32_t* t_index,
                              float* prev_sample, float* pred_x0, int64_t n, ldm_stream_t stream) {
-  return ldm_ddim_step_cfg(eps, nullptr, 0.f, sample, coef, t_index, prev_sample, pred_x0, n, stream);
+  return ldm_ddim_step_clip(eps, nullptr, 0.f, sample, coef, t_index, prev_sample, pred_x0, n, 0.f, 0, stream);
 }
 
 extern "C" int ldm_ddim_step_cfg(const float* eps_uncond, const float* eps_text, float guidance_scale,
                                  const float* sample, const float* coef, const int32_t* t_index, float* prev_sample,
                                  float* pred_x0, int64_t n, ldm_stream_t stream) {
+  return ldm_ddim_step_clip(eps_uncond, eps_text, guidance_scale, sample, coef, t_index, prev_sample, pred_x0, n, 0.f, 0,
+                            stream);
+}
+
+extern "C" int ldm_ddim_step_clip(const float* eps_uncond, const float* eps_text, float guidance_scale,
+                                  const float* sample, const float* coef, const int32_t* t_index, float* prev_sample,
+                                  float* pred_x0, int64_t n, float clip_sample_range, int32_t use_clipped_model_output,
+                                  ldm_stream_t stream) {
   using namespace ldm_host;
+  LDM_REQUIRE(clip_sample_range >= 0.f, LDM_ERR_BAD_ARG, "ldm_ddim_step: clip_sample_range=%g (0 = no clipping)",
+              (double)clip_sample_range);
   LDM_REQUIRE(eps_uncond && sample && coef, LDM_ERR_BAD_ARG, "ldm_ddim_step: null arg");
   LDM_REQUIRE(n > 0, LDM_ERR_BAD_SHAPE, "ldm_ddim_step: n=%lld", (long long)n);
   LDM_REQUIRE(((uintptr_t)eps_uncond | (uintptr_t)eps_text | (uintptr_t)sample | (uintptr_t)prev_sample |
                (uintptr_t)pred_x0) % 16 == 0,
               LDM_ERR_ALIGNMENT, "ldm_ddim_step: pointers must be 16-byte aligned");
   ddim_step_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, as_stream(stream)>>>(eps_uncond, eps_text, guidance_scale, sample,
-                                                                            coef, t_index, prev_sample, pred_x0, n);
+                                                                            coef, t_index, prev_sample, pred_x0, n,
+                                                                            clip_sample_range,
+                                                                            use_clipped_model_output != 0);
   count_launch();
   return check_launch("ddim_step_kernel");
 }

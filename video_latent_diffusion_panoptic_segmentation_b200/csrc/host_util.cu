@@ -105,7 +105,7 @@ long long launches();
 
 extern "C" {
 
-int ldm_abi_version(void) { return 3; }  // 3: ldm_gemm_desc.splitk_ws; 2: ldm_gemm_desc.qkv_part0, ldm_attn_desc.kv_seq
+int ldm_abi_version(void) { return 4; }  // 4: ldm_gemm_desc.row_stats_out / ln_stats (LayerNorm fold); 3: ldm_gemm_desc.splitk_ws; 2: ldm_gemm_desc.qkv_part0, ldm_attn_desc.kv_seq
 const char* ldm_last_error(void) { return ldm_host::last_error(); }
 long long ldm_launch_count(void) { return ldm_host::launches(); }
 

@@ -101,19 +101,26 @@ class DDIMNoiseScheduler(object):
         prev_t = t - num_train_timesteps // num_inference_steps, built with the reference's own fp32 tensor ops
         (:231-236,240,264,267)."""
         ratio = self.num_train_timesteps // self.num_inference_steps
-        rows = []
-        for t in range(self.num_train_timesteps):
-            prev_t = t - ratio
-            a_t = self.alphas_cumprod[t]
-            a_prev = self.alphas_cumprod[prev_t] if prev_t >= 0 else self.final_alpha_cumprod
-            rows.append(torch.stack([(1 - a_t) ** 0.5, a_t ** 0.5, a_prev ** 0.5, (1 - a_prev) ** 0.5]))
-        return torch.stack(rows).to(torch.float32).contiguous()
+        a_t = self.alphas_cumprod.to(torch.float32)
+        # alphas_cumprod[t - ratio], final_alpha_cumprod where t - ratio < 0: one vectorised pass (the element-wise fp32
+        # ops are the ones the reference applies to 0-dim tensors: same bits, checked in tests/test_host_cpu.py)
+        a_prev = torch.cat([self.final_alpha_cumprod.to(torch.float32).reshape(1).expand(min(ratio, a_t.numel())),
+                            a_t[:max(a_t.numel() - ratio, 0)]])
+        return torch.stack([(1 - a_t) ** 0.5, a_t ** 0.5, a_prev ** 0.5, (1 - a_prev) ** 0.5], dim=1).contiguous()
 
     def coef_table(self, device) -> torch.Tensor:
         device = torch.device(device)
         if device not in self._coef_dev:
             self._coef_dev[device] = self.step_coefficients().to(device)
         return self._coef_dev[device]
+
+    def clip_range(self) -> float:
+        """clip_sample_range when clip_sample is on (:253-257), else 0 (= no clipping for ldm_ddim_step_clip)."""
+        if not self.clip_sample:
+            return 0.0
+        if not self.clip_sample_range > 0:
+            raise L.LdmError(f"clip_sample needs clip_sample_range > 0, got {self.clip_sample_range}")
+        return float(self.clip_sample_range)
 
     # ------------------------------------------------------------------ step (:218-269)
     def step(self, model_output: torch.Tensor, timestep, sample: torch.Tensor,
@@ -122,8 +129,6 @@ class DDIMNoiseScheduler(object):
             raise NotImplementedError("only prediction_type='epsilon' is built (base.yaml:49)")
         if self.thresholding:
             raise NotImplementedError
-        if self.clip_sample or use_clipped_model_output:
-            raise NotImplementedError("clip_sample / use_clipped_model_output are off on this path (base.yaml:55)")
         if not (model_output.is_cuda and sample.is_cuda):
             raise L.LdmError("DDIMNoiseScheduler.step needs CUDA tensors: there is no CPU fallback")
         dev = sample.device
@@ -136,7 +141,8 @@ class DDIMNoiseScheduler(object):
         eps = model_output.contiguous().float()
         x = sample.contiguous().float()
         prev, x0 = torch.empty_like(x), torch.empty_like(x)
-        ops.ddim_step(eps, x, coef, t_index, prev, x0)
+        ops.ddim_step(eps, x, coef, t_index, prev, x0, clip_sample_range=self.clip_range(),
+                      use_clipped_model_output=use_clipped_model_output)
         return DDIMNoiseSchedulerOutput(prev_sample=prev, pred_original_sample=x0)
 
     # ------------------------------------------------------------------ training-side helpers (:155-216), plain tensor math

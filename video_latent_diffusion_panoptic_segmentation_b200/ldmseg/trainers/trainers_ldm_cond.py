@@ -192,6 +192,7 @@ class TrainerDiffusion:
             unet.set_context(plan, ctx if uncond is None else torch.cat([uncond, ctx]))   # (:1120)
         timesteps = scheduler.timesteps.to(dev)
         coef = scheduler.coef_table(dev)
+        clip = scheduler.clip_range()  # scheduler.step's clip_sample (:1152-1154 calls it with its defaults)
         all_latents = []
         n = timesteps.numel()
         for i in range(n):
@@ -210,7 +211,8 @@ class TrainerDiffusion:
             ops.ddim_step(plan.out[:B], latents, coef, t_index,
                           prev_sample=None if last else latents,
                           pred_x0=latents if last else (st["cond"] if self.self_condition else None),
-                          eps_text=plan.out[B:] if multiplier > 1 else None, guidance_scale=guidance_scale)
+                          eps_text=plan.out[B:] if multiplier > 1 else None, guidance_scale=guidance_scale,
+                          clip_sample_range=clip)
             if return_all_latents:
                 all_latents.append(latents.clone())
         if return_all_latents:

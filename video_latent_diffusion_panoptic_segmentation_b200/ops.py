@@ -246,14 +246,17 @@ def conv_out(x, w, bias, out):
     return out
 
 
-def ddim_step(eps, sample, coef, t_index, prev_sample=None, pred_x0=None, eps_text=None, guidance_scale=0.0):
-    """eps_text given: eps <- eps + guidance_scale * (eps_text - eps) first (classifier-free guidance)."""
+def ddim_step(eps, sample, coef, t_index, prev_sample=None, pred_x0=None, eps_text=None, guidance_scale=0.0,
+              clip_sample_range=0.0, use_clipped_model_output=False):
+    """eps_text given: eps <- eps + guidance_scale * (eps_text - eps) first (classifier-free guidance).
+    clip_sample_range > 0: x0 clamped to +-range; use_clipped_model_output: eps re-derived from the clamped x0."""
     for t, n in ((eps, "eps"), (sample, "sample"), (coef, "coef"), (prev_sample, "prev"), (pred_x0, "x0"),
                  (eps_text, "eps_text")):
         _chk(t, f32, n)
     _chk(t_index, i32, "t_index")
-    L.check(L.lib().ldm_ddim_step_cfg(_p(eps), _p(eps_text), float(guidance_scale), _p(sample), _p(coef), _p(t_index),
-                                      _p(prev_sample), _p(pred_x0), sample.numel(), _stream()), "ldm_ddim_step_cfg")
+    L.check(L.lib().ldm_ddim_step_clip(_p(eps), _p(eps_text), float(guidance_scale), _p(sample), _p(coef), _p(t_index),
+                                       _p(prev_sample), _p(pred_x0), sample.numel(), float(clip_sample_range),
+                                       int(bool(use_clipped_model_output)), _stream()), "ldm_ddim_step_clip")
 
 
 def upsample_nearest(x, out):
