@@ -391,6 +391,7 @@ def run_config(name, args, env):
                                    "the same kernels: bit-identical ids). In the strong-scaling configs the batch per GPU "
                                    "changes with N, and with it the tiling (block_n, split-K, GroupNorm slices) and the "
                                    "fp32 summation order: ids then agree up to bf16 rounding flips, see pq / dvpq"},
+            # nominal FLOPs of the reference's operators per frame; roofline.achieved counts EXECUTED ones
             "whole_job_frac_of_tensor_peak": fps / world * (T * work["unet_step"] + work["ae"]) / (tf_sus * 1e12)}
 
     if rank == 0:

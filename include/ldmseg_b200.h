@@ -115,6 +115,21 @@ typedef struct ldm_gemm_desc {
   const float* ln_colsum;
   float ln_fold_eps;
   int32_t ln_parts;
+  /* Strided and sub-pixel convolutions without a gather pass: the tensor maps carry element strides of 2 in the pixel
+     dimensions, so the TMA unit reads / writes every other pixel (tools/microbench/tma_stride_test.cu).
+     a_stride = 2 (taps = 9): Conv2d(3x3, stride 2) -- diffusers Downsample2D. B, H, W are the OUTPUT
+       extents, a1 (and a2) are [B, a_H, a_W, c]; output pixel (y, x) reads input (2y + ky - a_pad, 2x + kx - a_pad), zero
+       outside (a_pad = 1: padding 1; a_pad = 0: F.pad(x, (0, 1, 0, 1)) + padding 0). a_stride = 0 / 1: dense.
+     up2 = 1 (taps = 4, N = 4 * cout): F.interpolate(scale 2, nearest) followed by Conv2d(3x3, padding 1) -- diffusers
+       Upsample2D -- as four 2x2 convolutions of the LOW-resolution input, one per output parity class
+       cls = 2 * (row & 1) + (col & 1): 4/9 of the multiply-adds and no up-sampled copy. w rows [cls * cout, (cls + 1) *
+       cout) hold that class's kernel, tap (i, j) = 2 i + j reads input (y + i - 1 + (cls >> 1), x + j - 1 + (cls & 1));
+       bias is [4 * cout] (the conv bias four times). B, H, W are the INPUT extents, out is the dense
+       [B, out_H, out_W, cout] tensor with out_H = 2H, out_W = 2W exactly. (The nearest resize to an ODD size that
+       diffusers does for a skip connection -- 20 -> 39 columns -- keeps the gather pass: its last column sees the zero
+       padding where the collapsed kernel would see a pixel.) Plain bf16 epilogue only (bias, SiLU). */
+  int32_t a_stride, a_pad, a_H, a_W;
+  int32_t up2, out_H, out_W;
 } ldm_gemm_desc;
 
 int ldm_gemm_bf16(const ldm_gemm_desc* d, ldm_stream_t stream);

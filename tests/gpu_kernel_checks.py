@@ -315,6 +315,52 @@ def check_gemm_conv3x3(B=2, H=12, W=39, c1=128, c2=0, N=192, block_n=0):
     return _stats(out, ref, f"conv3x3 B={B} {H}x{W} c1={c1} c2={c2} N={N}", 5e-2, 2e-2)
 
 
+def check_gemm_conv3x3_stride2(B=2, H=24, W=78, c1=128, N=192, pad=1, silu=False):
+    """Conv2d(3x3, stride 2) as an implicit GEMM through element-strided tensor maps (ldm_gemm_desc.a_stride), padding 1
+    (diffusers Downsample2D of the UNet, the seg-AE encoder) and F.pad(0, 1, 0, 1) + padding 0 (the RGB VAE's)."""
+    x = _randn((B, H, W, c1), 136, 1.0, bf16)
+    wt = _randn((N, c1, 3, 3), 138, 0.03)
+    wp = wt.permute(0, 2, 3, 1).reshape(N, 9 * c1).contiguous().to(bf16)
+    bias = _randn((N,), 139)
+    xin = x.float().permute(0, 3, 1, 2)
+    if pad == 0:
+        xin = F.pad(xin, (0, 1, 0, 1))
+    ref = F.conv2d(xin, wp.float().view(N, 3, 3, c1).permute(0, 3, 1, 2), bias, stride=2, padding=pad)
+    if silu:
+        ref = F.silu(ref)
+    oh, ow = ref.shape[-2:]
+    out = _empty((B, oh, ow, N), dtype=bf16, device=DEV)
+    ops.gemm(x, wp, out, taps=9, bias=bias, a_stride=2, a_pad=pad, flags=L.LDM_GEMM_SILU if silu else 0)
+    return _stats(out, ref.permute(0, 2, 3, 1), f"conv3x3 stride 2 pad={pad} B={B} {H}x{W} -> {oh}x{ow} c={c1} N={N}",
+                  5e-2, 2e-2)
+
+
+def check_gemm_upsample_conv3x3(B=2, H=12, W=39, C=128, N=128):
+    """F.interpolate(scale 2, nearest) + Conv2d(3x3, padding 1) as four 2x2 convolutions of the low-resolution input
+    written through an element-strided output map (ldm_gemm_desc.up2). Reference: the two torch ops on the bf16 input
+    with the ORIGINAL 3x3 weights rounded to bf16 (what the gather-pass path computes)."""
+    x = _randn((B, H, W, C), 146, 1.0, bf16)
+    wt = _randn((N, 3, 3, C), 148, 0.03)
+    bias = _randn((N,), 149)
+    w4, b4 = ops.fold_upsample_conv3x3(wt, bias)
+    out = _empty((B, 2 * H, 2 * W, N), dtype=bf16, device=DEV)
+    ops.gemm(x, w4, out, taps=4, bias=b4, up2=True)
+    up = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
+    ref = F.conv2d(up, wt.to(bf16).float().permute(0, 3, 1, 2), bias, padding=1).permute(0, 2, 3, 1)
+    # and the path it replaces, on the same inputs: the collapsed kernel must not be further from fp32 than it is
+    upb = _empty((B, 2 * H, 2 * W, C), dtype=bf16, device=DEV)
+    ops.upsample_nearest(x, upb)
+    out2 = _empty((B, 2 * H, 2 * W, N), dtype=bf16, device=DEV)
+    ops.gemm(upb, wt.reshape(N, 9 * C).to(bf16).contiguous(), out2, taps=9, bias=bias)
+    ref32 = F.conv2d(up, wt.permute(0, 3, 1, 2), bias, padding=1).permute(0, 2, 3, 1)
+    rel = lambda o: ((o.float() - ref32).pow(2).sum().sqrt() / ref32.pow(2).sum().sqrt()).item()
+    assert rel(out) <= 1.5 * rel(out2) + 1e-3, f"up2 rel L2 {rel(out):.2e} vs gather path {rel(out2):.2e}"
+    r = _stats(out, ref, f"upsample x2 + conv3x3 B={B} {H}x{W} C={C} N={N}", 6e-2, 2e-2)
+    r["rel_l2_gather_path"] = rel(out2)
+    r["rel_l2_fp32_weights"] = rel(out)
+    return r
+
+
 def check_gemm_splitk(B=1, H=6, W=20, c1=1280, c2=0, N=1280, taps=9, residual=True, rowbias=True):
     """Long K, few tiles: the K range of every tile is cut into work items (ldm_gemm_desc.splitk_ws); the partials are
     added in slice order by a second small launch, so repeated launches are bit-identical."""
@@ -705,6 +751,14 @@ CHECKS = {
     "gemm_conv3x3_L0": lambda: check_gemm_conv3x3(1, 48, 156, 320, 0, 320),
     "gemm_conv3x3_L3": lambda: check_gemm_conv3x3(3, 6, 20, 256, 0, 256),
     "gemm_concat_1x1": check_gemm_concat_1x1,
+    "gemm_conv3x3_stride2": check_gemm_conv3x3_stride2,
+    "gemm_conv3x3_stride2_odd": lambda: check_gemm_conv3x3_stride2(2, 12, 39, 256, 256),
+    "gemm_conv3x3_stride2_L0": lambda: check_gemm_conv3x3_stride2(1, 48, 156, 320, 320),
+    "gemm_conv3x3_stride2_pad0_silu": lambda: check_gemm_conv3x3_stride2(2, 32, 64, 128, 128, pad=0, silu=True),
+    "gemm_conv3x3_stride2_pad0_odd": lambda: check_gemm_conv3x3_stride2(1, 13, 21, 64, 64, pad=0),
+    "gemm_upsample_conv3x3": check_gemm_upsample_conv3x3,
+    "gemm_upsample_conv3x3_L1": lambda: check_gemm_upsample_conv3x3(2, 24, 78, 640, 640),
+    "gemm_upsample_conv3x3_L2_1280": lambda: check_gemm_upsample_conv3x3(1, 12, 39, 1280, 1280),
     "gemm_splitk_conv_L3_b1": check_gemm_splitk,
     "gemm_splitk_conv_L3_b8": lambda: check_gemm_splitk(8),
     "gemm_splitk_conv_L3_cat_b2": lambda: check_gemm_splitk(2, c1=1280, c2=1280, rowbias=False),

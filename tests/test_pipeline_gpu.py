@@ -651,8 +651,18 @@ def test_resized_cropped_tail_vs_reference_chain(models):
         pred, cl, _ = LO.logits_to_panoptic(img, 0.3, 64, 0.2, 127)
         ids, cleaned, _ = got[b]
         assert tuple(ids.shape[-2:]) == im_sizes[b]
-        mism = float((ids[0].cpu().numpy() != pred).mean())
+        diff = ids[0].cpu().numpy() != pred
+        mism = float(diff.mean())
         assert mism < 2e-3, f"image {b}: {mism:.4%} of the ids differ from the reference chain"
+        # The integer part is exact wherever the floats decide: an id may only flip where the reference's own logits are
+        # a near-tie -- top-2 logit gap or distance of the max probability to mask_th below 1e-3 (the three chained
+        # resamplings agree with torch's to ~1e-6 relative; which of two equal-to-the-last-bit candidates wins is not
+        # a property of the algorithm).
+        top2 = img.topk(2, dim=0).values
+        gap = (top2[0] - top2[1]).numpy()
+        pmax = F.softmax(img, dim=0).max(dim=0)[0].numpy()
+        near = (gap < 1e-3) | (np.abs(pmax - 0.3) < 1e-3)
+        assert not (diff & ~near).any(), f"image {b}: {(diff & ~near).sum()} ids differ away from any tie"
         mism_c = float((cleaned[0].cpu().numpy() != cl).mean())
         assert mism_c < 1e-2, f"image {b}: {mism_c:.4%} of the merged ids differ"
 

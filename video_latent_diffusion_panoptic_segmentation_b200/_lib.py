@@ -33,6 +33,8 @@ class GemmDesc(C.Structure):
         ("vt_rows", c_i32), ("n_store", c_i32), ("qkv_part0", c_i32),
         ("identity", c_vp), ("splitk_ws", c_vp), ("splitk_ws_bytes", C.c_int64),
         ("row_stats_out", c_vp), ("ln_stats", c_vp), ("ln_colsum", c_vp), ("ln_fold_eps", c_f32), ("ln_parts", c_i32),
+        ("a_stride", c_i32), ("a_pad", c_i32), ("a_H", c_i32), ("a_W", c_i32),
+        ("up2", c_i32), ("out_H", c_i32), ("out_W", c_i32),
     ]
 
 

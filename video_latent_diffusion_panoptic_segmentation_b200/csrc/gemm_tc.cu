@@ -234,12 +234,18 @@ extern "C" int ldm_gemm_bf16(const ldm_gemm_desc* d, ldm_stream_t stream) {
   using namespace ldm_host;
   LDM_REQUIRE(d != nullptr, LDM_ERR_BAD_ARG, "ldm_gemm_bf16: null descriptor");
   LDM_REQUIRE(d->a1 && d->w, LDM_ERR_BAD_ARG, "ldm_gemm_bf16: null a1/w");
-  LDM_REQUIRE(d->taps == 1 || d->taps == 9, LDM_ERR_BAD_ARG, "ldm_gemm_bf16: taps must be 1 or 9 (got %d)", d->taps);
+  const bool up2 = d->up2 != 0;
+  const int a_stride = d->a_stride > 1 ? d->a_stride : 1;
+  LDM_REQUIRE(d->taps == 1 || d->taps == 9 || (d->taps == 4 && up2), LDM_ERR_BAD_ARG,
+              "ldm_gemm_bf16: taps must be 1 or 9, or 4 with up2 (got %d)", d->taps);
+  LDM_REQUIRE(!up2 || (d->taps == 4 && a_stride == 1), LDM_ERR_BAD_ARG, "ldm_gemm_bf16: up2 needs taps = 4 and a dense A");
+  LDM_REQUIRE(a_stride == 1 || (a_stride == 2 && d->taps == 9 && (d->a_pad == 0 || d->a_pad == 1) && d->a_H > 0 && d->a_W > 0),
+              LDM_ERR_BAD_ARG, "ldm_gemm_bf16: a_stride = 2 needs taps = 9, a_pad in {0, 1} and the input extents a_H, a_W");
   LDM_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0 && d->N > 0 && d->c1 > 0, LDM_ERR_BAD_SHAPE,
               "ldm_gemm_bf16: non-positive extent B=%d H=%d W=%d N=%d c1=%d", d->B, d->H, d->W, d->N, d->c1);
   const int c2 = d->a2 ? d->c2 : 0;
   LDM_REQUIRE(d->c1 % 8 == 0 && c2 % 8 == 0, LDM_ERR_ALIGNMENT, "ldm_gemm_bf16: channels must be multiples of 8");
-  if (d->taps == 9 || d->a2)
+  if (d->taps != 1 || d->a2)
     LDM_REQUIRE(d->c1 % 64 == 0 && c2 % 64 == 0, LDM_ERR_BAD_SHAPE,
                 "ldm_gemm_bf16: conv3x3 / concat sources need channels %% 64 == 0 (c1=%d c2=%d)", d->c1, c2);
   const int flags = d->flags;
@@ -264,7 +270,7 @@ extern "C" int ldm_gemm_bf16(const ldm_gemm_desc* d, ldm_stream_t stream) {
   const long kblocks_total = (long)d->taps * p.kblocks;
   double cost1 = 0.0, cost2 = 0.0;
   // split-K needs the caller's workspace and the plain bf16 [rows, N] epilogue (checked again below)
-  const bool split_ok = d->splitk_ws && d->splitk_ws_bytes > 0 && d->block_n <= 0 && !d->row_stats_out &&
+  const bool split_ok = d->splitk_ws && d->splitk_ws_bytes > 0 && d->block_n <= 0 && !d->row_stats_out && !up2 &&
                         !(flags & (LDM_GEMM_OUT_F32 | LDM_GEMM_OUT_NCHW_F32 | LDM_GEMM_QKV_SPLIT |
                                    LDM_GEMM_CONVT_LN_SILU | LDM_GEMM_GEGLU)) &&
                         d->N >= 64 && d->N % 8 == 0 && staged_enabled() && splitk_enabled() &&
@@ -297,6 +303,23 @@ extern "C" int ldm_gemm_bf16(const ldm_gemm_desc* d, ldm_stream_t stream) {
   int block_n = d->block_n > 0 ? d->block_n : (qkv_tma ? 160 : (pair ? bn2 : bn1));
   int split_k = d->block_n > 0 || qkv_tma ? 1 : (pair ? sp2 : sp1);
   if ((flags & LDM_GEMM_GEGLU) && d->block_n <= 0 && block_n < 128) block_n = 128;  // staged GEGLU blocks span 128 columns
+  int up2_cout = 0;
+  if (up2) {
+    // an N tile lies inside one parity class: block_n must divide cout (the widest that does, at most the model's choice)
+    LDM_REQUIRE(d->N % 4 == 0 && (d->N / 4) % 64 == 0 && d->out_H == 2 * d->H && d->out_W == 2 * d->W && !d->residual &&
+                    !d->rowbias && !d->row_stats_out && !d->a2 &&
+                    !(flags & ~(LDM_GEMM_SILU)),
+                LDM_ERR_BAD_ARG, "ldm_gemm_bf16: up2 needs N = 4 * cout (cout %% 64 == 0), out_H = 2H, out_W = 2W, "
+                "one source and the plain bf16 epilogue");
+    up2_cout = d->N / 4;
+    if (d->block_n <= 0) {
+      int bn = block_n;
+      while (bn > 64 && up2_cout % bn != 0) bn -= 32;
+      block_n = bn;
+    }
+    LDM_REQUIRE(up2_cout % block_n == 0 && block_n >= 64, LDM_ERR_BAD_ARG, "ldm_gemm_bf16: up2 block_n=%d does not divide cout=%d",
+                block_n, up2_cout);
+  }
   LDM_REQUIRE(block_n % 32 == 0 && block_n >= 32 && block_n <= 256, LDM_ERR_BAD_ARG, "ldm_gemm_bf16: block_n=%d",
               block_n);
   if (flags & LDM_GEMM_GEGLU) LDM_REQUIRE(d->N % 32 == 0, LDM_ERR_BAD_SHAPE, "GEGLU needs N %% 32 == 0");
@@ -384,22 +407,37 @@ extern "C" int ldm_gemm_bf16(const ldm_gemm_desc* d, ldm_stream_t stream) {
   p.rows_total = (long long)d->B * d->H * d->W;
   p.ln_invc = 1.0f / (float)d->c1;
   p.ln_fold_eps = d->ln_fold_eps;
+  p.a_stride = a_stride;
+  p.a_pad = a_stride == 2 ? d->a_pad : 1;
+  p.up2_cout = up2_cout;
+  p.up2_ntiles = up2 ? up2_cout / block_n : 0;
+  if (up2) LDM_REQUIRE(staged && split_k == 1, LDM_ERR_BAD_SHAPE, "ldm_gemm_bf16: up2 needs the staged epilogue");
   p.n_store = d->n_store > 0 ? d->n_store : d->N;
   p.img_px = (long long)d->H * d->W;
 
   CUtensorMap tmA1, tmA2, tmB;
+  // A: [B, aH, aW, c] with boxes of bw x bh pixels; stride 2: every other pixel of a (2 bw) x (2 bh) window
+  const uint64_t aW = a_stride == 2 ? (uint64_t)d->a_W : (uint64_t)p.W, aH = a_stride == 2 ? (uint64_t)d->a_H : (uint64_t)p.H;
+  const uint32_t a_es[4] = {1, (uint32_t)a_stride, (uint32_t)a_stride, 1};
+  if (a_stride == 2) {
+    // padding 1 on both sides, or (a_pad = 0) one zero row / column on the high side only
+    const long long pad_total = d->a_pad == 1 ? 2 : 1;
+    LDM_REQUIRE(((long long)aH + pad_total - 3) / 2 + 1 == d->H && ((long long)aW + pad_total - 3) / 2 + 1 == d->W,
+                LDM_ERR_BAD_SHAPE, "ldm_gemm_bf16: stride-2 extents: input %llux%llu with a_pad=%d does not give %dx%d",
+                (unsigned long long)aH, (unsigned long long)aW, d->a_pad, d->H, d->W);
+  }
   {
-    const uint64_t dims[4] = {(uint64_t)d->c1, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.B};
-    const uint64_t str[3] = {(uint64_t)d->c1 * 2, (uint64_t)d->c1 * 2 * p.W, (uint64_t)d->c1 * 2 * p.W * p.H};
-    const uint32_t box[4] = {kBlockK, (uint32_t)p.bw, (uint32_t)p.bh, 1};
-    int rc = make_tmap(&tmA1, d->a1, 4, dims, str, box, 2, true);
+    const uint64_t dims[4] = {(uint64_t)d->c1, aW, aH, (uint64_t)p.B};
+    const uint64_t str[3] = {(uint64_t)d->c1 * 2, (uint64_t)d->c1 * 2 * aW, (uint64_t)d->c1 * 2 * aW * aH};
+    const uint32_t box[4] = {kBlockK, (uint32_t)(p.bw * a_stride), (uint32_t)(p.bh * a_stride), 1};
+    int rc = make_tmap(&tmA1, d->a1, 4, dims, str, box, 2, true, a_es);
     if (rc) return rc;
   }
   if (c2 > 0) {
-    const uint64_t dims[4] = {(uint64_t)c2, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.B};
-    const uint64_t str[3] = {(uint64_t)c2 * 2, (uint64_t)c2 * 2 * p.W, (uint64_t)c2 * 2 * p.W * p.H};
-    const uint32_t box[4] = {kBlockK, (uint32_t)p.bw, (uint32_t)p.bh, 1};
-    int rc = make_tmap(&tmA2, d->a2, 4, dims, str, box, 2, true);
+    const uint64_t dims[4] = {(uint64_t)c2, aW, aH, (uint64_t)p.B};
+    const uint64_t str[3] = {(uint64_t)c2 * 2, (uint64_t)c2 * 2 * aW, (uint64_t)c2 * 2 * aW * aH};
+    const uint32_t box[4] = {kBlockK, (uint32_t)(p.bw * a_stride), (uint32_t)(p.bh * a_stride), 1};
+    int rc = make_tmap(&tmA2, d->a2, 4, dims, str, box, 2, true, a_es);
     if (rc) return rc;
   } else {
     tmA2 = tmA1;
@@ -414,7 +452,17 @@ extern "C" int ldm_gemm_bf16(const ldm_gemm_desc* d, ldm_stream_t stream) {
   }
 
   CUtensorMap tmO = tmB;
-  if (staged) {
+  if (staged && up2) {
+    // the dense [B, out_H, out_W, cout] output, written through a map that steps by two pixels: a tile's (y, x) lands on
+    // (2y + a, 2x + b)
+    const uint64_t dims[4] = {(uint64_t)up2_cout, (uint64_t)d->out_W, (uint64_t)d->out_H, (uint64_t)p.B};
+    const uint64_t str[3] = {(uint64_t)up2_cout * 2, (uint64_t)up2_cout * 2 * d->out_W,
+                             (uint64_t)up2_cout * 2 * d->out_W * d->out_H};
+    const uint32_t box[4] = {64, (uint32_t)(2 * p.bw), (uint32_t)(2 * p.bh), 1};
+    const uint32_t es[4] = {1, 2, 2, 1};
+    int rc = make_tmap(&tmO, d->out, 4, dims, str, box, 2, true, es);
+    if (rc) return rc;
+  } else if (staged) {
     const uint64_t dims[4] = {(uint64_t)n_out, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.B};
     const uint64_t str[3] = {(uint64_t)n_out * 2, (uint64_t)n_out * 2 * p.W, (uint64_t)n_out * 2 * p.W * p.H};
     const uint32_t box[4] = {64, (uint32_t)p.bw, (uint32_t)p.bh, 1};

@@ -46,6 +46,11 @@ struct GemmParams {
   int heads, head_dim, dpad, seq, seq_pad, vt_rows;
   int qkv_part0;    // QKV_SPLIT: first of the q|k|v parts the N columns hold (0: q.., 1: k.., 2: v only)
   unsigned long long magic_seq, magic_c, magic_d;  // ceil(2^40 / divisor): x / d == (x * magic) >> 40 for x * d < 2^40
+  // strided / sub-pixel convolutions (ldm_gemm_desc.a_stride, up2): element-strided tensor maps, no gather pass
+  int a_stride;     // 1, or 2: Conv2d(3x3, stride 2), the A boxes start at (2 x0 + kx - a_pad, 2 y0 + ky - a_pad)
+  int a_pad;        // taps == 9: tap (ky, kx) reads (y + ky - a_pad, x + kx - a_pad); 1 for the dense convolution
+  int up2_ntiles;   // > 0: nearest-upsample x2 + conv3x3 as four 2x2 convolutions; N tiles per output parity class
+  int up2_cout;     // output channels of one class
   int n_store;      // OUT_NCHW_F32: leading output channels actually stored
   long long img_px; // pixels per image of the un-flattened problem (H*W)
   // LayerNorm folded into the GEMMs around it (no normalisation pass, see ldm_gemm_desc.ln_stats):
@@ -182,9 +187,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         const int x0 = tx * p.bw, y0 = ty * p.bh;
         const int n0 = n_tile * p.block_n + (int)rank * b_rows;
         int tap = k_lo / p.kblocks, kb = k_lo - tap * p.kblocks;
+        // up2: output parity class of this N tile (row parity, column parity) shifts its 2x2 window
+        const int cls = p.up2_ntiles > 0 ? n_tile / p.up2_ntiles : 0;
+        const int ax0 = x0 * p.a_stride, ay0 = y0 * p.a_stride;
         for (int ki = k_lo; ki < k_hi; ++ki) {
-          const int dy = (p.taps == 9) ? tap / 3 - 1 : 0;
-          const int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
+          const int dy = (p.taps == 9) ? tap / 3 - p.a_pad : (p.taps == 4) ? (tap >> 1) - 1 + (cls >> 1) : 0;
+          const int dx = (p.taps == 9) ? tap % 3 - p.a_pad : (p.taps == 4) ? (tap & 1) - 1 + (cls & 1) : 0;
           {
             if (p.flags & kDbgNoWait) continue;
             mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -198,11 +206,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             } else if (kPair) {
               // the leader's barrier collects the bytes of both CTAs
               if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (a_bytes + b_bytes));
-              tma_load_4d_pair(sa, tmA, &full_bar[stage], kc, x0 + dx, y0 + dy, b);
+              tma_load_4d_pair(sa, tmA, &full_bar[stage], kc, ax0 + dx, ay0 + dy, b);
               tma_load_2d_pair(sb, &tmB, &full_bar[stage], tap * p.ktap + kb * kBlockK, n0);
             } else {
               mbar_arrive_expect_tx(&full_bar[stage], a_bytes + b_bytes);
-              tma_load_4d(sa, tmA, &full_bar[stage], kc, x0 + dx, y0 + dy, b);
+              tma_load_4d(sa, tmA, &full_bar[stage], kc, ax0 + dx, ay0 + dy, b);
               tma_load_2d(sb, &tmB, &full_bar[stage], tap * p.ktap + kb * kBlockK, n0);
             }
             if (++stage == p.stages) {
@@ -625,8 +633,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           fence_proxy_async_smem();
           named_bar_sync(1, 32 * kEpiWarps);
           if (epi_leader) {
-            const int ncol = geglu ? (n0 + c0) / 2 : n0 + c0;
-            tma_store_4d(&tmO, sbuf, ncol, tx * p.bw, ty * p.bh, b);
+            if (p.up2_ntiles > 0) {
+              // this tile's pixels (y, x) are the output pixels (2y + a, 2x + b) of its parity class: tmO steps by two
+              const int cls = n_tile / p.up2_ntiles;
+              tma_store_4d(&tmO, sbuf, n0 + c0 - cls * p.up2_cout, 2 * tx * p.bw + (cls & 1), 2 * ty * p.bh + (cls >> 1), b);
+            } else {
+              const int ncol = geglu ? (n0 + c0) / 2 : n0 + c0;
+              tma_store_4d(&tmO, sbuf, ncol, tx * p.bw, ty * p.bh, b);
+            }
             bulk_commit();
           }
           sb ^= 1;

@@ -71,7 +71,7 @@ static encode_tiled_fn get_encode() {
 }
 
 int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-              const uint32_t* box, int elem_bytes, bool swizzle128) {
+              const uint32_t* box, int elem_bytes, bool swizzle128, const uint32_t* elem_strides) {
   encode_tiled_fn enc = get_encode();
   if (!enc) return set_error(LDM_ERR_DRIVER, "cuTensorMapEncodeTiled entry point unavailable");
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0)
@@ -82,7 +82,7 @@ int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims
   for (int i = 0; i < rank; ++i) {
     gd[i] = dims[i];
     bx[i] = box[i];
-    es[i] = 1;
+    es[i] = elem_strides ? elem_strides[i] : 1;  // > 1: every es-th element; box[i] is then in traversal space
     if (box[i] == 0 || box[i] > 256) return set_error(LDM_ERR_BAD_SHAPE, "tensor map box[%d]=%u out of range", i, box[i]);
   }
   for (int i = 0; i + 1 < rank; ++i) {

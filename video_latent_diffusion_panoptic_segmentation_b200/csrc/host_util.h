@@ -16,9 +16,11 @@ void count_launch(int n = 1);
 int check_launch(const char* what);  // cudaGetLastError -> status
 
 // rank-`rank` bf16 (or other 2-byte / 4-byte) tiled tensor map. dims/box innermost first; strides in bytes for
-// dims 1..rank-1. swizzle128: inner box must span exactly 128 bytes.
+// dims 1..rank-1. swizzle128: inner box must span exactly 128 bytes. elem_strides (optional, per dim): s > 1 makes the
+// TMA unit touch every s-th element of that dimension, for loads and for stores; box[i] is then the extent in traversal
+// space (s * elements delivered) -- measured, tools/microbench/tma_stride_test.cu.
 int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-              const uint32_t* box, int elem_bytes, bool swizzle128);
+              const uint32_t* box, int elem_bytes, bool swizzle128, const uint32_t* elem_strides = nullptr);
 
 inline cudaStream_t as_stream(ldm_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 

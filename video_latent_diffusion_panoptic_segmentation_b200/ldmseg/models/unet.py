@@ -92,6 +92,9 @@ class UNet:
         # 0.54 ms of LayerNorm per forward but the QKV / GEGLU epilogues it lands in are issue-bound at K = 320 - 640
         # and pay 0.9 ms for it, so the default is the separate pass.
         self.ln_fold = False
+        # Upsample2D as four sub-pixel 2x2 convolutions (ldm_gemm_desc.up2) from this many low-resolution rows (B*H*W) on;
+        # below, the per-class GEMMs are too small and the nearest-upsample pass + one 3x3 convolution is faster
+        self.up2_min_rows = 1800
         self.training = False
 
     # ------------------------------------------------------------------ construction (main_ldm.py:147-169)
@@ -297,6 +300,9 @@ class UNet:
         for k in sd:
             if k.endswith("samplers.0.conv.weight"):
                 P[k[: -len(".weight")]] = conv3(k[: -len(".weight")])
+                if ".upsamplers." in k:  # nearest x2 + conv3x3 as four 2x2 convolutions (ldm_gemm_desc.up2)
+                    w4, b4 = ops.fold_upsample_conv3x3(sd[k].permute(0, 2, 3, 1), sd[k[: -len(".weight")] + ".bias"])
+                    P[k[: -len(".weight")] + ".up2"] = (dv(w4, bf16), dv(b4))
         self._packed = P
 
     # ------------------------------------------------------------------ plan
@@ -468,13 +474,12 @@ class UNet:
                 skips.append((x, H, W))
                 keep.add(id(x))
             if i < len(ch) - 1:
+                # Downsample2D: Conv2d(3x3, stride 2, padding 1) as an implicit GEMM -- the A tensor map steps by two
+                # pixels (ldm_gemm_desc.a_stride), no im2col buffer (it was 9x the input, written and read back)
                 oh, ow = (H - 1) // 2 + 1, (W - 1) // 2 + 1
-                col = arena.alloc((B * oh * ow, 9 * co))
-                add(ops.im2col3x3_s2, x, col)
                 y = arena.alloc((B, oh, ow, co))
                 wd_, bd_ = P[f"down_blocks.{i}.downsamplers.0.conv"]
-                add(ops.gemm, col, wd_, y.view(B * oh * ow, co), bias=bd_)
-                arena.release(col)
+                add(ops.gemm, x, wd_, y, taps=9, bias=bd_, a_stride=2, a_pad=1)
                 x, H, W = y, oh, ow
                 skips.append((x, H, W))
                 keep.add(id(x))
@@ -506,13 +511,21 @@ class UNet:
                     x = y
             if i < n_up:
                 oh, ow = skips[-1][1], skips[-1][2]
-                up = arena.alloc((B, oh, ow, x.shape[-1]))
-                add(ops.upsample_nearest, x, up)
-                arena.release(x)
-                y = arena.alloc((B, oh, ow, up.shape[-1]))
-                wu, bu = P[f"up_blocks.{i}.upsamplers.0.conv"]
-                add(ops.gemm, up, wu, y, taps=9, bias=bu)
-                arena.release(up)
+                cu = x.shape[-1]
+                y = arena.alloc((B, oh, ow, cu))
+                if (oh, ow) == (2 * H, 2 * W) and B * H * W >= self.up2_min_rows:
+                    # Upsample2D: the up-sampled copy is never made -- four 2x2 convolutions of the low-resolution map
+                    # (one per output parity), 4/9 of the multiply-adds, stored through a map that steps by two pixels
+                    wu4, bu4 = P[f"up_blocks.{i}.upsamplers.0.conv.up2"]
+                    add(ops.gemm, x, wu4, y, taps=4, bias=bu4, up2=True)
+                    arena.release(x)
+                else:  # odd target size (20 -> 39 columns), or too few rows to fill the SMs four times over
+                    up = arena.alloc((B, oh, ow, cu))
+                    add(ops.upsample_nearest, x, up)
+                    arena.release(x)
+                    wu, bu = P[f"up_blocks.{i}.upsamplers.0.conv"]
+                    add(ops.gemm, up, wu, y, taps=9, bias=bu)
+                    arena.release(up)
                 x, H, W = y, oh, ow
 
         # 6. conv_norm_out + SiLU + conv_out (unet.py:428-431) -> fp32 NCHW
@@ -601,6 +614,10 @@ class UNet:
             if fn is ops.gemm:
                 a1, w = a[0], a[1]
                 M = a1.numel() // a1.shape[-1]
+                if k.get("a_stride", 1) == 2:  # the GEMM's rows are the output pixels
+                    M = a[2].numel() // a[2].shape[-1]
+                # EXECUTED multiply-adds (up2: 4 classes x 4 taps on the low-resolution rows = 4/9 of the 3x3
+                # convolution of the up-sampled map it replaces)
                 rec["flops"] = 2 * M * w.shape[0] * w.shape[1]
                 rec["shape"] = (M, w.shape[0], w.shape[1], k.get("taps", 1))
                 rec["bytes"] = 2 * (a1.numel() + (k["a2"].numel() if k.get("a2") is not None else 0) + w.numel()

@@ -57,7 +57,7 @@ def _splitk_ws(device):
 
 
 def gemm(a1, w, out=None, *, a2=None, taps=1, bias=None, rowbias=None, residual=None, flags=0, block_n=0,
-         qkv=None, ln=None, n_store=0, row_stats=None, ln_fold=None):
+         qkv=None, ln=None, n_store=0, row_stats=None, ln_fold=None, a_stride=1, a_pad=1, up2=False):
     """out = epilogue(conv/gemm(a1 ++ a2, w)). a1/a2: [B,H,W,C] or [rows,C] bf16; w: [N, taps*(c1+c2)] bf16.
 
     qkv = dict(q=, k=, vt=, heads=, head_dim=, dpad=, seq=, seq_pad=[, part0=]) for LDM_GEMM_QKV_SPLIT (part0 and the
@@ -66,6 +66,9 @@ def gemm(a1, w, out=None, *, a2=None, taps=1, bias=None, rowbias=None, residual=
     LayerNorm fold (ldm_gemm_desc.ln_stats): row_stats = f32 [ceil(N/32), rows, 2] (part-major) written by the GEMM that produces x;
     ln_fold = (row_stats of x, colsum f32 [N], eps) on the QKV_SPLIT / GEGLU GEMM that consumes x with the folded
     weight / bias of fold_layernorm().
+    a_stride = 2 (taps = 9): Conv2d(3x3, stride 2) of a1 [B, Hin, Win, C] into out [B, oh, ow, N] (a_pad = 1: padding 1;
+    0: F.pad(0, 1, 0, 1) + padding 0), no im2col pass. up2 (taps = 4): nearest-upsample x2 + Conv2d(3x3, padding 1) of the
+    low-resolution a1 into out [B, oh, ow, N / 4] with the class weights / bias of fold_upsample_conv3x3().
     """
     _chk(a1, bf16, "a1"); _chk(a2, bf16, "a2"); _chk(w, bf16, "w"); _chk(bias, f32, "bias")
     _chk(rowbias, f32, "rowbias"); _chk(residual, bf16, "residual")
@@ -80,6 +83,15 @@ def gemm(a1, w, out=None, *, a2=None, taps=1, bias=None, rowbias=None, residual=
         d.identity = _p(_identity(a1.device))
     ws = _splitk_ws(a1.device)
     d.splitk_ws, d.splitk_ws_bytes = _p(ws), ws.numel()
+    if a_stride == 2:  # the GEMM's pixels are the OUTPUT pixels
+        if out is None or out.dim() != 4 or a1.dim() != 4:
+            raise L.LdmError("gemm: a_stride = 2 needs a1 [B, Hin, Win, C] and out [B, oh, ow, N]")
+        d.a_stride, d.a_pad, d.a_H, d.a_W = 2, a_pad, H, W
+        H, W = out.shape[1], out.shape[2]
+    if up2:            # the GEMM's pixels are the INPUT pixels; out is the dense up-sampled tensor
+        if out is None or out.dim() != 4 or a1.dim() != 4 or out.shape[-1] * 4 != w.shape[0]:
+            raise L.LdmError("gemm: up2 needs a1 [B, H, W, C], out [B, oh, ow, cout] and w [4 * cout, 4 * C]")
+        d.up2, d.out_H, d.out_W = 1, out.shape[1], out.shape[2]
     d.B, d.H, d.W, d.c1 = B, H, W, c1
     d.c2 = 0 if a2 is None else a2.shape[-1]
     d.N = w.shape[0]
@@ -129,6 +141,26 @@ def fold_layernorm(w, bias, gamma, beta):
     if bias is not None:
         b2 = b2 + bias.float()
     return w2.contiguous(), b2.contiguous(), w2.float().sum(dim=1).contiguous()
+
+
+def fold_upsample_conv3x3(w, bias):
+    """Weights of Conv2d(3x3, padding 1) behind F.interpolate(scale 2, nearest), for ldm_gemm_desc.up2. w: [N, 3, 3, C]
+    (or the packed [N, 9 * C], tap-major), bias f32 [N]. Output pixel (2y + a, 2x + b) only ever sees the input rows
+    {y - 1 + a, y + a} and columns {x - 1 + b, x + b}: its nine taps collapse onto a 2x2 kernel whose entries are sums of
+    the original ones (rows: a = 0 -> {k0, k1 + k2}, a = 1 -> {k0 + k1, k2}; columns likewise), summed in fp32 and rounded
+    to bf16 once. Returns (w' bf16 [4 * N, 4 * C], class-major rows, taps (i, j) = 2 i + j; bias' f32 [4 * N])."""
+    N = w.shape[0]
+    w = w.float().reshape(N, 3, 3, -1)
+    groups = {0: ([0], [1, 2]), 1: ([0, 1], [2])}
+    out = []
+    for a in (0, 1):
+        for b in (0, 1):
+            taps = []
+            for i in (0, 1):
+                for j in (0, 1):
+                    taps.append(sum(w[:, ky, kx] for ky in groups[a][i] for kx in groups[b][j]))
+            out.append(torch.stack(taps, dim=1).reshape(N, -1))
+    return torch.cat(out, 0).to(bf16).contiguous(), bias.float().repeat(4).contiguous()
 
 
 def gemm_last_config():
