@@ -12,7 +12,7 @@ up-sampling into the argmax kernel, so the 245 MB/frame full-resolution logits n
 ``encode(semseg)`` (vae.py:175-266, default topology: no resize_input / skip_encoder /
 mid blocks, gaussian parametrisation) runs the bit planes through
   conv3x3 in->c0 + SiLU (few-channel kernel)                              vae.py:191-195
-  [conv3x3 ci->ci ; conv3x3 stride 2 ci->ci+1 + SiLU] per level           vae.py:199-208  (implicit GEMM; im2col + GEMM)
+  [conv3x3 ci->ci ; conv3x3 stride 2 ci->ci+1 + SiLU] per level           vae.py:199-208  (implicit GEMMs; stride 2 = a_stride)
   conv3x3 c_last->int ; GroupNorm(eps 1e-6) + SiLU ; conv3x3 int->2*latent  vae.py:215-237
 and returns ``EncoderOutput(latent_dist=DiagonalGaussianDistribution)`` (vae.py:371-425). Channel counts below 64 are
 zero-padded to 64 in the packed weights (the tensor-core conv wants K blocks of 64 channels).
@@ -262,7 +262,6 @@ class GeneralVAESeg:
             for (_, _, cip, cop) in P["down"]:
                 oh, ow = (h - 1) // 2 + 1, (w - 1) // 2 + 1
                 bufs["lv"].append((torch.empty((B, h, w, cip), dtype=bf16, device=dev),
-                                   torch.empty((B * oh * ow, 9 * cip), dtype=bf16, device=dev),
                                    torch.empty((B, oh, ow, cop), dtype=bf16, device=dev)))
                 h, w = oh, ow
             bufs["mid"] = torch.empty((B, h, w, self.int_channels), dtype=bf16, device=dev)
@@ -271,10 +270,10 @@ class GeneralVAESeg:
             self._enc_bufs = {key: bufs}
         bufs = self._enc_bufs[key]
         x = ops.conv3x3_small_cin([x_in], P["in_w"], P["in_b"], bufs["x0"], silu=True)
-        for ((wa, ba), (wb, bb), cip, cop), (ta, col, tb) in zip(P["down"], bufs["lv"]):
+        for ((wa, ba), (wb, bb), cip, cop), (ta, tb) in zip(P["down"], bufs["lv"]):
             ops.gemm(x, wa, ta, taps=9, bias=ba)
-            ops.im2col3x3_s2(ta, col)
-            ops.gemm(col, wb, tb.view(col.shape[0], cop), bias=bb, flags=L.LDM_GEMM_SILU)
+            # Conv2d(3x3, stride 2, padding 1) + SiLU as an implicit GEMM (element-strided A map, no im2col buffer)
+            ops.gemm(ta, wb, tb, taps=9, bias=bb, flags=L.LDM_GEMM_SILU, a_stride=2, a_pad=1)
             x = tb
         ops.gemm(x, P["mid"][0], bufs["mid"], taps=9, bias=P["mid"][1])
         ops.groupnorm(bufs["mid"], *P["gn"], bufs["gn"], bufs["stats"], groups=self.norm_num_groups, eps=1e-6, silu=True)

@@ -10,7 +10,7 @@ Data flow (NHWC bf16 activations, fp32 accumulate):
   conv_in 3 -> 128 fused with an affine map of the image (``2 * images - 1`` of encode_inputs)    few-channel kernel
   4 x DownEncoderBlock2D: 2 x [GroupNorm(eps 1e-6)+SiLU, conv3x3, GroupNorm+SiLU, conv3x3 + shortcut]   implicit GEMM;
       the 1x1 shortcut and the residual add ride in the second conv's launch sequence like the UNet's resnets
-      Downsample2D(padding=0): F.pad(x, (0, 1, 0, 1)) + conv3x3 stride 2                         im2col (pad_lo 0) + GEMM
+      Downsample2D(padding=0): F.pad(x, (0, 1, 0, 1)) + conv3x3 stride 2                         implicit GEMM (a_stride 2)
   mid block: resnet, single-head attention over the 512 channels, resnet
       one 512-wide head does not fit the fused flash kernels (their O accumulator lives in TMEM: 512 fp32 columns =
       all of it), so it runs unfused per image: S = Q K^T (GEMM, fp32 out), row softmax, O = P V (GEMM against V^T,
@@ -196,13 +196,12 @@ class GeneralVAEImage:
                 x = y
             if i < len(boc) - 1:
                 oh, ow = (h - 2) // 2 + 1, (w - 2) // 2 + 1
-                col = arena.alloc((B * oh * ow, 9 * co))
-                add(ops.im2col3x3_s2, x, col, pad_lo=0)
-                arena.release(x)
                 y = arena.alloc((B, oh, ow, co))
                 wd_, bd_ = P[f"encoder.down_blocks.{i}.downsamplers.0.conv"]
-                add(ops.gemm, col, wd_, y.view(B * oh * ow, co), bias=bd_)
-                arena.release(col)
+                # F.pad(x, (0, 1, 0, 1)) + Conv2d(3x3, stride 2, padding 0): the A map steps by two pixels and its
+                # out-of-range row / column reads as zero (at 384x1248 the im2col buffer of the first one was 2.2 GB)
+                add(ops.gemm, x, wd_, y, taps=9, bias=bd_, a_stride=2, a_pad=0)
+                arena.release(x)
                 x, h, w = y, oh, ow
 
         y = resnet("encoder.mid_block.resnets.0", x, h, w)
