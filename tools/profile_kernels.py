@@ -75,6 +75,30 @@ def cases():
                                   2 * 2 * B * h * w * 960)
     out["conv3x3_960to320_L0"] = (lambda: ops.gemm(t0, wc, oc, taps=9, bias=bc), 2 * B * h * w * 320 * 9 * 960,
                                   2 * (B * h * w * 1280 + 9 * 960 * 320))
+    # Upsample2D (nearest x2 + conv3x3) as four sub-pixel 2x2 convolutions, against the gather pass + 3x3 convolution
+    # it replaces; Downsample2D (conv3x3 stride 2) through the element-strided A map (ldm_gemm_desc.up2 / a_stride)
+    for name, (hl, wl, Cu) in {"L2toL1": (12, 39, 1280), "L1toL0": (24, 78, 640)}.items():
+        xl = rn((B, hl, wl, Cu))
+        w9 = torch.randn((Cu, 3, 3, Cu), device=DEV) * 0.02
+        bu = rn((Cu,), f32)
+        w4, b4 = ops.fold_upsample_conv3x3(w9, bu)
+        oh_ = rn((B, 2 * hl, 2 * wl, Cu))
+        upb = rn((B, 2 * hl, 2 * wl, Cu))
+        w9p = w9.reshape(Cu, 9 * Cu).to(bf16).contiguous()
+        Ml = B * hl * wl
+        out[f"upconv_subpixel_{name}"] = (lambda xl=xl, w4=w4, b4=b4, oh_=oh_: ops.gemm(xl, w4, oh_, taps=4, bias=b4, up2=True),
+                                          2 * Ml * 4 * Cu * 4 * Cu, 2 * (5 * Ml * Cu + 16 * Cu * Cu))
+        out[f"upconv_gather_{name}"] = (lambda xl=xl, upb=upb, w9p=w9p, bu=bu, oh_=oh_: (ops.upsample_nearest(xl, upb),
+                                                                                     ops.gemm(upb, w9p, oh_, taps=9, bias=bu)),
+                                        2 * 4 * Ml * Cu * 9 * Cu, 2 * (13 * Ml * Cu + 9 * Cu * Cu))
+    hd, wd2, Cd = LEVELS["L0"]
+    xd = rn((B, hd, wd2, Cd))
+    wdn, bdn, od = rn((Cd, 9 * Cd), scale=0.02), rn((Cd,), f32), rn((B, hd // 2, wd2 // 2, Cd))
+    cold = rn((B * (hd // 2) * (wd2 // 2), 9 * Cd))
+    out["downconv_strided_L0toL1"] = (lambda: ops.gemm(xd, wdn, od, taps=9, bias=bdn, a_stride=2, a_pad=1),
+                                      2 * od.numel() * 9 * Cd, 2 * (xd.numel() + od.numel() + wdn.numel()))
+    out["downconv_im2col_L0toL1"] = (lambda: (ops.im2col3x3_s2(xd, cold), ops.gemm(cold, wdn, od.view(-1, Cd), bias=bdn)),
+                                     2 * od.numel() * 9 * Cd, 2 * (xd.numel() + 2 * cold.numel() + od.numel() + wdn.numel()))
     # HBM-bound tail / scheduler kernels at full size (8 frames of 384x1248)
     H, W, Cc = 192, 624, 128
     lo = torch.randn((B, H, W, Cc), device=DEV)
