@@ -592,14 +592,18 @@ class UNet:
         return st
 
     def profile_plan(self, st, iters=3):
-        """Per-launch device time of one forward, measured with CUDA events on the launching stream (eager, not the
-        graph). Returns a list of dicts {op, ms, flops, bytes} in program order; `flops` are algorithmic (2*M*N*K for
+        """Per-launch device time of one forward, measured with CUDA events on the launching stream (eager launches
+        queued behind a spin kernel, so that host launch time does not leak into the intervals). Returns a list of dicts {op, ms, flops, bytes} in program order; `flops` are algorithmic (2*M*N*K for
         the contraction kernel, 4*B*heads*seq^2*d for attention), `bytes` the minimal operand traffic."""
         stream = torch.cuda.current_stream()
         n = len(st.plan)
         acc = [0.0] * n
         for it in range(iters + 1):
             evs = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+            # The host needs 10 - 20 us per launch through ctypes, most kernels of the small levels less: with an idle
+            # GPU the interval between two events is the HOST's time per launch. A spin kernel in front lets the host
+            # queue the whole forward first, so the events bracket back-to-back device time as in the graph replay.
+            torch.cuda._sleep(int(6e4) * n)
             evs[0].record(stream)
             for i, (fn, a, k) in enumerate(st.plan):
                 fn(*a, **k)
