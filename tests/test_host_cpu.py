@@ -378,3 +378,49 @@ def test_output_dict_types_keep_items_and_attributes_in_sync():
     v = VAEOutput(sample=t, posterior=None)
     assert v.sample is t and v["posterior"] is None
     assert RangeDict(min=t.min(), max=t.max()).max == 2.0
+
+
+def test_fold_upsample_conv3x3_algebra():
+    """ops.fold_upsample_conv3x3 (ldm_gemm_desc.up2): the four 2x2 sub-pixel kernels reproduce
+    F.interpolate(scale 2, nearest) + Conv2d(3x3, padding 1) exactly (fp32 weights; the packed ones are bf16)."""
+    import torch.nn.functional as F
+    from video_latent_diffusion_panoptic_segmentation_b200 import ops
+    torch.manual_seed(3)
+    H, W, C, N = 5, 7, 8, 6
+    x, w, b = torch.randn(2, C, H, W), torch.randn(N, C, 3, 3), torch.randn(N)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), w, b, padding=1)
+    w4, b4 = ops.fold_upsample_conv3x3(w.permute(0, 2, 3, 1).contiguous(), b)
+    assert w4.shape == (4 * N, 4 * C) and w4.dtype == torch.bfloat16 and torch.equal(b4, b.repeat(4))
+    # the same sums in fp32 (the bf16 rounding of the packed weights is covered by the GPU check)
+    wf = w.permute(0, 2, 3, 1)
+    rows = {0: ([0], [1, 2]), 1: ([0, 1], [2])}
+    xp = F.pad(x, (1, 1, 1, 1))
+    out = torch.zeros(2, N, 2 * H, 2 * W)
+    for a in (0, 1):
+        for bb in (0, 1):
+            k = torch.stack([sum(wf[:, ky, kx] for ky in rows[a][i] for kx in rows[bb][j])
+                             for i in (0, 1) for j in (0, 1)], dim=1).reshape(N, 2, 2, C).permute(0, 3, 1, 2)
+            cls = 2 * a + bb
+            assert torch.allclose(w4[cls * N:(cls + 1) * N].float().reshape(N, 2, 2, C).permute(0, 3, 1, 2), k,
+                                  atol=2e-2, rtol=1e-2)   # bf16 rounding of the packed class weights
+            # tap (i, j) reads input (y + i - 1 + a, x + j - 1 + b): rows a .. a + H of the zero-padded input
+            out[:, :, a::2, bb::2] = F.conv2d(xp[:, :, a:a + H + 1, bb:bb + W + 1], k, b)
+    assert torch.allclose(out, ref, atol=1e-4, rtol=1e-4)
+
+
+def test_fold_layernorm_algebra():
+    """ops.fold_layernorm (ldm_gemm_desc.ln_stats): rstd (x W'^T - mean g) + b' == LayerNorm(x) W^T + b."""
+    import torch.nn.functional as F
+    from video_latent_diffusion_panoptic_segmentation_b200 import ops
+    torch.manual_seed(4)
+    M, C, N = 12, 64, 24
+    x = torch.randn(M, C) * 2 + 0.7
+    w, b = torch.randn(N, C) * 0.1, torch.randn(N)
+    gamma, beta = torch.rand(C) + 0.5, torch.randn(C) * 0.2
+    ref = F.layer_norm(x, (C,), gamma, beta, 1e-5) @ w.t() + b
+    w2, b2, g = ops.fold_layernorm(w, b, gamma, beta)
+    mean, var = x.mean(-1, keepdim=True), x.var(-1, unbiased=False, keepdim=True)
+    rstd = (var + 1e-5).rsqrt()
+    got = rstd * (x @ w2.float().t() - mean * g[None, :]) + b2[None, :]
+    assert torch.allclose(got, ref, atol=3e-2, rtol=2e-2)   # w2 is rounded to bf16; g is the row sum of the ROUNDED w2
+    assert torch.equal(g, w2.float().sum(1))
