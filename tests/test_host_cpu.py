@@ -424,3 +424,21 @@ def test_fold_layernorm_algebra():
     got = rstd * (x @ w2.float().t() - mean * g[None, :]) + b2[None, :]
     assert torch.allclose(got, ref, atol=3e-2, rtol=2e-2)   # w2 is rounded to bf16; g is the row sum of the ROUNDED w2
     assert torch.equal(g, w2.float().sum(1))
+
+
+def test_color_map_and_encode_seg_match_reference():
+    """ldmseg/utils/utils.py:240-258 and trainers_ldm_cond.py:326-334 (what decode_latents returns without
+    return_logits), against arrays of the real reference functions (tests/golden/make_golden_color_map.py)."""
+    from video_latent_diffusion_panoptic_segmentation_b200.ldmseg.trainers import TrainerDiffusion
+    from video_latent_diffusion_panoptic_segmentation_b200.ldmseg.utils import color_map
+    z = np.load(os.path.join(G, "color_map.npz"))
+    cm = color_map()
+    assert cm.dtype == np.uint8 and np.array_equal(cm, z["cmap"])
+    assert cm[:4].tolist() == [[0, 0, 0], [128, 0, 0], [0, 128, 0], [128, 128, 0]]   # the published PASCAL palette
+    cn = color_map(normalized=True)
+    assert cn.dtype == z["cmap_norm"].dtype and np.array_equal(cn, z["cmap_norm"])
+    assert np.array_equal(color_map(N=19), z["cmap_19"])
+    got = TrainerDiffusion.encode_seg(type("T", (), {"cmap": None})(), z["labels"])
+    assert got.dtype == z["colours"].dtype and np.array_equal(got, z["colours"])
+    two = np.stack([np.arange(256), np.arange(256)[::-1]], 1).astype(np.float32)     # a caller's own palette
+    assert np.array_equal(TrainerDiffusion.encode_seg(None, z["labels"], cmap=two), two[z["labels"].astype(np.uint8)])

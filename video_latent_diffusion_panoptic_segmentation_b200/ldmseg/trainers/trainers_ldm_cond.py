@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from ..evaluations.cityscapes_pap_eval import CityscapesPanopticEvaluator
-from ..utils import get_world_size, is_dist_avail_and_initialized, is_main_process
+from ..utils import color_map, get_world_size, is_dist_avail_and_initialized, is_main_process
 from ... import _lib as L
 from ... import ops
 
@@ -43,6 +43,7 @@ class TrainerDiffusion:
         self.self_condition = bool(tk.get("self_condition", False))
         self.ignore_label = p.get("ignore_label", 127)
         self.num_classes = p.get("num_classes", 128)
+        self.cmap = color_map()   # :173, the palette decode_latents / encode_seg paint label maps with
         self.fp16_scaler = None
         self.weight_dtype = weight_dtype
         self.unet_dtype = torch.float32
@@ -237,7 +238,18 @@ class TrainerDiffusion:
         counts = torch.empty((B, 2, C), dtype=i32, device=logits.device)
         ops.logits_to_ids(logits, ids, counts, up=up, mask_th=self.mask_th if threshold_output else -1.0,
                           ignore_label=self.ignore_label)
-        return ids.cpu().numpy()
+        # :435-436: the label map leaves as a colour image, uint8 [B, H, W, 3]
+        return self.encode_seg(ids.cpu().numpy()).astype(np.uint8)
+
+    def encode_seg(self, semseg, cmap=None):
+        """trainers_ldm_cond.py:326-334: labels [B, H, W] (taken modulo 256, as the reference's astype(uint8) does) ->
+        the palette colour of every pixel, [B, H, W, cmap.shape[1]] in the palette's dtype. One gather instead of the
+        reference's loop over the labels present."""
+        if cmap is None:
+            if getattr(self, "cmap", None) is None:
+                self.cmap = color_map()
+            cmap = self.cmap
+        return cmap[np.asarray(semseg).astype(np.uint8)]
 
     @torch.no_grad()
     def panoptic_ids(self, latents):

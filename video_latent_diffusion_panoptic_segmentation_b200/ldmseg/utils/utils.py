@@ -1,7 +1,9 @@
 """Host-side helpers the sampler path uses from ldmseg/utils/utils.py: OutputDict (:26-31), rank helpers (:44-67),
-gpu_gather (:76-81). Training meters / LR schedules / visualisers are out of scope."""
+gpu_gather (:76-81), color_map (:240-258). Training meters / LR schedules / visualisers are out of scope (SURVEY.md
+section 2 row 9)."""
 from collections import OrderedDict
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -39,3 +41,16 @@ def gpu_gather(tensor: torch.Tensor) -> torch.Tensor:
     outs = [torch.empty_like(tensor) for _ in range(dist.get_world_size())]
     dist.all_gather(outs, tensor.contiguous())
     return torch.cat(outs, dim=0)
+
+
+def color_map(N: int = 256, normalized: bool = False) -> np.ndarray:
+    """The PASCAL VOC label palette of ldmseg/utils/utils.py:240-258, [N, 3] uint8 (float32 in [0, 1] if normalized):
+    bit 3j + k of the label index becomes bit 7 - j of channel k (k = 0, 1, 2 for r, g, b). All labels at once."""
+    idx = np.arange(N, dtype=np.int64)
+    cmap = np.zeros((N, 3), dtype=np.int64)
+    for j in range(8):
+        for k in range(3):
+            cmap[:, k] |= ((idx >> (3 * j + k)) & 1) << (7 - j)
+    if normalized:
+        return (cmap.astype("float32") / 255).astype("float32")
+    return cmap.astype("uint8")
