@@ -442,3 +442,30 @@ def test_color_map_and_encode_seg_match_reference():
     assert got.dtype == z["colours"].dtype and np.array_equal(got, z["colours"])
     two = np.stack([np.arange(256), np.arange(256)[::-1]], 1).astype(np.float32)     # a caller's own palette
     assert np.array_equal(TrainerDiffusion.encode_seg(None, z["labels"], cmap=two), two[z["labels"].astype(np.uint8)])
+
+
+def test_load_unet_checkpoint_keeps_descriptor_mode_additions():
+    """tools/main_ldm.py load_path branch: a checkpoint without object queries must not silently drop the ones
+    define_learnable_embeddings added; one that carries them wins; 'remove' drops attn2 / norm2 again."""
+    from video_latent_diffusion_panoptic_segmentation_b200.tools.main_ldm import load_unet_checkpoint
+    cfg = dict(block_out_channels=(64, 128, 256, 256), cross_attention_dim=768)
+    torch.manual_seed(1)
+    sd = {k: v.clone() for k, v in UO.UNetOracle(**cfg).state_dict().items()}
+    assert any(".attn2." in k for k in sd)
+    m = UNet(device="cpu", **cfg)
+    m.load_state_dict(sd)
+    m.define_learnable_embeddings(16, 768)
+    q0 = m.state_dict()["object_queries.weight"].clone()
+    ckpt = {"module." + k: v + 1.0 for k, v in sd.items()}          # DDP-prefixed, different weights, no queries
+    load_unet_checkpoint(m, ckpt, "learnable")
+    got = m.state_dict()
+    assert torch.equal(got["object_queries.weight"], q0) and m.has_cross_attention()
+    assert torch.equal(got["conv_in.weight"], sd["conv_in.weight"] + 1.0)
+    ckpt["module.object_queries.weight"] = torch.full_like(q0, 3.0)  # a checkpoint trained in that mode carries its own
+    load_unet_checkpoint(m, ckpt, "learnable")
+    assert torch.equal(m.state_dict()["object_queries.weight"], torch.full_like(q0, 3.0))
+    m2 = UNet(device="cpu", **cfg)
+    m2.load_state_dict(sd)
+    m2.remove_cross_attention()
+    load_unet_checkpoint(m2, {k: v for k, v in ckpt.items() if "object_queries" not in k}, "remove")
+    assert not m2.has_cross_attention() and not any(".attn2." in k for k in m2.state_dict())

@@ -173,6 +173,22 @@ def fit_trained_like_head(trainer, latent_hw, num_inference_steps, seed=42, data
     return lat
 
 
+def load_unet_checkpoint(unet, state_dict, image_descriptors="remove"):
+    """main_ldm.py:205-214: the checkpoint's UNet weights replace the freshly built ones. UNet.load_state_dict swaps the
+    whole state dict, so what the constructor path ADDED for the descriptor mode (descriptors.py:89-95) is re-applied:
+    'remove' drops attn2 / norm2 again; 'learnable' keeps the object queries / encoder_hid_proj defined before the load
+    when the checkpoint does not carry its own (a checkpoint trained in that mode does, and then wins)."""
+    added = {k: v for k, v in unet.state_dict().items()
+             if k.startswith(("object_queries.", "encoder_hid_proj."))} if image_descriptors == "learnable" else {}
+    sd = {k.replace("module.", ""): v for k, v in state_dict.items()}
+    for k, v in added.items():
+        sd.setdefault(k, v)
+    unet.load_state_dict(sd)
+    if image_descriptors == "remove":
+        unet.remove_cross_attention()
+    return unet
+
+
 def build_vae_image(p, device, seed=0):
     """main_ldm.py:138-140: the RGB VAE (decoder dropped); random-init SD-1.4 VAE encoder without a checkpoint."""
     vim = GeneralVAEImage.from_pretrained(state_dict=unet_init.random_vae_image_state_dict(seed=seed + 3), device=device)
@@ -234,9 +250,7 @@ def main_worker(gpu, ngpus_per_node, cfg_dist, p, name="b200"):
                                args={"gpu": gpu})
     if p.get("load_path"):
         data = torch.load(p["load_path"], map_location="cpu")
-        unet.load_state_dict(data["unet"])
-        if p["train_kwargs"].get("image_descriptors", "remove") == "remove":
-            unet.remove_cross_attention()
+        load_unet_checkpoint(unet, data["unet"], p["train_kwargs"].get("image_descriptors", "remove"))
         if "vae_image" in data and vae_image is not None:
             vae_image.load_state_dict(data["vae_image"])
         if "vae_semseg" in data:
